@@ -1,0 +1,154 @@
+/*
+ * mp3stego_b200.h -- C ABI of libmp3stego_b200.so, the B200 (sm_100a) implementation of the
+ * per-granule codec hot path of mp3stego (tomershay100/mp3-steganography-lib 1.1.8).
+ *
+ * The reference has no FFI of its own: the hot path sits behind two Python methods,
+ *   MP3Parser.parse_file()   mp3stego/decoder/MP3_Parser.py:57-85   (MP3 -> PCM + reveal bits)
+ *   MP3Encoder.encode()      mp3stego/encoder/MP3_Encoder.py:596-621 (PCM -> MP3, optional hide)
+ * and this header declares exactly what those two methods would bind (ctypes).
+ * Everything is plain C: pointers + sizes, int status returns, no exceptions, no torch types.
+ *
+ * Conventions
+ *   - Every call returns M3S_OK (0) or a negative M3S_ERR_*; m3s_last_error() gives the text.
+ *   - `mem` arguments say where the caller's bulk buffers live: M3S_MEM_HOST (pageable or pinned host
+ *     memory; the library stages through the device inside the call) or M3S_MEM_DEVICE (device
+ *     pointers, e.g. torch tensors' data_ptr(); nothing crosses PCIe).
+ *     Small per-file descriptor arrays (offsets, counts, status) are ALWAYS host memory.
+ *   - A handle owns one CUDA stream (or borrows one via m3s_set_stream) and grow-only device
+ *     workspaces; calls on one handle are serialised and block until their results are readable,
+ *     except where a function says it is asynchronous.  Handles are not thread-safe.
+ *   - Supported streams: MPEG-1 Layer III, 32/44.1/48 kHz, mono or stereo, CBR or VBR, with or
+ *     without CRC -- the domain in which the reference itself works (FrameHeader.py:125-143).
+ */
+#ifndef MP3STEGO_B200_H
+#define MP3STEGO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define M3S_API __attribute__((visibility("default")))
+#else
+#define M3S_API
+#endif
+
+typedef struct m3s_ctx *m3s_handle_t;
+
+enum {
+    M3S_OK = 0,
+    M3S_ERR_CUDA = -1,        /* a CUDA runtime call or kernel failed */
+    M3S_ERR_ARG = -2,         /* bad argument */
+    M3S_ERR_STATE = -3,       /* call order violated (e.g. decode_run without decode_scan) */
+    M3S_ERR_NO_DEVICE = -4,   /* no CUDA device / not an sm_100 part */
+    M3S_ERR_CAPACITY = -5     /* output buffer too small */
+};
+
+enum { M3S_MEM_HOST = 0, M3S_MEM_DEVICE = 1 };
+
+/* per-file status written by m3s_decode_scan (mirrors where MP3Parser stops or raises) */
+enum {
+    M3S_FILE_OK = 0,
+    M3S_FILE_NO_SYNC = 1,        /* first audio bytes are not 0xFF 0xEx: MP3Parser.__valid False (MP3_Parser.py:36-44) */
+    M3S_FILE_UNSUPPORTED = 2,    /* a frame header outside MPEG-1 Layer III / reserved sample rate or bitrate index 15 */
+    M3S_FILE_TRAILING_JUNK = 4   /* parsing stopped at a bad sync word; the last frame's PCM is repeated once (MP3_Parser.py:68-79) */
+};
+
+/* flags for m3s_decode_run */
+enum {
+    M3S_DEC_PCM_FLOAT = 1        /* pcm buffer is float32 (pre-int16 samples) instead of int16 */
+};
+
+/* ---------------------------------------------------------------- lifetime */
+M3S_API int m3s_create(int device, m3s_handle_t *out);
+M3S_API int m3s_destroy(m3s_handle_t h);
+M3S_API const char *m3s_last_error(m3s_handle_t h);
+/* Borrow a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the handle's own. */
+M3S_API int m3s_set_stream(m3s_handle_t h, void *cuda_stream);
+/* Block until everything queued on the handle's stream has finished. */
+M3S_API int m3s_synchronize(m3s_handle_t h);
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+M3S_API int64_t m3s_launch_count(m3s_handle_t h);
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+M3S_API int m3s_version(void);
+
+/* ------------------------------------------------------------------ decode
+ * Replaces MP3Parser.__init__ + the frame walk of MP3Parser.parse_file (MP3_Parser.py:21-85),
+ * FrameHeader.init_header_params (FrameHeader.py:51-192), Frame.set_frame_size (Frame.py:288-316),
+ * FrameSideInformation.set_side_info (FrameSideInformation.py:39-137) and the reveal-bit rule
+ * Frame.__get_frame_huffman_tables + util.bit_from_huffman_tables (Frame.py:676-685, util.py:67-81)
+ * for a BATCH of files laid end to end in `bytes`.
+ *
+ *   bytes        all files concatenated (host or device per `mem`)
+ *   file_off     [n_files+1] host: byte offset of each file in `bytes`; file i = [file_off[i], file_off[i+1])
+ *   audio_start  [n_files] host or NULL: offset of the first audio byte inside each file (ID3v2 skip,
+ *                decoder.py:29-33); NULL = 0 for every file
+ * outputs (host arrays of n_files entries, any may be NULL):
+ *   n_frames     frames parsed                      (parse_file's return value)
+ *   pcm_rows     PCM rows the file decodes to = 1152 * (n_frames + 1 if trailing junk)
+ *   sample_rate, channels, bitrate_bps   of the LAST frame, as MP3Parser.get_bitrate / Frame.sampling_rate report
+ *   status       M3S_FILE_* bits
+ * The scan result stays in the handle for m3s_decode_reveal / m3s_decode_run.
+ */
+M3S_API int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, const int64_t *file_off,
+                            const int64_t *audio_start, int32_t n_files, int64_t *n_frames, int64_t *pcm_rows,
+                            int32_t *sample_rate, int32_t *channels, int32_t *bitrate_bps, int32_t *status);
+
+/* Reveal outputs of the last scan (the `reveal` half of decode+reveal; needs no Huffman decode).
+ *   table_ids    [total_frames*12] per frame the 12 table ids in (ch, gr, region) order incl. the stale
+ *                region-2 id of window-switched granules (Frame.py:676-685); mono frames fill 6. May be NULL.
+ *   reveal_bits  ['0'/'1' chars] file i's string starts at 12 * (sum of n_frames of files < i); May be NULL.
+ *   reveal_len   [n_files] host: number of chars of each file's string (MP3Parser.output_bits). */
+M3S_API int m3s_decode_reveal(m3s_handle_t h, uint8_t *table_ids, uint8_t *reveal_bits, int mem, int64_t *reveal_len);
+
+/* Huffman decode -> requantize -> stereo -> reorder/alias -> IMDCT/overlap -> polyphase synthesis of the
+ * last scanned batch: Frame.init_frame_params (Frame.py:244-286) for every frame, then
+ * MP3Parser.write_to_wav's float->int16 conversion (MP3_Parser.py:87-91).
+ *   pcm       interleaved samples, file i at element offset pcm_off[i]; rows*channels elements per file
+ *   pcm_off   [n_files] host element offsets, or NULL for back-to-back
+ *   spectra   optional parity tap (device or host per mem): int16 [total_frames][gr][ch][576] integer spectra
+ *             as Frame.__unpack_samples leaves them (Frame.py:443-559); NULL to skip */
+M3S_API int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t *pcm_off, int16_t *spectra,
+                           uint32_t flags);
+
+/* ------------------------------------------------------------------ encode
+ * Replaces MP3Encoder.__init__ + MP3Encoder.encode (MP3_Encoder.py:462-650): analysis filterbank + MDCT
+ * (:652-758), rate loop with the stego table swap (:760-1264) and bitstream formatting (:1266-1552),
+ * for a BATCH of 16-bit stereo clips.
+ *   pcm           interleaved int16 stereo, clip i at element offset pcm_off[i], 2*n_samples[i] elements
+ *   n_samples     [n_clips] host: samples per channel; must be a multiple of 1152 (the reference raises otherwise)
+ *   payload_bits  '0'/'1' chars of all payloads concatenated (host), clip i = [payload_off[i], payload_off[i+1]);
+ *                 NULL or empty range = plain encode (no swap)
+ *   mp3_out       output bytes, clip i at mp3_off[i]; capacity mp3_cap[i] >= m3s_encode_bound()
+ *   out_len       [n_clips] host: bytes written (a multiple of 4, MP3_Encoder.py:1370-1392,1549-1552)
+ *   hide_str_offset_out  [n_clips] host: MP3Encoder.hide_str_offset after the last frame
+ */
+M3S_API int64_t m3s_encode_bound(int64_t n_samples, int32_t sample_rate, int32_t bitrate_kbps);
+M3S_API int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int64_t *pcm_off, const int64_t *n_samples,
+                       int32_t n_clips, int32_t sample_rate, int32_t bitrate_kbps, const uint8_t *payload_bits,
+                       const int64_t *payload_off, uint8_t *mp3_out, const int64_t *mp3_off, const int64_t *mp3_cap,
+                       int64_t *out_len, int64_t *hide_str_offset_out);
+/* Parity taps of the last m3s_encode call (host buffers): mdct int32 [frames][ch][gr][576] (MP3_Encoder.py:652),
+ * ix int32 [frames][ch][gr][576] signed as written (:1272-1276), info int32 [frames][gr][ch][16]:
+ * part2_3_length, big_values, count1, global_gain, table_select[3], region0_count, region1_count,
+ * count1table_select, address1..3, quantizerStepSize, padding, hide_str_offset-after-frame. */
+M3S_API int m3s_encode_taps(m3s_handle_t h, int32_t *mdct, int32_t *ix, int32_t *info, int32_t *scfsi);
+
+/* ------------------------------------------------------------- diagnostics */
+/* sha-free table export used by tests/test_tables.py: copies table `which` (see m3s_table_id) into out. */
+enum {
+    M3S_TAB_HUFF_PACKED = 0, M3S_TAB_HUFF_BOOK_OFF, M3S_TAB_HUFF_DIM, M3S_TAB_HUFF_LINBITS, M3S_TAB_SFB_LONG,
+    M3S_TAB_SFB_SHORT, M3S_TAB_SFW_SHORT, M3S_TAB_SLEN, M3S_TAB_PRETAB, M3S_TAB_SYNTH_WINDOW, M3S_TAB_ENWINDOW,
+    M3S_TAB_ENC_FL, M3S_TAB_ENC_COSL, M3S_TAB_ENC_STEPTABI, M3S_TAB_ENC_STEPTAB, M3S_TAB_ENC_INT2IDX,
+    M3S_TAB_ENC_CA, M3S_TAB_ENC_CS, M3S_TAB_SUBDV, M3S_TAB_STEGO_PAIR, M3S_TAB_ALIAS_CS, M3S_TAB_ALIAS_CA,
+    M3S_TAB_H0_MASK, M3S_TAB_COUNT
+};
+/* Returns the element count (or <0); if out != NULL copies min(count, cap) elements widened to double. */
+M3S_API int64_t m3s_table_export(int which, double *out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP3STEGO_B200_H */

@@ -1,0 +1,185 @@
+// m3s_common.cuh -- shared declarations of libmp3stego_b200 (host context, device record layouts).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mp3stego_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// device-side record layouts (HBM-resident, SoA across frames; see DESIGN.md "Data layout")
+// ------------------------------------------------------------------------------------------------
+
+// One per input file, built on the host after the frame walk.
+struct M3sFileRec {
+    int64_t begin;        // first byte of the file in the batch buffer
+    int64_t end;          // one past the last byte
+    int64_t audio;        // first audio byte (after ID3v2)
+    int64_t frame_base;   // global index of the file's first frame
+    int64_t s_base;       // byte offset of the file's header-stripped main-data stream in S
+    int64_t pcm_base;     // element offset of the file's PCM in the output buffer
+    int32_t n_frames;
+    int32_t flags;        // M3S_FILE_* bits
+    int32_t channels;
+    int32_t pad;
+};
+
+// Written by the walk kernel, one per file.
+struct M3sFileOut {
+    int64_t payload_total;  // bytes of main data (sum of frame payloads)
+    int32_t n_frames;
+    int32_t status;         // M3S_FILE_* bits
+    int32_t sample_rate;
+    int32_t channels;
+    int32_t bitrate;
+    int32_t reveal_len;
+};
+
+// frame meta word (fr_meta)
+#define M3S_META_PAYLOAD_MASK 0x7FFu      // [0:11)  payload bytes present in the file (frame_size - header - side info - crc, clipped)
+#define M3S_META_CRC (1u << 11)           // CRC word present (protection bit 0)
+#define M3S_META_MODE_SHIFT 12            // [12:14) channel mode
+#define M3S_META_MS (1u << 14)            // joint stereo with mode_extension bit 0x20 (Frame.py:273)
+#define M3S_META_SR_SHIFT 15              // [15:17) sampling_frequency index
+#define M3S_META_MONO (1u << 17)
+#define M3S_META_FIRST (1u << 18)         // first frame of its file
+#define M3S_META_DUP (1u << 19)           // last frame of a file that ends in junk: its PCM is emitted twice
+#define M3S_META_HDR_SHIFT 20             // [20:26) header + crc + side-info bytes (36/38/21/23)
+
+// One per granule-channel ("unit"), 4 slots per frame: slot = 2*gr + ch.
+struct __align__(16) M3sUnitRec {
+    uint64_t bit_start;   // absolute bit position in S where part2 (scalefactors) starts
+    int32_t limit_bits;   // bits readable from bit_start before the frame's assembled main data ends (may be <= 0)
+    uint32_t a;           // part2_3_length[0:12) big_values[12:21) global_gain[21:29) window_switching[29] block_type[30:32)
+    uint32_t b;           // scalefac_compress[0:4) mixed[4] table_select0[5:10) 1[10:15) 2[15:20) region0[20:24) region1[24:27)
+                          // preflag[27] scalefac_scale[28] count1table[29] ms[30] mono[31]
+    uint32_t c;           // subblock_gain0[0:3) 1[3:6) 2[6:9) scfsi[9:13) sr_idx[13:15) gr[15] ch[16] valid[17] first_frame[18]
+    uint32_t frame;       // global frame index
+    uint32_t pad;
+};
+
+#define M3S_UA_P23(a) ((a) & 0xFFFu)
+#define M3S_UA_BV(a) (((a) >> 12) & 0x1FFu)
+#define M3S_UA_GG(a) (((a) >> 21) & 0xFFu)
+#define M3S_UA_WS(a) (((a) >> 29) & 1u)
+#define M3S_UA_BT(a) (((a) >> 30) & 3u)
+#define M3S_UB_SFC(b) ((b) & 0xFu)
+#define M3S_UB_MIXED(b) (((b) >> 4) & 1u)
+#define M3S_UB_TS(b, r) (((b) >> (5 + 5 * (r))) & 0x1Fu)
+#define M3S_UB_R0(b) (((b) >> 20) & 0xFu)
+#define M3S_UB_R1(b) (((b) >> 24) & 0x7u)
+#define M3S_UB_PREFLAG(b) (((b) >> 27) & 1u)
+#define M3S_UB_SFSCALE(b) (((b) >> 28) & 1u)
+#define M3S_UB_C1SEL(b) (((b) >> 29) & 1u)
+#define M3S_UB_MS(b) (((b) >> 30) & 1u)
+#define M3S_UB_MONO(b) (((b) >> 31) & 1u)
+#define M3S_UC_SBG(c, w) (((c) >> (3 * (w))) & 7u)
+#define M3S_UC_SCFSI(c) (((c) >> 9) & 0xFu)
+#define M3S_UC_SR(c) (((c) >> 13) & 3u)
+#define M3S_UC_GR(c) (((c) >> 15) & 1u)
+#define M3S_UC_CH(c) (((c) >> 16) & 1u)
+#define M3S_UC_VALID(c) (((c) >> 17) & 1u)
+#define M3S_UC_FIRST(c) (((c) >> 18) & 1u)
+
+// scalefactor bytes per unit: long [0..21], short [22 + 13*win + sfb]
+#define M3S_SF_STRIDE 64
+#define M3S_SF_SHORT 22
+
+// Huffman decode LUT (built on the host at m3s_create, see m3s_context.cu):
+//   entry uint16: leaf      0 | len[8:13) | x[4:8) | y[0:4)
+//                 internal  0x8000 | nbits[11:15) | (sub offset >> 1)[0:11)
+//   per table id: desc = l1_base[0:13) | l1_bits[13:17) | linbits[17:21);  sub = absolute index of the book's sub-table area
+#define M3S_HUFF_L1_BITS 8
+struct M3sDevTables {
+    uint16_t huff_lut[8192];
+    uint32_t huff_desc[32];
+    uint32_t huff_sub[32];
+    uint8_t count1_lut[64];      // table A: len[4:8) | v w x y [0:4)
+    uint16_t sfb_long[3][23];
+    uint16_t sfb_short[3][14];
+    uint8_t sfw_short[3][12];
+    uint8_t slen[16][2];
+    uint8_t pretab[22];
+    uint8_t long_sfb_of[3][576];   // sample index -> long sfb
+    uint8_t short_sfw_of[3][576];  // sample index (pre-reorder) -> sfb*3 + window
+    uint16_t reorder_dst[3][576];  // short-block reorder: source index -> destination index (Frame.py:574-602)
+    float pow43[256];              // |x|^(4/3) for small |x| (double-rounded)
+    float quarter[4];              // 2^(0/4) .. 2^(3/4)
+    float imdct_cos36[36][18];
+    float imdct_cos12[12][8];      // padded rows
+    float sine_block[4][36];
+    float synth_n[64][32];
+    float synth_d[512];
+    float alias_cs[8], alias_ca[8];
+    // encoder
+    int32_t enwindow[512];
+    int32_t enc_fl[32][64];
+    int32_t enc_cosl[18][36];
+    int32_t enc_ca[8], enc_cs[8];
+    int32_t steptabi[128];
+    double steptab[128];
+    int32_t int2idx[10000];
+    uint8_t subdv[23][2];
+    uint8_t pair[32][2];
+    uint32_t enc_hpacked[1410];    // (code << 8) | len
+    uint16_t enc_hoff[34];
+    uint8_t enc_hdim[34];
+    uint8_t enc_linbits[34];
+    uint16_t enc_linmax[34];
+};
+
+// ------------------------------------------------------------------------------------------------
+// host context
+// ------------------------------------------------------------------------------------------------
+struct M3sBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct m3s_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    M3sDevTables *d_tab = nullptr;
+    int sm_count = 148;
+
+    // ---- decode state (valid between m3s_decode_scan and the next scan)
+    bool scanned = false;
+    int32_t n_files = 0;
+    int64_t total_frames = 0;
+    int64_t s_bytes = 0;
+    const uint8_t *d_bytes = nullptr;  // device pointer to the batch bytes (caller's or staged)
+    std::vector<M3sFileRec> files;
+    std::vector<M3sFileOut> fouts;
+    M3sBuf b_stage_in, b_files, b_fouts, b_fr_pos, b_fr_P, b_fr_meta, b_fr_carry, b_fr_reveal, b_fr_file;
+    M3sBuf b_units, b_sf, b_S, b_spec, b_tabids, b_reveal, b_work, b_pcm_stage, b_spec_export;
+    // ---- encode state
+    M3sBuf e_pcm, e_clips, e_mdct, e_ix, e_info, e_gran, e_out, e_payload, e_misc, e_pad;
+    int64_t enc_total_frames = 0;
+    int32_t enc_n_clips = 0;
+    std::vector<int64_t> enc_frame_base;
+};
+
+int m3s_fail(m3s_ctx *h, int code, const char *fmt, ...);
+int m3s_buf_reserve(m3s_ctx *h, M3sBuf &b, size_t bytes);
+
+#define M3S_CUDA(h, call)                                                                             \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return m3s_fail((h), M3S_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                      \
+    } while (0)
+
+#define M3S_LAUNCH_CHECK(h)                                                                           \
+    do {                                                                                              \
+        (h)->launches++;                                                                              \
+        cudaError_t e__ = cudaGetLastError();                                                         \
+        if (e__ != cudaSuccess)                                                                       \
+            return m3s_fail((h), M3S_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                      \
+    } while (0)

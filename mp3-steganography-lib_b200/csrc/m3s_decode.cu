@@ -1,0 +1,985 @@
+// m3s_decode.cu -- decode half of the hot path: D0 frame walk + side-info scan (+ reveal bits),
+// main-data compaction, D1 Huffman/scalefactor decode, D2+D3 fused requantize -> stereo -> reorder/alias ->
+// IMDCT/overlap -> polyphase synthesis -> int16.   Reference: mp3stego/decoder/{MP3_Parser,Frame,
+// FrameHeader,FrameSideInformation,util}.py (cited per kernel below).
+#include <string.h>
+
+#include <algorithm>
+
+#include "m3s_common.cuh"
+#include "m3s_tables_data.h"
+
+// ================================================================================================
+// small device helpers
+// ================================================================================================
+__device__ __forceinline__ uint32_t ldb(const uint8_t *bytes, int64_t p, int64_t fend)
+{
+    return p < fend ? (uint32_t)__ldg(bytes + p) : 0u;  // util.get_bits pads with zeros past the buffer (util.py:41-43)
+}
+
+// n <= 16 bits at bit offset `bitoff` from byte position `base`, MSB first, file-clipped
+__device__ __forceinline__ uint32_t bits_at(const uint8_t *bytes, int64_t base, int64_t fend, int bitoff, int n)
+{
+    int64_t p = base + (bitoff >> 3);
+    uint32_t w = (ldb(bytes, p, fend) << 16) | (ldb(bytes, p + 1, fend) << 8) | ldb(bytes, p + 2, fend);
+    return (w >> (24 - (bitoff & 7) - n)) & ((1u << n) - 1u);
+}
+
+struct M3sHdr {
+    int frame_size, hdrlen, mono, crc_present, mode, ms, sr_idx, bitrate, sr;
+};
+
+// FrameHeader.init_header_params (FrameHeader.py:51-192) + Frame.set_frame_size (Frame.py:288-316).
+// Returns 0, or <0 outside the supported domain (MPEG-1 Layer III, non-reserved rate, bitrate index != 15).
+__device__ __forceinline__ int parse_header(uint32_t b1, uint32_t b2, uint32_t b3, M3sHdr &h)
+{
+    if (((b1 >> 3) & 3) != 3) return -2;
+    if (((b1 >> 1) & 3) != 1) return -3;
+    int sri = (b2 >> 2) & 3;
+    if (sri == 3) return -4;
+    int bi = (int)(b2 >> 4);
+    if (bi == 15) return -5;
+    const int br_tab[14] = {32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
+    bi = bi == 0 ? 13 : bi - 1;  // index 0 -> rates[-1] in the reference (FrameHeader.py:180-181)
+    h.bitrate = br_tab[bi] * 1000;
+    h.sr = sri == 0 ? 44100 : (sri == 1 ? 48000 : 32000);
+    h.sr_idx = sri;
+    h.crc_present = (b1 & 1) ? 0 : 1;
+    h.mode = (b3 >> 6) & 3;
+    h.mono = h.mode == 3;
+    h.ms = (h.mode == 1) && (b3 & 0x20);
+    h.frame_size = (144 * h.bitrate) / h.sr + ((b2 >> 1) & 1);  // == int((1152/8*bit_rate)/sampling_rate) + padding
+    h.hdrlen = 4 + (h.crc_present ? 2 : 0) + (h.mono ? 17 : 32);
+    return 0;
+}
+
+// ================================================================================================
+// D0a: sequential frame walk, one thread per file (MP3_Parser.py:57-85).  Pass 1 (WRITE=false) only
+// counts; pass 2 also emits per-frame records, the carried table_select[2] (A.D3) and reveal offsets.
+// ================================================================================================
+template <bool WRITE>
+__global__ void k_walk(const uint8_t *__restrict__ bytes, const M3sFileRec *__restrict__ files, M3sFileOut *fouts,
+                       int n_files, int64_t *fr_pos, uint32_t *fr_P, uint32_t *fr_meta, uint32_t *fr_carry,
+                       uint32_t *fr_reveal, int32_t *fr_file)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_files) return;
+    M3sFileRec fr = files[f];
+    int64_t off = fr.audio, fend = fr.end;
+    M3sFileOut o;
+    o.payload_total = 0; o.n_frames = 0; o.status = 0; o.sample_rate = 0; o.channels = 0; o.bitrate = 0; o.reveal_len = 0;
+    if (!(fend - off >= 2 && ldb(bytes, off, fend) == 0xFF && ldb(bytes, off + 1, fend) >= 0xE0)) {
+        o.status = M3S_FILE_NO_SYNC;
+        fouts[f] = o;
+        return;
+    }
+    uint32_t carry = 0;  // table_select[2] currently held in each (gr, ch) slot, 5 bits per slot
+    uint32_t reveal = 0, P = 0;
+    int n = 0;
+    int64_t g = fr.frame_base;
+    while (fend > off + 4) {
+        uint32_t b0 = ldb(bytes, off, fend), b1 = ldb(bytes, off + 1, fend), b2 = ldb(bytes, off + 2, fend),
+                 b3 = ldb(bytes, off + 3, fend);
+        if (!(b0 == 0xFF && b1 >= 0xE0)) { o.status |= M3S_FILE_TRAILING_JUNK; break; }
+        M3sHdr h;
+        if (parse_header(b1, b2, b3, h) < 0) { o.status |= M3S_FILE_UNSUPPORTED; break; }
+        int64_t avail = fend - off;
+        int fs = h.frame_size < avail ? h.frame_size : (int)avail;
+        int payload = fs - h.hdrlen;
+        if (payload < 0) payload = 0;
+        if (WRITE) {
+            int64_t si = off + 4 + (h.crc_present ? 2 : 0);
+            int rb = h.mono ? 18 : 20;
+            int nz = 0;
+            for (int gr = 0; gr < 2; gr++)
+                for (int ch = 0; ch < (h.mono ? 1 : 2); ch++) {
+                    int slot = 2 * gr + ch;
+                    uint32_t ws = bits_at(bytes, si, fend, rb + 33, 1);
+                    uint32_t t0, t1, t2;
+                    if (ws) {
+                        t0 = bits_at(bytes, si, fend, rb + 37, 5);
+                        t1 = bits_at(bytes, si, fend, rb + 42, 5);
+                        t2 = (carry >> (5 * slot)) & 31u;
+                    } else {
+                        t0 = bits_at(bytes, si, fend, rb + 34, 5);
+                        t1 = bits_at(bytes, si, fend, rb + 39, 5);
+                        t2 = bits_at(bytes, si, fend, rb + 44, 5);
+                        carry = (carry & ~(31u << (5 * slot))) | (t2 << (5 * slot));
+                    }
+                    nz += (t0 != 0) + (t1 != 0) + (t2 != 0);
+                    rb += 59;
+                }
+            fr_pos[g] = off;
+            fr_P[g] = P;
+            fr_meta[g] = (uint32_t)payload | (h.crc_present ? M3S_META_CRC : 0) | ((uint32_t)h.mode << M3S_META_MODE_SHIFT) |
+                         (h.ms ? M3S_META_MS : 0) | ((uint32_t)h.sr_idx << M3S_META_SR_SHIFT) | (h.mono ? M3S_META_MONO : 0) |
+                         (n == 0 ? M3S_META_FIRST : 0) | ((uint32_t)h.hdrlen << M3S_META_HDR_SHIFT);
+            fr_carry[g] = carry;
+            fr_reveal[g] = reveal;
+            fr_file[g] = f;
+            reveal += nz;
+        }
+        P += payload;
+        o.sample_rate = h.sr;
+        o.channels = h.mono ? 1 : 2;
+        o.bitrate = h.bitrate;
+        n++;
+        g++;
+        off += h.frame_size;
+    }
+    if (WRITE && (o.status & M3S_FILE_TRAILING_JUNK) && n > 0) fr_meta[g - 1] |= M3S_META_DUP;
+    o.n_frames = n;
+    o.payload_total = P;
+    o.reveal_len = reveal;
+    fouts[f] = o;
+}
+
+// ================================================================================================
+// D0b + D4: side-info parse, one thread per frame (FrameSideInformation.py:39-137), bit cursors through
+// the reservoir (Frame.py:318-363 restated on the header-stripped stream S), table ids and reveal chars
+// (Frame.py:676-685, util.py:67-81).
+// ================================================================================================
+__global__ void k_sideinfo(const uint8_t *__restrict__ bytes, const M3sFileRec *__restrict__ files, int64_t total_frames,
+                           const int64_t *__restrict__ fr_pos, const uint32_t *__restrict__ fr_P,
+                           const uint32_t *__restrict__ fr_meta, const uint32_t *__restrict__ fr_carry,
+                           const uint32_t *__restrict__ fr_reveal, const int32_t *__restrict__ fr_file, M3sUnitRec *units,
+                           uint8_t *tabids, uint8_t *reveal)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_frames) return;
+    int f = fr_file[g];
+    const M3sFileRec fr = files[f];
+    uint32_t meta = fr_meta[g];
+    int mono = (meta & M3S_META_MONO) != 0;
+    int64_t fend = fr.end;
+    int64_t si = fr_pos[g] + 4 + ((meta & M3S_META_CRC) ? 2 : 0);
+    uint32_t carry = fr_carry[g];
+    uint32_t mdb = bits_at(bytes, si, fend, 0, 9);
+    uint32_t scfsi_all = mono ? bits_at(bytes, si, fend, 14, 4) << 4 : bits_at(bytes, si, fend, 12, 8);
+    int rb = mono ? 18 : 20;
+    int payload = meta & M3S_META_PAYLOAD_MASK;
+    int64_t cur = 8 * (fr.s_base + (int64_t)fr_P[g] - (int64_t)mdb);
+    int64_t limit = 8 * (fr.s_base + (int64_t)fr_P[g] + payload);
+    uint8_t ids[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) ids[i] = 0;
+    M3sUnitRec inval;
+    inval.bit_start = 0; inval.limit_bits = 0; inval.a = 0; inval.b = 0; inval.c = 0; inval.frame = (uint32_t)g; inval.pad = 0;
+    if (mono) { units[4 * g + 1] = inval; units[4 * g + 3] = inval; }
+    for (int gr = 0; gr < 2; gr++)
+        for (int ch = 0; ch < (mono ? 1 : 2); ch++) {
+            int slot = 2 * gr + ch;
+            uint32_t p23 = bits_at(bytes, si, fend, rb, 12);
+            uint32_t bv = bits_at(bytes, si, fend, rb + 12, 9);
+            uint32_t gg = bits_at(bytes, si, fend, rb + 21, 8);
+            uint32_t sfc = bits_at(bytes, si, fend, rb + 29, 4);
+            uint32_t ws = bits_at(bytes, si, fend, rb + 33, 1);
+            uint32_t bt = 0, mixed = 0, t0, t1, t2, r0, r1, sbg = 0;
+            if (ws) {
+                bt = bits_at(bytes, si, fend, rb + 34, 2);
+                mixed = bits_at(bytes, si, fend, rb + 36, 1);
+                t0 = bits_at(bytes, si, fend, rb + 37, 5);
+                t1 = bits_at(bytes, si, fend, rb + 42, 5);
+                t2 = (carry >> (5 * slot)) & 31u;  // stale region-2 id (A.D3)
+                sbg = bits_at(bytes, si, fend, rb + 47, 3) | (bits_at(bytes, si, fend, rb + 50, 3) << 3) |
+                      (bits_at(bytes, si, fend, rb + 53, 3) << 6);
+                r0 = bt == 2 ? 8 : 7;
+                r1 = 20 - r0;  // kept in 4 bits below; only used when not (ws && bt == 2)
+            } else {
+                t0 = bits_at(bytes, si, fend, rb + 34, 5);
+                t1 = bits_at(bytes, si, fend, rb + 39, 5);
+                t2 = bits_at(bytes, si, fend, rb + 44, 5);
+                r0 = bits_at(bytes, si, fend, rb + 49, 4);
+                r1 = bits_at(bytes, si, fend, rb + 53, 3);
+            }
+            uint32_t pre = bits_at(bytes, si, fend, rb + 56, 1);
+            uint32_t sfs = bits_at(bytes, si, fend, rb + 57, 1);
+            uint32_t c1 = bits_at(bytes, si, fend, rb + 58, 1);
+            M3sUnitRec u;
+            u.bit_start = (uint64_t)cur;
+            int64_t lb = limit - cur;
+            u.limit_bits = lb > 0x7FFFFFFF ? 0x7FFFFFFF : (lb < -0x7FFFFFFF ? -0x7FFFFFFF : (int32_t)lb);
+            u.a = p23 | (bv << 12) | (gg << 21) | (ws << 29) | (bt << 30);
+            // region1 of a window-switched granule (12 or 13) does not fit 3 bits: store region0+region1+2 capped to 22 instead
+            uint32_t r01 = r0 + r1 + 2;
+            if (r01 > 22) r01 = 22;
+            u.b = sfc | (mixed << 4) | (t0 << 5) | (t1 << 10) | (t2 << 15) | (r0 << 20) | ((uint32_t)(meta & M3S_META_MS ? 1 : 0) << 30) |
+                  ((uint32_t)mono << 31) | (pre << 27) | (sfs << 28) | (c1 << 29);
+            uint32_t scfsi = ch == 0 ? (scfsi_all >> 4) & 15u : scfsi_all & 15u;
+            u.c = sbg | (scfsi << 9) | (((meta >> M3S_META_SR_SHIFT) & 3u) << 13) | ((uint32_t)gr << 15) | ((uint32_t)ch << 16) |
+                  (1u << 17) | ((meta & M3S_META_FIRST) ? (1u << 18) : 0) | (r01 << 19);
+            u.frame = (uint32_t)g;
+            u.pad = 0;
+            units[4 * g + slot] = u;
+            ids[ch * 6 + gr * 3 + 0] = (uint8_t)t0;
+            ids[ch * 6 + gr * 3 + 1] = (uint8_t)t1;
+            ids[ch * 6 + gr * 3 + 2] = (uint8_t)t2;
+            cur += p23;
+            rb += 59;
+        }
+    uint8_t *rv = reveal + 12 * fr.frame_base + fr_reveal[g];
+    int j = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        tabids[12 * g + i] = ids[i];
+        if (ids[i]) rv[j++] = ((M3S_H0_MASK >> ids[i]) & 1u) ? '0' : '1';
+    }
+}
+
+// ================================================================================================
+// main-data compaction: copy every frame's payload (bytes after header/CRC/side info, clipped to the
+// file) to its position in the header-stripped stream S, one warp per frame.
+// ================================================================================================
+__global__ void k_strip(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec *__restrict__ files,
+                        int64_t total_frames, const int64_t *__restrict__ fr_pos, const uint32_t *__restrict__ fr_P,
+                        const uint32_t *__restrict__ fr_meta, const int32_t *__restrict__ fr_file, uint8_t *S)
+{
+    int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (g >= total_frames) return;
+    uint32_t meta = fr_meta[g];
+    int n = meta & M3S_META_PAYLOAD_MASK;
+    int64_t src = fr_pos[g] + ((meta >> M3S_META_HDR_SHIFT) & 63);
+    int64_t dst = files[fr_file[g]].s_base + fr_P[g];
+    int head = (int)((4 - (dst & 3)) & 3);
+    if (head > n) head = n;
+    if (lane < head) S[dst + lane] = bytes[src + lane];
+    int nwords = (n - head) >> 2;
+    const uint8_t *sp = bytes + src + head;
+    uint32_t *dp = (uint32_t *)(S + dst + head);
+    uintptr_t sa = (uintptr_t)sp;
+    int sh = (int)(sa & 3);
+    const uint32_t *sw = (const uint32_t *)(sa - sh);
+    // the aligned two-word read may touch up to 7 bytes past the last payload byte: keep it inside the batch buffer
+    int64_t safe_words = (total_bytes - (src + head) - 8) >> 2;
+    for (int wi = lane; wi < nwords; wi += 32) {
+        uint32_t v;
+        if (wi < safe_words) {
+            uint32_t lo = __ldg(sw + wi), hi = __ldg(sw + wi + 1);
+            v = __funnelshift_r(lo, hi, 8 * sh);
+        } else {
+            const uint8_t *q = sp + 4 * wi;
+            v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+        }
+        dp[wi] = v;
+    }
+    int tail = n - head - 4 * nwords;
+    if (lane < tail) S[dst + head + 4 * nwords + lane] = bytes[src + head + 4 * nwords + lane];
+}
+
+// ================================================================================================
+// D1: scalefactor + Huffman decode, one thread per granule-channel (Frame.py:365-559).
+// ================================================================================================
+struct BitReader {
+    const uint32_t *w;  // word-aligned base in S
+    int lim;            // bits readable relative to w (reads at or beyond read as zero)
+    int pos;            // current bit position relative to w
+    int idx;
+    uint32_t hi, lo;
+    __device__ __forceinline__ uint32_t load(int wi) const
+    {
+        int b = wi * 32;
+        if (b >= lim) return 0u;
+        uint32_t v = __byte_perm(__ldg(w + wi), 0, 0x0123);
+        int rem = lim - b;
+        if (rem < 32) v &= ~(0xFFFFFFFFu >> rem);
+        return v;
+    }
+    __device__ __forceinline__ void init(const uint8_t *S, uint64_t bit_start, int limit_bits)
+    {
+        uint64_t wbase = bit_start >> 5;
+        w = (const uint32_t *)S + wbase;
+        pos = (int)(bit_start & 31);
+        lim = limit_bits > 0x7FFFFF00 ? 0x7FFFFF00 : limit_bits + pos;
+        idx = 0;
+        hi = load(0);
+        lo = load(1);
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos & 31); }
+    __device__ __forceinline__ void skip(int n)  // n <= 32
+    {
+        pos += n;
+        int ni = pos >> 5;
+        if (ni != idx) {
+            hi = lo;
+            lo = load(ni + 1);
+            idx = ni;
+        }
+    }
+    __device__ __forceinline__ uint32_t get(int n)  // n <= 16
+    {
+        if (n == 0) return 0u;
+        uint32_t v = peek() >> (32 - n);
+        skip(n);
+        return v;
+    }
+};
+
+// arbitrary-position read used by the rare stale-scalefactor paths (A.D4, scfsi from a non-long gr0)
+__device__ __noinline__ uint32_t read_bits_at(const uint8_t *S, const M3sUnitRec &d, int rel_bit, int n)
+{
+    if (n == 0) return 0u;
+    BitReader r;
+    r.init(S, d.bit_start, d.limit_bits);
+    // advance in <=32-bit steps
+    int to = rel_bit;
+    while (to > 0) { int s = to > 32 ? 32 : to; r.skip(s); to -= s; }
+    return r.get(n);
+}
+
+// scale_fac_l[0][ch][sfb] as the reference's persistent array holds it when granule 1 copies it (Frame.py:419-437):
+// the latest frame <= this one whose gr0 wrote that band.
+__device__ __noinline__ uint32_t fetch_gr0_long_sf(const uint8_t *S, const M3sUnitRec *units, const M3sDevTables *T,
+                                                   int64_t u_gr0, int sfb)
+{
+    for (int64_t u = u_gr0;; u -= 4) {
+        const M3sUnitRec d = units[u];
+        uint32_t sl0 = T->slen[M3S_UB_SFC(d.b)][0], sl1 = T->slen[M3S_UB_SFC(d.b)][1];
+        bool is_short = M3S_UA_BT(d.a) == 2 && M3S_UA_WS(d.a);
+        if (!is_short) return read_bits_at(S, d, sfb < 11 ? sfb * sl0 : 11 * sl0 + (sfb - 11) * sl1, sfb < 11 ? sl0 : sl1);
+        if (M3S_UB_MIXED(d.b) && sfb < 8) return read_bits_at(S, d, sfb * sl0, sl0);
+        if (M3S_UC_FIRST(d.c)) return 0u;
+    }
+}
+
+// scale_fac_s[gr][ch][win][sfb<3] left behind by the latest earlier pure-short granule in the same slot (A.D4)
+__device__ __noinline__ uint32_t fetch_stale_short_sf(const uint8_t *S, const M3sUnitRec *units, const M3sDevTables *T,
+                                                      int64_t u_self, int win, int sfb)
+{
+    if (M3S_UC_FIRST(units[u_self].c)) return 0u;
+    for (int64_t u = u_self - 4;; u -= 4) {
+        const M3sUnitRec d = units[u];
+        if (M3S_UC_VALID(d.c) && M3S_UA_BT(d.a) == 2 && M3S_UA_WS(d.a) && !M3S_UB_MIXED(d.b)) {
+            uint32_t sl0 = T->slen[M3S_UB_SFC(d.b)][0];
+            return read_bits_at(S, d, (sfb * 3 + win) * sl0, sl0);
+        }
+        if (M3S_UC_FIRST(d.c)) return 0u;
+    }
+}
+
+#define HUFF_THREADS 256
+
+__global__ void __launch_bounds__(HUFF_THREADS)
+k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int64_t n_units,
+       const M3sDevTables *__restrict__ T, uint32_t *__restrict__ spec, uint8_t *__restrict__ sfout)
+{
+    __shared__ uint16_t s_lut[8192];
+    __shared__ uint32_t s_desc[32], s_sub[32];
+    __shared__ uint8_t s_c1[64];
+    for (int i = threadIdx.x; i < 4096; i += HUFF_THREADS) ((uint32_t *)s_lut)[i] = ((const uint32_t *)T->huff_lut)[i];
+    if (threadIdx.x < 32) { s_desc[threadIdx.x] = T->huff_desc[threadIdx.x]; s_sub[threadIdx.x] = T->huff_sub[threadIdx.x]; }
+    if (threadIdx.x < 64) s_c1[threadIdx.x] = T->count1_lut[threadIdx.x];
+    __syncthreads();
+    int64_t u = (int64_t)blockIdx.x * HUFF_THREADS + threadIdx.x;
+    if (u >= n_units) return;
+    const M3sUnitRec rec = units[u];
+    uint32_t *out = spec + (u >> 2) * (288 * 4) + (u & 3);
+    if (!M3S_UC_VALID(rec.c)) {
+        for (int k = 0; k < 288; k++) out[4 * k] = 0u;
+        return;
+    }
+    const uint32_t a = rec.a, b = rec.b, c = rec.c;
+    const int gr = M3S_UC_GR(c), sr = M3S_UC_SR(c);
+    const bool is_short = M3S_UA_BT(a) == 2 && M3S_UA_WS(a);
+    BitReader br;
+    br.init(S, rec.bit_start, rec.limit_bits);
+    const int pos0 = br.pos;
+    // ---------------------------------------------------------------- scalefactors (Frame.py:365-441)
+    uint32_t sfw[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) sfw[i] = 0;
+    uint8_t *sfb8 = (uint8_t *)sfw;  // local byte view
+    {
+        const int sl0 = T->slen[M3S_UB_SFC(b)][0], sl1 = T->slen[M3S_UB_SFC(b)][1];
+        if (is_short) {
+            if (M3S_UB_MIXED(b)) {
+                br.skip(8 * sl0 > 32 ? 32 : 8 * sl0);  // scale_fac_l[0..7] are parsed but never used by the short requantize path (A.D2)
+                for (int sfb = 0; sfb < 3; sfb++)
+                    for (int w = 0; w < 3; w++) sfb8[M3S_SF_SHORT + 13 * w + sfb] = (uint8_t)fetch_stale_short_sf(S, units, T, u, w, sfb);
+                for (int sfb = 3; sfb < 6; sfb++)
+                    for (int w = 0; w < 3; w++) sfb8[M3S_SF_SHORT + 13 * w + sfb] = (uint8_t)br.get(sl0);
+            } else {
+                for (int sfb = 0; sfb < 6; sfb++)
+                    for (int w = 0; w < 3; w++) sfb8[M3S_SF_SHORT + 13 * w + sfb] = (uint8_t)br.get(sl0);
+            }
+            for (int sfb = 6; sfb < 12; sfb++)
+                for (int w = 0; w < 3; w++) sfb8[M3S_SF_SHORT + 13 * w + sfb] = (uint8_t)br.get(sl1);
+        } else if (gr == 0) {
+            for (int sfb = 0; sfb < 11; sfb++) sfb8[sfb] = (uint8_t)br.get(sl0);
+            for (int sfb = 11; sfb < 21; sfb++) sfb8[sfb] = (uint8_t)br.get(sl1);
+        } else {
+            const uint32_t scfsi = M3S_UC_SCFSI(c);
+            const int lo_[4] = {0, 6, 11, 16}, hi_[4] = {6, 11, 16, 21};
+            for (int i = 0; i < 4; i++) {
+                int sl = i < 2 ? sl0 : sl1;
+                for (int sfb = lo_[i]; sfb < hi_[i]; sfb++) {
+                    if ((scfsi >> (3 - i)) & 1u) sfb8[sfb] = (uint8_t)fetch_gr0_long_sf(S, units, T, u - 2, sfb);
+                    else sfb8[sfb] = (uint8_t)br.get(sl);
+                }
+            }
+        }
+    }
+    {
+        uint4 *so = (uint4 *)(sfout + u * M3S_SF_STRIDE);
+        so[0] = make_uint4(sfw[0], sfw[1], sfw[2], sfw[3]);
+        so[1] = make_uint4(sfw[4], sfw[5], sfw[6], sfw[7]);
+        so[2] = make_uint4(sfw[8], sfw[9], sfw[10], sfw[11]);
+        so[3] = make_uint4(sfw[12], sfw[13], sfw[14], sfw[15]);
+    }
+    // ---------------------------------------------------------------- big values + count1 (Frame.py:443-559)
+    const int max_pos = pos0 + (int)M3S_UA_P23(a);
+    int bv = M3S_UA_BV(a);
+    if (bv > 288) bv = 288;  // the reference raises IndexError beyond 576 samples
+    int r0p, r1p;
+    if (is_short) { r0p = 18; r1p = 288; }
+    else {
+        r0p = T->sfb_long[sr][M3S_UB_R0(b) + 1] >> 1;
+        r1p = T->sfb_long[sr][(c >> 19) & 31u] >> 1;
+    }
+    const uint32_t d0 = s_desc[M3S_UB_TS(b, 0)], d1 = s_desc[M3S_UB_TS(b, 1)], d2 = s_desc[M3S_UB_TS(b, 2)];
+    const uint32_t sb0 = s_sub[M3S_UB_TS(b, 0)], sb1 = s_sub[M3S_UB_TS(b, 1)], sb2 = s_sub[M3S_UB_TS(b, 2)];
+    const bool c1b = M3S_UB_C1SEL(b);
+    bool c1_active = true, pending = false;
+    uint32_t pend = 0;
+    for (int k = 0; k < 288; k++) {
+        uint32_t o = 0;
+        if (k < bv) {
+            uint32_t desc = k < r0p ? d0 : (k < r1p ? d1 : d2);
+            uint32_t sub = k < r0p ? sb0 : (k < r1p ? sb1 : sb2);
+            int l1b = (desc >> 13) & 15;
+            if (l1b) {  // tables 0, 4 and 14 carry no codes: zeros, no bits consumed (A.D6)
+                uint32_t wv = br.peek();
+                uint32_t e = s_lut[(desc & 0x1FFF) + (wv >> (32 - l1b))];
+                if (e & 0x8000u) {
+                    int nb = (e >> 11) & 15;
+                    e = s_lut[sub + ((e & 0x7FFu) << 1) + ((wv << l1b) >> (32 - nb))];
+                }
+                br.skip((e >> 8) & 31);
+                int x = (e >> 4) & 15, y = e & 15;
+                int lb = (desc >> 17) & 15;
+                wv = br.peek();
+                int used = 0;
+                if (lb && x == 15) { x += wv >> (32 - lb); wv <<= lb; used += lb; }
+                if (x) { if (wv >> 31) x = -x; wv <<= 1; used++; }
+                if (lb && y == 15) { y += wv >> (32 - lb); wv <<= lb; used += lb; }
+                if (y) { if (wv >> 31) y = -y; used++; }
+                br.skip(used);
+                o = ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16);
+            }
+        } else if (pending) {
+            o = pend;
+            pending = false;
+        } else if (c1_active) {
+            if (br.pos < max_pos && 2 * k + 4 < 576) {
+                uint32_t wv = br.peek();
+                uint32_t q;  // v w x y in bits 3..0
+                int used;
+                if (c1b) { q = (~wv >> 28) & 15u; used = 4; }
+                else { uint32_t e = s_c1[wv >> 26]; q = e & 15u; used = e >> 4; }
+                wv <<= used;
+                int v0 = (q >> 3) & 1, v1 = (q >> 2) & 1, v2 = (q >> 1) & 1, v3 = q & 1;
+                if (v0) { if (wv >> 31) v0 = -1; wv <<= 1; used++; }
+                if (v1) { if (wv >> 31) v1 = -1; wv <<= 1; used++; }
+                if (v2) { if (wv >> 31) v2 = -1; wv <<= 1; used++; }
+                if (v3) { if (wv >> 31) v3 = -1; used++; }
+                br.skip(used);
+                o = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
+                pend = ((uint32_t)v2 & 0xFFFFu) | ((uint32_t)v3 << 16);
+                pending = true;
+            } else c1_active = false;
+        }
+        out[4 * k] = o;
+    }
+}
+
+// int16 [frame][gr][ch][576] parity tap from the pair-major spectra layout
+__global__ void k_spec_export(const uint32_t *__restrict__ spec, int64_t total_frames, int16_t *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (frame, pair, slot)
+    if (i >= total_frames * 288 * 4) return;
+    int slot = (int)(i & 3);
+    int64_t r = i >> 2;
+    int k = (int)(r % 288);
+    int64_t g = r / 288;
+    uint32_t v = spec[i];
+    int16_t *o = out + ((g * 4 + slot) * 576 + 2 * k);
+    o[0] = (int16_t)(v & 0xFFFF);
+    o[1] = (int16_t)(v >> 16);
+}
+
+// ================================================================================================
+// D2 + D3: requantize, MS stereo, reorder / alias, IMDCT + window + overlap, frequency inversion,
+// polyphase synthesis, int16 pack.  One CTA walks a run of consecutive frames of one file, keeping the
+// overlap buffer and the 15-slot V history in shared memory; a run that does not start its file first
+// re-decodes one warm-up frame whose PCM is discarded.
+// (Frame.py:157-218 re_quantize, :561-572, :574-602, :604-622, :106-154 imdct, :624-631, :65-103 synth,
+//  :633-640 interleave, MP3_Parser.py:91 int16 conversion)
+// ================================================================================================
+struct M3sWork {
+    int64_t g_first;   // first frame whose PCM this CTA emits
+    int32_t count;     // frames to emit
+    int32_t warm;      // 1: decode frame g_first-1 first without emitting
+    int64_t pcm_elem;  // element offset of frame g_first's first sample in the PCM buffer
+    int32_t channels;
+    int32_t pad;
+};
+
+#define HYB_THREADS 256
+
+struct HybSmem {
+    float xr[2][576];
+    float prev[2][2][576];
+    float tt[2][18][32];
+    float v[2][33][64];
+    float cos36[36][18];
+    float cos12[12][8];
+    float sine[4][36];
+    float d[512];
+    float pow43[256];
+    float cs[8], ca[8];
+    float quarter[4];
+    uint16_t reorder[576];
+    uint8_t long_sfb[576];
+    uint8_t short_sfw[576];
+    uint8_t pretab[24];
+    M3sUnitRec rec[4];
+    uint8_t sf[4][M3S_SF_STRIDE];
+    int sr_loaded;
+};
+
+__device__ __forceinline__ float pow2i(int e)  // 2^e for e in the normal float range
+{
+    e = e < -126 ? -126 : (e > 127 ? 127 : e);
+    return __int_as_float((e + 127) << 23);
+}
+
+template <bool FLOAT_OUT>
+__global__ void __launch_bounds__(HYB_THREADS)
+k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
+         const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
+         void *__restrict__ pcm_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HybSmem &sm = *reinterpret_cast<HybSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const M3sWork wk = work[blockIdx.x];
+    const int nch = wk.channels;
+
+    // ---- one-time table staging
+    for (int i = tid; i < 36 * 18; i += HYB_THREADS) (&sm.cos36[0][0])[i] = (&T->imdct_cos36[0][0])[i];
+    for (int i = tid; i < 12 * 8; i += HYB_THREADS) (&sm.cos12[0][0])[i] = (&T->imdct_cos12[0][0])[i];
+    for (int i = tid; i < 4 * 36; i += HYB_THREADS) (&sm.sine[0][0])[i] = (&T->sine_block[0][0])[i];
+    for (int i = tid; i < 512; i += HYB_THREADS) sm.d[i] = T->synth_d[i];
+    for (int i = tid; i < 256; i += HYB_THREADS) sm.pow43[i] = T->pow43[i];
+    if (tid < 8) { sm.cs[tid] = T->alias_cs[tid]; sm.ca[tid] = T->alias_ca[tid]; }
+    if (tid < 4) sm.quarter[tid] = T->quarter[tid];
+    if (tid < 22) sm.pretab[tid] = T->pretab[tid];
+    if (tid == 0) sm.sr_loaded = -1;
+    for (int i = tid; i < 2 * 2 * 576; i += HYB_THREADS) (&sm.prev[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * 33 * 64; i += HYB_THREADS) (&sm.v[0][0][0])[i] = 0.f;
+    // matrixing row held in registers: output index i = (warp & 1) * 32 + lane
+    float nrow[32];
+    {
+        const int i = (warp & 1) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; j++) nrow[j] = T->synth_n[i][j];
+    }
+    __syncthreads();
+
+    int pp = 0;  // ping-pong index of the overlap buffer: prev[pp] is read, prev[pp ^ 1] written
+    const int64_t g_begin = wk.g_first - (wk.warm ? 1 : 0);
+    const int64_t g_end = wk.g_first + wk.count;
+    for (int64_t g = g_begin; g < g_end; g++) {
+        const bool emit = g >= wk.g_first;
+        const uint32_t meta = fr_meta[g];
+        const int sr = (meta >> M3S_META_SR_SHIFT) & 3;
+        // ---- per-frame records
+        if (tid < 4) sm.rec[tid] = units[4 * g + tid];
+        if (tid >= 32 && tid < 32 + 16) ((uint4 *)&sm.sf[0][0])[tid - 32] = ((const uint4 *)(sfin + 4 * g * M3S_SF_STRIDE))[tid - 32];
+        if (sm.sr_loaded != sr) {  // uniform branch: sr_loaded is only written behind the barrier below
+            for (int i = tid; i < 576; i += HYB_THREADS) {
+                sm.reorder[i] = T->reorder_dst[sr][i];
+                sm.long_sfb[i] = T->long_sfb_of[sr][i];
+                sm.short_sfw[i] = T->short_sfw_of[sr][i];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) sm.sr_loaded = sr;
+        const bool ms = (meta & M3S_META_MS) != 0;
+
+        for (int gr = 0; gr < 2; gr++) {
+            // ------------------------------------------------ requantize + MS + reorder (fused)
+            for (int p = tid; p < 288; p += HYB_THREADS) {
+                const uint4 w4 = ((const uint4 *)spec)[g * 288 + p];
+                float val[2][2];
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch >= nch) { val[ch][0] = val[ch][1] = 0.f; continue; }
+                    const int slot = 2 * gr + ch;
+                    const uint32_t wv = slot == 0 ? w4.x : (slot == 1 ? w4.y : (slot == 2 ? w4.z : w4.w));
+                    const M3sUnitRec &r = sm.rec[slot];
+                    const uint8_t *sf = sm.sf[slot];
+                    const int gg = M3S_UA_GG(r.a);
+                    const int mult4 = M3S_UB_SFSCALE(r.b) ? 4 : 2;
+                    const bool shortp = M3S_UA_BT(r.a) == 2;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int i = 2 * p + h;
+                        int x = (int)(int16_t)(h ? (wv >> 16) : (wv & 0xFFFFu));
+                        int e4;
+                        if (shortp) {
+                            const int q = sm.short_sfw[i];
+                            const int sfb = q / 3, wnd = q - 3 * sfb;
+                            e4 = gg - 210 - 8 * (int)M3S_UC_SBG(r.c, wnd) - mult4 * (int)sf[M3S_SF_SHORT + 13 * wnd + sfb];
+                        } else {
+                            const int sfb = sm.long_sfb[i];
+                            e4 = gg - 210 - mult4 * ((int)sf[sfb] + (int)M3S_UB_PREFLAG(r.b) * (int)sm.pretab[sfb]);
+                        }
+                        const int ax = x < 0 ? -x : x;
+                        float m = ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax);
+                        m *= sm.quarter[e4 & 3] * pow2i(e4 >> 2);
+                        val[ch][h] = x < 0 ? -m : m;
+                    }
+                }
+                if (ms && nch == 2) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float mm = val[0][h], ss = val[1][h];
+                        val[0][h] = (mm + ss) * 0.70710678118654752f;
+                        val[1][h] = (mm - ss) * 0.70710678118654752f;
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch >= nch) continue;
+                    const M3sUnitRec &r = sm.rec[2 * gr + ch];
+                    const bool reord = M3S_UA_BT(r.a) == 2 || M3S_UB_MIXED(r.b);
+                    if (reord) {
+                        sm.xr[ch][sm.reorder[2 * p]] = val[ch][0];
+                        sm.xr[ch][sm.reorder[2 * p + 1]] = val[ch][1];
+                    } else {
+                        sm.xr[ch][2 * p] = val[ch][0];
+                        sm.xr[ch][2 * p + 1] = val[ch][1];
+                    }
+                }
+            }
+            __syncthreads();
+            // ------------------------------------------------ alias reduction (long blocks only)
+            for (int aidx = tid; aidx < nch * 248; aidx += HYB_THREADS) {
+                const int ch = aidx / 248, r_ = aidx - ch * 248;
+                const M3sUnitRec &r = sm.rec[2 * gr + ch];
+                if (M3S_UA_BT(r.a) == 2 || M3S_UB_MIXED(r.b)) continue;
+                const int sb = 1 + (r_ >> 3), i = r_ & 7;
+                const int o1 = 18 * sb - i - 1, o2 = 18 * sb + i;
+                const float s1 = sm.xr[ch][o1], s2 = sm.xr[ch][o2];
+                sm.xr[ch][o1] = s1 * sm.cs[i] - s2 * sm.ca[i];
+                sm.xr[ch][o2] = s2 * sm.cs[i] + s1 * sm.ca[i];
+            }
+            __syncthreads();
+            // ------------------------------------------------ IMDCT + window + overlap + frequency inversion
+            {
+                const int ch = warp & 1, q = warp >> 1, sb = lane;
+                if (ch < nch) {
+                    const M3sUnitRec &r = sm.rec[2 * gr + ch];
+                    const int bt = M3S_UA_BT(r.a);
+                    float x[18];
+#pragma unroll
+                    for (int k = 0; k < 18; k++) x[k] = sm.xr[ch][18 * sb + k];
+                    const float *pv = sm.prev[pp][ch];
+                    float *pn = sm.prev[pp ^ 1][ch];
+#pragma unroll
+                    for (int ii = 0; ii < 9; ii++) {
+                        const int i = 9 * q + ii;
+                        float acc = 0.f;
+                        if (bt != 2) {
+#pragma unroll
+                            for (int k = 0; k < 18; k++) acc = fmaf(x[k], sm.cos36[i][k], acc);
+                            acc *= sm.sine[bt][i];
+                        } else if (i >= 6 && i < 30) {
+                            // three 12-point windows placed at 6/12/18 with overlap (Frame.py:135-148)
+                            const int w_hi = (i - 6) / 6;            // window whose first half covers i
+                            const int i_hi = i - 6 - 6 * w_hi;       // 0..5
+                            if (w_hi < 3) {
+                                float a2 = 0.f;
+#pragma unroll
+                                for (int k = 0; k < 6; k++) a2 = fmaf(sm.xr[ch][18 * sb + 6 * w_hi + k], sm.cos12[i_hi][k], a2);
+                                acc += a2 * sm.sine[2][i_hi];
+                            }
+                            const int w_lo = w_hi - 1;               // window whose second half covers i
+                            if (w_lo >= 0) {
+                                float a2 = 0.f;
+#pragma unroll
+                                for (int k = 0; k < 6; k++) a2 = fmaf(sm.xr[ch][18 * sb + 6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
+                                acc += a2 * sm.sine[2][i_hi + 6];
+                            }
+                        }
+                        if (i < 18) {
+                            float o = acc + pv[18 * sb + i];
+                            if ((sb & 1) && (i & 1)) o = -o;
+                            sm.tt[ch][i][sb] = o;
+                        } else pn[18 * sb + (i - 18)] = acc;
+                    }
+                }
+            }
+            __syncthreads();
+            // ------------------------------------------------ matrixing: V[t][i] = sum_j N[i][j] * S_t[j]
+            {
+                const int i = (warp & 1) * 32 + lane, tg = warp >> 1;
+                for (int cidx = tg; cidx < nch * 18; cidx += 4) {
+                    const int ch = cidx / 18, t = cidx - 18 * ch;
+                    const float4 *s4 = (const float4 *)sm.tt[ch][t];
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; j4++) {
+                        const float4 s = s4[j4];
+                        acc = fmaf(s.x, nrow[4 * j4 + 0], acc);
+                        acc = fmaf(s.y, nrow[4 * j4 + 1], acc);
+                        acc = fmaf(s.z, nrow[4 * j4 + 2], acc);
+                        acc = fmaf(s.w, nrow[4 * j4 + 3], acc);
+                    }
+                    sm.v[ch][15 + t][i] = acc;
+                }
+            }
+            __syncthreads();
+            // ------------------------------------------------ windowing + output
+            for (int o = tid; o < 576; o += HYB_THREADS) {
+                const int t = o >> 5, i = o & 31;
+                float s[2] = {0.f, 0.f};
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch >= nch) continue;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        acc = fmaf(sm.v[ch][15 + t - 2 * m][i], sm.d[64 * m + i], acc);
+                        acc = fmaf(sm.v[ch][15 + t - 2 * m - 1][32 + i], sm.d[64 * m + 32 + i], acc);
+                    }
+                    s[ch] = acc;
+                }
+                if (emit) {
+                    const int reps = (meta & M3S_META_DUP) ? 2 : 1;
+                    for (int rep = 0; rep < reps; rep++) {
+                        const int64_t row = (g - wk.g_first + rep) * 1152 + gr * 576 + o;
+                        if (FLOAT_OUT) {
+                            float *po = (float *)pcm_out + wk.pcm_elem + row * nch;
+                            po[0] = s[0];
+                            if (nch == 2) po[1] = s[1];
+                        } else {
+                            // (pcm * 32767).astype(int16): truncate toward zero, keep the low 16 bits (A.D8)
+                            const int a0 = __float2int_rz(s[0] * 32767.f), a1 = __float2int_rz(s[1] * 32767.f);
+                            if (nch == 2)
+                                ((uint32_t *)pcm_out)[(wk.pcm_elem >> 1) + row] = ((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16);
+                            else
+                                ((int16_t *)pcm_out)[wk.pcm_elem + row] = (int16_t)(a0 & 0xFFFF);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ------------------------------------------------ slide the V history: slots 18..32 -> 0..14
+            for (int idx = tid; idx < nch * 15 * 64; idx += HYB_THREADS) {
+                const int ch = idx / (15 * 64), r_ = idx - ch * 15 * 64;
+                (&sm.v[ch][0][0])[r_] = (&sm.v[ch][18][0])[r_];
+            }
+            pp ^= 1;
+            __syncthreads();
+        }
+    }
+}
+
+// ================================================================================================
+// host orchestration
+// ================================================================================================
+static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, const int64_t *file_off,
+                               const int64_t *audio_start, int32_t n_files, int64_t *n_frames, int64_t *pcm_rows,
+                               int32_t *sample_rate, int32_t *channels, int32_t *bitrate_bps, int32_t *status)
+{
+    if (!h) return M3S_ERR_ARG;
+    h->scanned = false;
+    if (!bytes || !file_off || n_files <= 0) return m3s_fail(h, M3S_ERR_ARG, "decode_scan: bytes/file_off/n_files");
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    const int64_t total_bytes = file_off[n_files];
+    for (int i = 0; i < n_files; i++)
+        if (file_off[i + 1] < file_off[i] || (audio_start && (audio_start[i] < 0)))
+            return m3s_fail(h, M3S_ERR_ARG, "decode_scan: file_off must be non-decreasing, audio_start >= 0");
+    // ---- stage the bytes on the device when they are host memory
+    if (mem == M3S_MEM_HOST) {
+        int rc = m3s_buf_reserve(h, h->b_stage_in, (size_t)total_bytes + 16);
+        if (rc) return rc;
+        M3S_CUDA(h, cudaMemcpyAsync(h->b_stage_in.p, bytes, (size_t)total_bytes, cudaMemcpyHostToDevice, h->stream));
+        h->d_bytes = (const uint8_t *)h->b_stage_in.p;
+    } else
+        h->d_bytes = bytes;
+    h->n_files = n_files;
+    h->files.assign(n_files, M3sFileRec());
+    h->fouts.assign(n_files, M3sFileOut());
+    for (int i = 0; i < n_files; i++) {
+        M3sFileRec &f = h->files[i];
+        f.begin = file_off[i];
+        f.end = file_off[i + 1];
+        f.audio = file_off[i] + (audio_start ? audio_start[i] : 0);
+        if (f.audio > f.end) f.audio = f.end;
+        f.frame_base = 0; f.s_base = 0; f.pcm_base = 0; f.n_frames = 0; f.flags = 0; f.channels = 0; f.pad = 0;
+    }
+    int rc;
+    if ((rc = m3s_buf_reserve(h, h->b_files, sizeof(M3sFileRec) * n_files))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_fouts, sizeof(M3sFileOut) * n_files))) return rc;
+    M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
+    const int wb = 32, wg = (n_files + wb - 1) / wb;
+    k_walk<false><<<wg, wb, 0, h->stream>>>(h->d_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p, n_files,
+                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    M3S_LAUNCH_CHECK(h);
+    M3S_CUDA(h, cudaMemcpyAsync(h->fouts.data(), h->b_fouts.p, sizeof(M3sFileOut) * n_files, cudaMemcpyDeviceToHost, h->stream));
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    int64_t fb = 0, sb = 0;
+    for (int i = 0; i < n_files; i++) {
+        M3sFileRec &f = h->files[i];
+        f.frame_base = fb;
+        f.n_frames = h->fouts[i].n_frames;
+        fb += f.n_frames;
+        sb += 512;  // zero pad in front: a main_data_begin that reaches before the first frame reads zeros
+        f.s_base = sb;
+        sb += round_up(h->fouts[i].payload_total, 16) + 64;
+    }
+    h->total_frames = fb;
+    h->s_bytes = sb + 64;
+    const int64_t nf = std::max<int64_t>(fb, 1);
+    if ((rc = m3s_buf_reserve(h, h->b_fr_pos, sizeof(int64_t) * nf))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_fr_P, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_fr_meta, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_fr_carry, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_fr_reveal, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_fr_file, sizeof(int32_t) * nf))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_units, sizeof(M3sUnitRec) * 4 * nf))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_tabids, 12 * nf))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_reveal, 12 * nf))) return rc;
+    M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
+    k_walk<true><<<wg, wb, 0, h->stream>>>(h->d_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p, n_files,
+                                           (int64_t *)h->b_fr_pos.p, (uint32_t *)h->b_fr_P.p, (uint32_t *)h->b_fr_meta.p,
+                                           (uint32_t *)h->b_fr_carry.p, (uint32_t *)h->b_fr_reveal.p, (int32_t *)h->b_fr_file.p);
+    M3S_LAUNCH_CHECK(h);
+    if (fb > 0) {
+        k_sideinfo<<<(unsigned)((fb + 127) / 128), 128, 0, h->stream>>>(
+            h->d_bytes, (const M3sFileRec *)h->b_files.p, fb, (const int64_t *)h->b_fr_pos.p, (const uint32_t *)h->b_fr_P.p,
+            (const uint32_t *)h->b_fr_meta.p, (const uint32_t *)h->b_fr_carry.p, (const uint32_t *)h->b_fr_reveal.p,
+            (const int32_t *)h->b_fr_file.p, (M3sUnitRec *)h->b_units.p, (uint8_t *)h->b_tabids.p, (uint8_t *)h->b_reveal.p);
+        M3S_LAUNCH_CHECK(h);
+    }
+    M3S_CUDA(h, cudaMemcpyAsync(h->fouts.data(), h->b_fouts.p, sizeof(M3sFileOut) * n_files, cudaMemcpyDeviceToHost, h->stream));
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n_files; i++) {
+        const M3sFileOut &o = h->fouts[i];
+        h->files[i].flags = o.status;
+        h->files[i].channels = o.channels;
+        if (n_frames) n_frames[i] = o.n_frames;
+        if (pcm_rows) pcm_rows[i] = 1152LL * (o.n_frames + ((o.status & M3S_FILE_TRAILING_JUNK) && o.n_frames > 0 ? 1 : 0));
+        if (sample_rate) sample_rate[i] = o.sample_rate;
+        if (channels) channels[i] = o.channels;
+        if (bitrate_bps) bitrate_bps[i] = o.bitrate;
+        if (status) status[i] = o.status;
+    }
+    h->scanned = true;
+    return M3S_OK;
+}
+
+extern "C" int m3s_decode_reveal(m3s_handle_t h, uint8_t *table_ids, uint8_t *reveal_bits, int mem, int64_t *reveal_len)
+{
+    if (!h) return M3S_ERR_ARG;
+    if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_reveal: call m3s_decode_scan first");
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    const cudaMemcpyKind kind = mem == M3S_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (h->total_frames > 0) {
+        if (table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids, h->b_tabids.p, 12 * h->total_frames, kind, h->stream));
+        if (reveal_bits) M3S_CUDA(h, cudaMemcpyAsync(reveal_bits, h->b_reveal.p, 12 * h->total_frames, kind, h->stream));
+    }
+    if (reveal_len)
+        for (int i = 0; i < h->n_files; i++) reveal_len[i] = h->fouts[i].reveal_len;
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    return M3S_OK;
+}
+
+#define M3S_HYB_RUN 32  // frames per CTA run (one warm-up frame per run: ~3% recompute)
+
+extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t *pcm_off, int16_t *spectra, uint32_t flags)
+{
+    if (!h) return M3S_ERR_ARG;
+    if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_run: call m3s_decode_scan first");
+    if (!pcm) return m3s_fail(h, M3S_ERR_ARG, "decode_run: pcm is NULL");
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    const int64_t nf = h->total_frames;
+    if (nf == 0) return M3S_OK;
+    const bool fl = (flags & M3S_DEC_PCM_FLOAT) != 0;
+    const size_t esz = fl ? 4 : 2;
+    int rc;
+    // ---- PCM layout
+    int64_t total_elems = 0;
+    std::vector<M3sWork> work;
+    for (int i = 0; i < h->n_files; i++) {
+        M3sFileRec &f = h->files[i];
+        const int64_t rows = 1152LL * (f.n_frames + ((f.flags & M3S_FILE_TRAILING_JUNK) && f.n_frames > 0 ? 1 : 0));
+        const int64_t elems = rows * std::max(f.channels, 1);
+        f.pcm_base = pcm_off ? pcm_off[i] : total_elems;
+        if (f.channels == 2 && !fl && (f.pcm_base & 1)) return m3s_fail(h, M3S_ERR_ARG, "decode_run: stereo pcm_off must be even");
+        total_elems = std::max(total_elems, f.pcm_base + elems);
+        for (int64_t k = 0; k < f.n_frames; k += M3S_HYB_RUN) {
+            M3sWork w;
+            w.g_first = f.frame_base + k;
+            w.count = (int32_t)std::min<int64_t>(M3S_HYB_RUN, f.n_frames - k);
+            w.warm = k > 0 ? 1 : 0;
+            w.pcm_elem = f.pcm_base + k * 1152 * f.channels;
+            w.channels = f.channels;
+            w.pad = 0;
+            work.push_back(w);
+        }
+    }
+    // ---- workspaces
+    if ((rc = m3s_buf_reserve(h, h->b_S, (size_t)h->s_bytes))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_spec, (size_t)nf * 288 * 4 * 4))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_sf, (size_t)nf * 4 * M3S_SF_STRIDE))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->b_work, sizeof(M3sWork) * work.size()))) return rc;
+    void *d_pcm = pcm;
+    if (mem == M3S_MEM_HOST) {
+        if ((rc = m3s_buf_reserve(h, h->b_pcm_stage, (size_t)total_elems * esz))) return rc;
+        d_pcm = h->b_pcm_stage.p;
+    }
+    M3S_CUDA(h, cudaMemcpyAsync(h->b_work.p, work.data(), sizeof(M3sWork) * work.size(), cudaMemcpyHostToDevice, h->stream));
+    M3S_CUDA(h, cudaMemsetAsync(h->b_S.p, 0, (size_t)h->s_bytes, h->stream));
+    int64_t total_bytes = h->files[h->n_files - 1].end;
+    k_strip<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, h->stream>>>(
+        h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, nf, (const int64_t *)h->b_fr_pos.p,
+        (const uint32_t *)h->b_fr_P.p, (const uint32_t *)h->b_fr_meta.p, (const int32_t *)h->b_fr_file.p, (uint8_t *)h->b_S.p);
+    M3S_LAUNCH_CHECK(h);
+    k_huff<<<(unsigned)((4 * nf + HUFF_THREADS - 1) / HUFF_THREADS), HUFF_THREADS, 0, h->stream>>>(
+        (const uint8_t *)h->b_S.p, (const M3sUnitRec *)h->b_units.p, 4 * nf, h->d_tab, (uint32_t *)h->b_spec.p, (uint8_t *)h->b_sf.p);
+    M3S_LAUNCH_CHECK(h);
+    if (spectra) {
+        int16_t *d_sp = spectra;
+        if (mem == M3S_MEM_HOST) {
+            if ((rc = m3s_buf_reserve(h, h->b_spec_export, (size_t)nf * 4 * 576 * 2))) return rc;
+            d_sp = (int16_t *)h->b_spec_export.p;
+        }
+        k_spec_export<<<(unsigned)((nf * 288 * 4 + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)h->b_spec.p, nf, d_sp);
+        M3S_LAUNCH_CHECK(h);
+        if (mem == M3S_MEM_HOST)
+            M3S_CUDA(h, cudaMemcpyAsync(spectra, d_sp, (size_t)nf * 4 * 576 * 2, cudaMemcpyDeviceToHost, h->stream));
+    }
+    const size_t smem = sizeof(HybSmem);
+    if (fl) {
+        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hybrid<true><<<(unsigned)work.size(), HYB_THREADS, smem, h->stream>>>(
+            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)h->b_units.p, (const uint8_t *)h->b_sf.p,
+            (const uint32_t *)h->b_fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, d_pcm);
+    } else {
+        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hybrid<false><<<(unsigned)work.size(), HYB_THREADS, smem, h->stream>>>(
+            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)h->b_units.p, (const uint8_t *)h->b_sf.p,
+            (const uint32_t *)h->b_fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, d_pcm);
+    }
+    M3S_LAUNCH_CHECK(h);
+    if (mem == M3S_MEM_HOST)
+        M3S_CUDA(h, cudaMemcpyAsync(pcm, d_pcm, (size_t)total_elems * esz, cudaMemcpyDeviceToHost, h->stream));
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    return M3S_OK;
+}

@@ -1,0 +1,229 @@
+"""ctypes binding of libmp3stego_b200.so (include/mp3stego_b200.h) plus the batch entry points.
+
+There is no CPU fallback: importing this module without the built library, or creating a handle
+without an sm_100 GPU, raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmp3stego_b200.so")
+
+M3S_MEM_HOST, M3S_MEM_DEVICE = 0, 1
+M3S_FILE_NO_SYNC, M3S_FILE_UNSUPPORTED, M3S_FILE_TRAILING_JUNK = 1, 2, 4
+M3S_DEC_PCM_FLOAT = 1
+
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_c_i32p = ctypes.POINTER(ctypes.c_int32)
+
+# every symbol include/mp3stego_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("m3s_create", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    ("m3s_destroy", ctypes.c_int, [ctypes.c_void_p]),
+    ("m3s_last_error", ctypes.c_char_p, [ctypes.c_void_p]),
+    ("m3s_set_stream", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    ("m3s_synchronize", ctypes.c_int, [ctypes.c_void_p]),
+    ("m3s_launch_count", ctypes.c_int64, [ctypes.c_void_p]),
+    ("m3s_version", ctypes.c_int, []),
+    ("m3s_decode_scan", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, _c_i64p, ctypes.c_int32,
+                                       _c_i64p, _c_i64p, _c_i32p, _c_i32p, _c_i32p, _c_i32p]),
+    ("m3s_decode_reveal", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p]),
+    ("m3s_decode_run", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, ctypes.c_void_p,
+                                      ctypes.c_uint32]),
+    ("m3s_encode_bound", ctypes.c_int64, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
+    ("m3s_encode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, _c_i64p, ctypes.c_int32,
+                                  ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, _c_i64p, ctypes.c_void_p, _c_i64p,
+                                  _c_i64p, _c_i64p, _c_i64p]),
+    ("m3s_encode_taps", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
+    ("m3s_table_export", ctypes.c_int64, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
+]
+
+_lib = None
+
+
+class M3SError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises M3SError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise M3SError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_c_i64p)
+
+
+def _ptr(x):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return ctypes.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        return ctypes.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        return ctypes.c_void_p(x.data_ptr())
+    raise TypeError(type(x))
+
+
+def _mem_of(x):
+    if hasattr(x, "is_cuda"):
+        return M3S_MEM_DEVICE if x.is_cuda else M3S_MEM_HOST
+    return M3S_MEM_HOST
+
+
+class Handle:
+    """One CUDA stream + grow-only device workspaces (m3s_handle_t)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load()
+        h = ctypes.c_void_p()
+        rc = self._L.m3s_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise M3SError(f"m3s_create(device={device}) failed with {rc}: no sm_100 CUDA device "
+                           "(this library has no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.m3s_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise M3SError(f"{what} failed ({rc}): {self._L.m3s_last_error(self._h).decode()}")
+
+    def set_stream(self, stream_ptr):
+        self._check(self._L.m3s_set_stream(self._h, ctypes.c_void_p(stream_ptr) if stream_ptr else None), "m3s_set_stream")
+
+    def synchronize(self):
+        self._check(self._L.m3s_synchronize(self._h), "m3s_synchronize")
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.m3s_launch_count(self._h))
+
+    # ------------------------------------------------------------------ decode
+    def decode_scan(self, data, file_off, audio_start=None):
+        """D0 + D4 over a batch.  `data`: uint8 numpy array / torch tensor (host or cuda) of all files end to end."""
+        n = len(file_off) - 1
+        fo, fo_p = _i64(file_off)
+        if audio_start is not None:
+            au, au_p = _i64(audio_start)
+        else:
+            au, au_p = None, None
+        out = dict(n_frames=np.zeros(n, np.int64), pcm_rows=np.zeros(n, np.int64), sample_rate=np.zeros(n, np.int32),
+                   channels=np.zeros(n, np.int32), bitrate=np.zeros(n, np.int32), status=np.zeros(n, np.int32))
+        self._keep = (data, fo, au)
+        rc = self._L.m3s_decode_scan(self._h, _ptr(data), _mem_of(data), fo_p, au_p, n,
+                                     out["n_frames"].ctypes.data_as(_c_i64p), out["pcm_rows"].ctypes.data_as(_c_i64p),
+                                     out["sample_rate"].ctypes.data_as(_c_i32p), out["channels"].ctypes.data_as(_c_i32p),
+                                     out["bitrate"].ctypes.data_as(_c_i32p), out["status"].ctypes.data_as(_c_i32p))
+        self._check(rc, "m3s_decode_scan")
+        self._scan = out
+        return out
+
+    def decode_reveal(self):
+        """Table ids [frames, 12] and the per-file reveal bit strings of the last scan."""
+        sc = self._scan
+        total = int(sc["n_frames"].sum())
+        ids = np.zeros((max(total, 1), 12), np.uint8)
+        bits = np.zeros(max(total, 1) * 12, np.uint8)
+        ln = np.zeros(len(sc["n_frames"]), np.int64)
+        rc = self._L.m3s_decode_reveal(self._h, _ptr(ids), _ptr(bits), M3S_MEM_HOST, ln.ctypes.data_as(_c_i64p))
+        self._check(rc, "m3s_decode_reveal")
+        base = np.concatenate([[0], np.cumsum(sc["n_frames"])])
+        strings = [bits[12 * base[i]: 12 * base[i] + ln[i]].tobytes().decode("ascii") for i in range(len(ln))]
+        return ids[:total], strings
+
+    def decode_run(self, pcm=None, pcm_off=None, spectra=False, as_float=False):
+        """D1-D3 of the last scan.  With pcm=None a host numpy buffer is allocated and returned."""
+        sc = self._scan
+        elems = sc["pcm_rows"] * np.maximum(sc["channels"], 1)
+        total = int(elems.sum())
+        total_frames = int(sc["n_frames"].sum())
+        if pcm is None:
+            pcm = np.zeros(max(total, 1), np.float32 if as_float else np.int16)
+        po, po_p = (None, None) if pcm_off is None else _i64(pcm_off)
+        sp = None
+        if spectra is True:
+            sp = np.zeros((max(total_frames, 1), 2, 2, 576), np.int16)
+        elif spectra is not False and spectra is not None:
+            sp = spectra
+        rc = self._L.m3s_decode_run(self._h, _ptr(pcm), _mem_of(pcm), po_p, _ptr(sp), M3S_DEC_PCM_FLOAT if as_float else 0)
+        self._check(rc, "m3s_decode_run")
+        return pcm, sp
+
+    # ------------------------------------------------------------------ encode
+    def encode(self, pcm, n_samples, sample_rate, bitrate_kbps, payloads=None, pcm_off=None, mp3_out=None, taps=False):
+        """E1-E3 over a batch of int16 stereo clips laid end to end in `pcm` (numpy or torch, host or cuda)."""
+        L = self._L
+        n = len(n_samples)
+        ns, ns_p = _i64(n_samples)
+        if pcm_off is None:
+            pcm_off = np.concatenate([[0], np.cumsum(ns * 2)])[:-1]
+        po, po_p = _i64(pcm_off)
+        bounds = np.array([L.m3s_encode_bound(int(s), sample_rate, bitrate_kbps) for s in ns], np.int64)
+        mo, mo_p = _i64(np.concatenate([[0], np.cumsum(bounds)])[:-1])
+        mc, mc_p = _i64(bounds)
+        mem = _mem_of(pcm)
+        if mp3_out is None:
+            if mem == M3S_MEM_DEVICE:
+                import torch
+                mp3_out = torch.zeros(int(bounds.sum()) + 16, dtype=torch.uint8, device=pcm.device)
+            else:
+                mp3_out = np.zeros(int(bounds.sum()) + 16, np.uint8)
+        if payloads is not None and any(len(p) for p in payloads):
+            pl = np.frombuffer("".join(payloads).encode("ascii"), dtype=np.uint8).copy()
+            ploff, ploff_p = _i64(np.concatenate([[0], np.cumsum([len(p) for p in payloads])]))
+            pl_p = _ptr(pl)
+        else:
+            pl, ploff, ploff_p, pl_p = None, None, None, None
+        out_len = np.zeros(n, np.int64)
+        hoff = np.zeros(n, np.int64)
+        rc = L.m3s_encode(self._h, _ptr(pcm), mem, po_p, ns_p, n, sample_rate, bitrate_kbps, pl_p, ploff_p, _ptr(mp3_out),
+                          mo_p, mc_p, out_len.ctypes.data_as(_c_i64p), hoff.ctypes.data_as(_c_i64p))
+        self._check(rc, "m3s_encode")
+        res = dict(mp3=mp3_out, mp3_off=mo, out_len=out_len, hide_str_offset=hoff)
+        if taps:
+            nf = int((ns // 1152).sum())
+            res["mdct"] = np.zeros((nf, 2, 2, 576), np.int32)
+            res["ix"] = np.zeros((nf, 2, 2, 576), np.int32)
+            res["info"] = np.zeros((nf, 2, 2, 16), np.int32)
+            res["scfsi"] = np.zeros((nf, 2, 4), np.int32)
+            self._check(L.m3s_encode_taps(self._h, _ptr(res["mdct"]), _ptr(res["ix"]), _ptr(res["info"]), _ptr(res["scfsi"])),
+                        "m3s_encode_taps")
+        return res
+
+
+_default = {}
+
+
+def default_handle(device: int = 0) -> Handle:
+    """Process-wide handle used by the single-file classes (MP3Parser / MP3Encoder)."""
+    if device not in _default:
+        _default[device] = Handle(device)
+    return _default[device]
