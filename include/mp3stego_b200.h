@@ -136,6 +136,29 @@ M3S_API int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
  * count1table_select, address1..3, quantizerStepSize, padding, hide_str_offset-after-frame. */
 M3S_API int m3s_encode_taps(m3s_handle_t h, int32_t *mdct, int32_t *ix, int32_t *info, int32_t *scfsi);
 
+/* ---------------------------------------------------------------- timing
+ * Optional per-kernel device timing used by bench.py's roofline line: when enabled every kernel launch of
+ * the handle is bracketed by a cudaEvent pair on the launching stream.  m3s_timing_get synchronises the
+ * stream and returns the accumulated device milliseconds and launch count of kernel `kernel_id`
+ * (launch counts are kept even while timing is disabled). m3s_timing_enable(…, on) also resets both. */
+enum {
+    M3S_K_WALK = 0,      /* D0a frame walk (one thread per file) */
+    M3S_K_SIDEINFO,      /* D0b side-info parse + D4 reveal bits (one thread per frame) */
+    M3S_K_STRIP,         /* main-data compaction through the bit reservoir */
+    M3S_K_HUFF,          /* D1 scalefactor + Huffman decode */
+    M3S_K_SPEC_EXPORT,   /* parity tap */
+    M3S_K_HYBRID,        /* D2+D3 requantize .. polyphase synthesis .. int16 */
+    M3S_K_ENC_ANALYSIS,  /* E1 polyphase analysis + MDCT + alias (fixed point) */
+    M3S_K_ENC_RATE,      /* E2 per-granule rate loop incl. table selection + stego swap */
+    M3S_K_ENC_RESOLVE,   /* E2b per-clip sequential offset scan over granule variants */
+    M3S_K_ENC_PACK,      /* E3 side-info + main-data bit packing */
+    M3S_K_ENC_AUX,       /* small helper kernels of the encoder */
+    M3S_K_COUNT
+};
+M3S_API int m3s_timing_enable(m3s_handle_t h, int on);
+M3S_API int m3s_timing_get(m3s_handle_t h, int kernel_id, double *total_ms, int64_t *launches);
+M3S_API const char *m3s_kernel_name(int kernel_id);
+
 /* ------------------------------------------------------------- diagnostics */
 /* sha-free table export used by tests/test_tables.py: copies table `which` (see m3s_table_id) into out. */
 enum {

@@ -144,6 +144,13 @@ struct m3s_ctx {
     cudaStream_t own_stream = nullptr;
     std::string err;
     int64_t launches = 0;
+    // ---- optional per-kernel device timing (m3s_timing_enable): cudaEvent pairs on the launching stream
+    bool timing = false;
+    struct Timed { int id; cudaEvent_t e0, e1; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> ev_pool;
+    double k_ms[M3S_K_COUNT] = {0};
+    int64_t k_launches[M3S_K_COUNT] = {0};
     M3sDevTables *d_tab = nullptr;
     int sm_count = 148;
 
@@ -165,6 +172,8 @@ struct m3s_ctx {
 };
 
 int m3s_fail(m3s_ctx *h, int code, const char *fmt, ...);
+void m3s_time_begin(m3s_ctx *h, int id);
+void m3s_time_end(m3s_ctx *h);
 int m3s_buf_reserve(m3s_ctx *h, M3sBuf &b, size_t bytes);
 
 #define M3S_CUDA(h, call)                                                                             \
@@ -175,9 +184,17 @@ int m3s_buf_reserve(m3s_ctx *h, M3sBuf &b, size_t bytes);
                             __FILE__, __LINE__);                                                      \
     } while (0)
 
+// M3S_KBEGIN(h, id); kernel<<<...>>>(...); M3S_LAUNCH_CHECK(h);
+#define M3S_KBEGIN(h, id)                  \
+    do {                                   \
+        (h)->k_launches[id]++;             \
+        if ((h)->timing) m3s_time_begin((h), (id)); \
+    } while (0)
+
 #define M3S_LAUNCH_CHECK(h)                                                                           \
     do {                                                                                              \
         (h)->launches++;                                                                              \
+        if ((h)->timing) m3s_time_end(h);                                                                              \
         cudaError_t e__ = cudaGetLastError();                                                         \
         if (e__ != cudaSuccess)                                                                       \
             return m3s_fail((h), M3S_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \

@@ -250,6 +250,8 @@ extern "C" int m3s_create(int device, m3s_handle_t *out)
     return M3S_OK;
 }
 
+static void timing_resolve(m3s_ctx *h);
+
 static void free_buf(M3sBuf &b)
 {
     if (b.p) cudaFree(b.p);
@@ -267,6 +269,8 @@ extern "C" int m3s_destroy(m3s_handle_t h)
                       &h->b_reveal, &h->b_work, &h->b_pcm_stage, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
                       &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad};
     for (M3sBuf *b : bufs) free_buf(*b);
+    timing_resolve(h);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->d_tab) cudaFree(h->d_tab);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -292,6 +296,75 @@ extern "C" int m3s_synchronize(m3s_handle_t h)
 }
 
 extern "C" int64_t m3s_launch_count(m3s_handle_t h) { return h ? h->launches : -1; }
+
+// ------------------------------------------------------------------------------------------------
+// per-kernel device timing (bench.py roofline): event pairs on the launching stream, resolved lazily
+// ------------------------------------------------------------------------------------------------
+static cudaEvent_t take_event(m3s_ctx *h)
+{
+    if (!h->ev_pool.empty()) {
+        cudaEvent_t e = h->ev_pool.back();
+        h->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void m3s_time_begin(m3s_ctx *h, int id)
+{
+    m3s_ctx::Timed t;
+    t.id = id;
+    t.e0 = take_event(h);
+    t.e1 = take_event(h);
+    cudaEventRecord(t.e0, h->stream);
+    h->timed.push_back(t);
+}
+
+void m3s_time_end(m3s_ctx *h)
+{
+    if (!h->timed.empty()) cudaEventRecord(h->timed.back().e1, h->stream);
+}
+
+static void timing_resolve(m3s_ctx *h)
+{
+    cudaStreamSynchronize(h->stream);
+    for (auto &t : h->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) h->k_ms[t.id] += ms;
+        h->ev_pool.push_back(t.e0);
+        h->ev_pool.push_back(t.e1);
+    }
+    h->timed.clear();
+}
+
+extern "C" int m3s_timing_enable(m3s_handle_t h, int on)
+{
+    if (!h) return M3S_ERR_ARG;
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    timing_resolve(h);
+    for (int i = 0; i < M3S_K_COUNT; i++) { h->k_ms[i] = 0; h->k_launches[i] = 0; }
+    h->timing = on != 0;
+    return M3S_OK;
+}
+
+extern "C" int m3s_timing_get(m3s_handle_t h, int kernel_id, double *total_ms, int64_t *launches)
+{
+    if (!h || kernel_id < 0 || kernel_id >= M3S_K_COUNT) return M3S_ERR_ARG;
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    timing_resolve(h);
+    if (total_ms) *total_ms = h->k_ms[kernel_id];
+    if (launches) *launches = h->k_launches[kernel_id];
+    return M3S_OK;
+}
+
+extern "C" const char *m3s_kernel_name(int kernel_id)
+{
+    static const char *names[M3S_K_COUNT] = {"k_walk", "k_sideinfo", "k_strip", "k_huff", "k_spec_export", "k_hybrid",
+                                             "k_enc_analysis", "k_enc_rate", "k_enc_resolve", "k_enc_pack", "k_enc_aux"};
+    return kernel_id >= 0 && kernel_id < M3S_K_COUNT ? names[kernel_id] : "?";
+}
 
 // ------------------------------------------------------------------------------------------------
 // table export for tests/test_tables.py (host-only, needs no GPU)

@@ -828,7 +828,8 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     if ((rc = m3s_buf_reserve(h, h->b_fouts, sizeof(M3sFileOut) * n_files))) return rc;
     M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
     const int wb = 32, wg = (n_files + wb - 1) / wb;
-    k_walk<false><<<wg, wb, 0, h->stream>>>(h->d_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p, n_files,
+    M3S_KBEGIN(h, M3S_K_WALK);
+        k_walk<false><<<wg, wb, 0, h->stream>>>(h->d_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p, n_files,
                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     M3S_LAUNCH_CHECK(h);
     M3S_CUDA(h, cudaMemcpyAsync(h->fouts.data(), h->b_fouts.p, sizeof(M3sFileOut) * n_files, cudaMemcpyDeviceToHost, h->stream));
@@ -856,11 +857,13 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     if ((rc = m3s_buf_reserve(h, h->b_tabids, 12 * nf))) return rc;
     if ((rc = m3s_buf_reserve(h, h->b_reveal, 12 * nf))) return rc;
     M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
-    k_walk<true><<<wg, wb, 0, h->stream>>>(h->d_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p, n_files,
+    M3S_KBEGIN(h, M3S_K_WALK);
+        k_walk<true><<<wg, wb, 0, h->stream>>>(h->d_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p, n_files,
                                            (int64_t *)h->b_fr_pos.p, (uint32_t *)h->b_fr_P.p, (uint32_t *)h->b_fr_meta.p,
                                            (uint32_t *)h->b_fr_carry.p, (uint32_t *)h->b_fr_reveal.p, (int32_t *)h->b_fr_file.p);
     M3S_LAUNCH_CHECK(h);
     if (fb > 0) {
+        M3S_KBEGIN(h, M3S_K_SIDEINFO);
         k_sideinfo<<<(unsigned)((fb + 127) / 128), 128, 0, h->stream>>>(
             h->d_bytes, (const M3sFileRec *)h->b_files.p, fb, (const int64_t *)h->b_fr_pos.p, (const uint32_t *)h->b_fr_P.p,
             (const uint32_t *)h->b_fr_meta.p, (const uint32_t *)h->b_fr_carry.p, (const uint32_t *)h->b_fr_reveal.p,
@@ -947,11 +950,13 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
     M3S_CUDA(h, cudaMemcpyAsync(h->b_work.p, work.data(), sizeof(M3sWork) * work.size(), cudaMemcpyHostToDevice, h->stream));
     M3S_CUDA(h, cudaMemsetAsync(h->b_S.p, 0, (size_t)h->s_bytes, h->stream));
     int64_t total_bytes = h->files[h->n_files - 1].end;
-    k_strip<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, h->stream>>>(
+    M3S_KBEGIN(h, M3S_K_STRIP);
+        k_strip<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, h->stream>>>(
         h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, nf, (const int64_t *)h->b_fr_pos.p,
         (const uint32_t *)h->b_fr_P.p, (const uint32_t *)h->b_fr_meta.p, (const int32_t *)h->b_fr_file.p, (uint8_t *)h->b_S.p);
     M3S_LAUNCH_CHECK(h);
-    k_huff<<<(unsigned)((4 * nf + HUFF_THREADS - 1) / HUFF_THREADS), HUFF_THREADS, 0, h->stream>>>(
+    M3S_KBEGIN(h, M3S_K_HUFF);
+        k_huff<<<(unsigned)((4 * nf + HUFF_THREADS - 1) / HUFF_THREADS), HUFF_THREADS, 0, h->stream>>>(
         (const uint8_t *)h->b_S.p, (const M3sUnitRec *)h->b_units.p, 4 * nf, h->d_tab, (uint32_t *)h->b_spec.p, (uint8_t *)h->b_sf.p);
     M3S_LAUNCH_CHECK(h);
     if (spectra) {
@@ -960,6 +965,7 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
             if ((rc = m3s_buf_reserve(h, h->b_spec_export, (size_t)nf * 4 * 576 * 2))) return rc;
             d_sp = (int16_t *)h->b_spec_export.p;
         }
+        M3S_KBEGIN(h, M3S_K_SPEC_EXPORT);
         k_spec_export<<<(unsigned)((nf * 288 * 4 + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)h->b_spec.p, nf, d_sp);
         M3S_LAUNCH_CHECK(h);
         if (mem == M3S_MEM_HOST)
@@ -968,11 +974,13 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
     const size_t smem = sizeof(HybSmem);
     if (fl) {
         M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        M3S_KBEGIN(h, M3S_K_HYBRID);
         k_hybrid<true><<<(unsigned)work.size(), HYB_THREADS, smem, h->stream>>>(
             (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)h->b_units.p, (const uint8_t *)h->b_sf.p,
             (const uint32_t *)h->b_fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, d_pcm);
     } else {
         M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        M3S_KBEGIN(h, M3S_K_HYBRID);
         k_hybrid<false><<<(unsigned)work.size(), HYB_THREADS, smem, h->stream>>>(
             (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)h->b_units.p, (const uint8_t *)h->b_sf.p,
             (const uint32_t *)h->b_fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, d_pcm);

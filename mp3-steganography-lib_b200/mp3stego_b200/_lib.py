@@ -39,7 +39,11 @@ SYMBOLS = [
     ("m3s_encode_taps", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]),
     ("m3s_table_export", ctypes.c_int64, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]),
+    ("m3s_timing_enable", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    ("m3s_timing_get", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), _c_i64p]),
+    ("m3s_kernel_name", ctypes.c_char_p, [ctypes.c_int]),
 ]
+M3S_K_COUNT = 11
 
 _lib = None
 
@@ -126,6 +130,19 @@ class Handle:
     def launches(self) -> int:
         return int(self._L.m3s_launch_count(self._h))
 
+    def timing_enable(self, on=True):
+        self._check(self._L.m3s_timing_enable(self._h, 1 if on else 0), "m3s_timing_enable")
+
+    def timing(self):
+        """{kernel name: (device ms accumulated, launches)} since the last timing_enable()."""
+        out = {}
+        for k in range(M3S_K_COUNT):
+            ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+            self._check(self._L.m3s_timing_get(self._h, k, ctypes.byref(ms), ctypes.byref(n)), "m3s_timing_get")
+            if n.value:
+                out[self._L.m3s_kernel_name(k).decode()] = (ms.value, n.value)
+        return out
+
     # ------------------------------------------------------------------ decode
     def decode_scan(self, data, file_off, audio_start=None):
         """D0 + D4 over a batch.  `data`: uint8 numpy array / torch tensor (host or cuda) of all files end to end."""
@@ -158,6 +175,15 @@ class Handle:
         base = np.concatenate([[0], np.cumsum(sc["n_frames"])])
         strings = [bits[12 * base[i]: 12 * base[i] + ln[i]].tobytes().decode("ascii") for i in range(len(ln))]
         return ids[:total], strings
+
+    def decode_reveal_into(self, table_ids, reveal_bits):
+        """Like decode_reveal but into caller buffers (numpy / torch, host or cuda; either may be None).
+        Returns the per-file reveal string lengths; file i's chars start at 12 * (frames of files < i)."""
+        ln = np.zeros(len(self._scan["n_frames"]), np.int64)
+        mem = _mem_of(table_ids if table_ids is not None else reveal_bits)
+        rc = self._L.m3s_decode_reveal(self._h, _ptr(table_ids), _ptr(reveal_bits), mem, ln.ctypes.data_as(_c_i64p))
+        self._check(rc, "m3s_decode_reveal")
+        return ln
 
     def decode_run(self, pcm=None, pcm_off=None, spectra=False, as_float=False):
         """D1-D3 of the last scan.  With pcm=None a host numpy buffer is allocated and returned."""

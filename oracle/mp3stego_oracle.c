@@ -1302,3 +1302,25 @@ ORA_API void ora_enc_free(ora_enc_result *r)
 /* accessors for ctypes */
 ORA_API int ora_side_fields(void) { return ORA_SIDE_FIELDS; }
 ORA_API int ora_enc_fields(void) { return ORA_ENC_FIELDS; }
+
+/* SURVEY.md A.E10 known answers for the fixed-point primitives (encoder/util.py:123-172), measured on the reference.
+ * Returns 0 when all hold, else the 1-based index of the first failing one. */
+ORA_API int ora_fixed_kat(void)
+{
+    if (e_mul(-1, 1) != -1) return 1;
+    if (e_mul(2147483647, 2147483647) != 1073741823) return 2;
+    if (e_mul((int32_t)(-2147483647 - 1), 2147483647) != -1073741824) return 3;
+    if (e_mulr(-3, 2147483647) != -1) return 4;
+    if (e_mulr(3, 2147483647) != 1) return 5;
+    if (e_mulsr((int32_t)(-2147483647 - 1), (int32_t)(-2147483647 - 1)) != (int32_t)(-2147483647 - 1)) return 6;
+    if (e_mulsr(46341, 46341) != 1) return 7;
+    if (e_mulsr(-7, 3) != 0) return 8;
+    {
+        int64_t are = -5, aim = 7, bre = 2147483647, bim = -1073741824;
+        int32_t tre = (int32_t)((are * bre - aim * bim) >> 31);
+        int32_t dim = (int32_t)((are * bim + aim * bre) >> 31);
+        if (tre != -2 || dim != 9) return 9;
+    }
+    if (ORA_ENC_CA[0] != -1104871221 || ORA_ENC_CA[7] != -7945635 || ORA_ENC_CS[0] != 1841452035 || ORA_ENC_CS[7] != 2147468947) return 10;
+    return 0;
+}

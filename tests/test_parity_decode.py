@@ -1,0 +1,158 @@
+"""GPU: decode + reveal parity of the CUDA path (through the C ABI) against the oracle and the reference-generated
+golden vectors.  Gates (BASELINE.json north_star): integer spectra, table ids and reveal bits bit-exact;
+PCM within 1 LSB at 16 bit and 1e-5 abs in float."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SYNTH_CASES, golden_path, load_npz, synth_wav
+
+pytestmark = pytest.mark.gpu
+
+PCM_TOL_LSB = 1       # int16 samples: |cuda - reference| <= 1
+PCM_TOL_FLOAT = 1e-5  # pre-quantisation float samples
+
+
+def _decode_batch(handle, blobs, audio_start=None, spectra=True, as_float=False):
+    data = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])])
+    sc = handle.decode_scan(data, off, audio_start)
+    ids, bits = handle.decode_reveal()
+    pcm, sp = handle.decode_run(spectra=spectra, as_float=as_float)
+    fb = np.concatenate([[0], np.cumsum(sc["n_frames"])])
+    eb = np.concatenate([[0], np.cumsum(sc["pcm_rows"] * np.maximum(sc["channels"], 1))])
+    out = []
+    for i in range(len(blobs)):
+        ch = max(int(sc["channels"][i]), 1)
+        out.append(dict(n_frames=int(sc["n_frames"][i]), status=int(sc["status"][i]), bitrate=int(sc["bitrate"][i]),
+                        sample_rate=int(sc["sample_rate"][i]), channels=int(sc["channels"][i]),
+                        ids=ids[fb[i]:fb[i + 1]], bits=bits[i],
+                        spectra=None if sp is None else sp[fb[i]:fb[i + 1]].astype(np.int32),
+                        pcm=pcm[eb[i]:eb[i + 1]].reshape(-1, ch)))
+    return out
+
+
+def _check(got, ref, pcm16=True):
+    assert got["n_frames"] == ref["n_frames"]
+    if got["spectra"] is not None:
+        assert np.array_equal(got["spectra"], ref["spectra"]), "integer spectra differ"
+    assert np.array_equal(got["ids"], ref["tables"]), "table ids differ"
+    assert got["bits"] == ref["bits"], "reveal bits differ"
+    if pcm16:
+        assert got["pcm"].shape == ref["pcm16"].shape
+        d = np.abs(got["pcm"].astype(np.int32) - ref["pcm16"].astype(np.int32))
+        assert d.max() <= PCM_TOL_LSB, f"PCM off by {d.max()} LSB"
+    else:
+        assert got["pcm"].shape == ref["pcm"].shape
+        assert np.abs(got["pcm"].astype(np.float64) - ref["pcm"]).max() <= PCM_TOL_FLOAT
+
+
+def test_test_mp3_vs_reference_golden(handle):
+    """configs[0]: tests/test.mp3 against the values the unmodified reference produced."""
+    z = load_npz("ref_test_mp3.npz")
+    got = _decode_batch(handle, [open(golden_path("test.mp3"), "rb").read()])[0]
+    assert got["n_frames"] == 36 and got["bitrate"] == 320000 and got["sample_rate"] == 44100
+    assert np.array_equal(got["spectra"], z["spectra"].astype(np.int32))
+    assert np.array_equal(got["ids"], z["tables"])
+    assert got["bits"] == str(z["bits"])
+    d = np.abs(got["pcm"].astype(np.int32) - z["pcm16"].astype(np.int32))
+    assert d.max() <= PCM_TOL_LSB
+    gotf = _decode_batch(handle, [open(golden_path("test.mp3"), "rb").read()], spectra=False, as_float=True)[0]
+    for k, f in enumerate(z["pcm64_frames"]):
+        df = np.abs(gotf["pcm"][f * 1152:(f + 1) * 1152].astype(np.float64) - z["pcm64"][k * 1152:(k + 1) * 1152])
+        assert df.max() <= PCM_TOL_FLOAT
+
+
+@pytest.mark.parametrize("case", SYNTH_CASES)
+def test_synth_vs_reference_golden(handle, case):
+    z = load_npz(f"ref_synth_{case}.npz")
+    got = _decode_batch(handle, [z["mp3"].tobytes()])[0]
+    assert got["n_frames"] == int(z["dec_n_frames"])
+    assert np.array_equal(got["spectra"], z["dec_spectra"].astype(np.int32))
+    assert np.array_equal(got["ids"], z["dec_tables"])
+    assert got["bits"] == str(z["dec_bits"])
+    assert np.abs(got["pcm"].astype(np.int32) - z["dec_pcm16"].astype(np.int32)).max() <= PCM_TOL_LSB
+
+
+def test_batch_of_all_goldens_vs_oracle(handle, oracle):
+    """Every golden MP3 in ONE batch (mixed bitrates / lengths, incl. stream-writer cases) vs the oracle."""
+    blobs = [open(golden_path("test.mp3"), "rb").read()]
+    blobs += [np.load(p)["mp3"].tobytes() for p in sorted(glob.glob(os.path.join(GOLDEN, "ref_synth_*.npz")))]
+    blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "ref_test_*.mp3")))]
+    blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "stream_*.mp3")))]
+    res = _decode_batch(handle, blobs)
+    resf = _decode_batch(handle, blobs, spectra=False, as_float=True)
+    for b, g, gf in zip(blobs, res, resf):
+        ref = oracle.decode(b)
+        _check(g, ref)
+        _check(gf, ref, pcm16=False)
+
+
+def test_long_file_run_boundaries(handle, oracle):
+    """Files longer than one CTA run (32 frames): every run boundary re-decodes one warm-up frame;
+    the result must equal the sequential oracle everywhere."""
+    wav = synth_wav(21, 150)
+    blobs = [oracle.encode(wav, 44100, br, "", taps=False)["mp3"] for br in (320, 128, 64)]
+    for g, b in zip(_decode_batch(handle, blobs), blobs):
+        _check(g, oracle.decode(b))
+
+
+def test_id3_and_trailing_junk(handle, oracle):
+    """ID3v2 skip (decoder.py:29-33) and the bad-sync stop that repeats the last frame once (MP3_Parser.py:68-79)."""
+    z = load_npz("ref_synth_s12_320_plain.npz")
+    mp3 = z["mp3"].tobytes()
+    body = b"\x00" * 57
+    size = len(body)
+    tag = b"ID3\x03\x00\x00" + bytes([(size >> 21) & 127, (size >> 14) & 127, (size >> 7) & 127, size & 127]) + body
+    with_tag = tag + mp3
+    with_junk = mp3 + b"TAG" + b"\x00" * 125
+    truncated = mp3[:-300]
+    blobs = [with_tag, with_junk, truncated, mp3]
+    starts = [oracle.id3_offset(b) for b in blobs]
+    assert starts[0] == 67
+    res = _decode_batch(handle, blobs, audio_start=starts)
+    for b, s, g in zip(blobs, starts, res):
+        ref = oracle.decode(b, s)
+        _check(g, ref)
+    assert res[1]["status"] & 4 and res[1]["pcm"].shape[0] == 1152 * (res[1]["n_frames"] + 1)
+
+
+def test_no_sync_and_empty(handle, oracle):
+    z = load_npz("ref_synth_s13_64_hide.npz")
+    mp3 = z["mp3"].tobytes()
+    blobs = [b"RIFFxxxxWAVE" + b"\x00" * 100, mp3, b"", b"\xff"]
+    res = _decode_batch(handle, blobs)
+    assert res[0]["n_frames"] == 0 and res[0]["status"] & 1
+    assert res[2]["n_frames"] == 0 and res[3]["n_frames"] == 0
+    _check(res[1], oracle.decode(mp3))
+
+
+def test_full_size_properties(handle, oracle):
+    """BASELINE configs[1] shape (3-minute 320 kbps stereo files), checked through size-independent properties:
+    a long file built by concatenating self-contained clips (reference-encoder frames have main_data_begin = 0)
+    must decode, segment by segment, to the PCM of the clips decoded alone -- except the first frame of every
+    segment, whose overlap/synthesis history comes from the preceding clip -- and reveal the concatenated bits."""
+    clips = [oracle.encode(synth_wav(100 + s, 65), 44100, 320, "", taps=False)["mp3"] for s in range(4)]
+    # a 4-byte-flush truncated clip (A.E8) is 0-3 bytes short: pad the last frame so the next header lands right
+    full = []
+    for c in clips:
+        ref = oracle.decode(c)
+        last = int(ref["frame_off"][-1])
+        fs = (144 * 320000) // 44100 + ((c[last + 2] >> 1) & 1)
+        full.append(c + b"\x00" * (last + fs - len(c)))
+    order = np.random.default_rng(0).integers(0, 4, size=106)   # 106 * 65 = 6,890 frames = 179.98 s
+    big = b"".join(full[i] for i in order)
+    got = _decode_batch(handle, [big, full[0]], spectra=False)
+    assert got[0]["n_frames"] == 6890
+    singles = [oracle.decode(c) for c in full]
+    bits = "".join(singles[i]["bits"] for i in order)
+    assert got[0]["bits"] == bits
+    pos = 0
+    for i in order:
+        seg = got[0]["pcm"][pos * 1152:(pos + 65) * 1152].astype(np.int32)
+        ref = singles[i]["pcm16"].astype(np.int32)
+        assert np.abs(seg[1152:] - ref[1152:]).max() <= PCM_TOL_LSB
+        pos += 65
+    _check(got[1], singles[0])
