@@ -142,7 +142,8 @@ M3S_API int m3s_encode_taps(m3s_handle_t h, int32_t *mdct, int32_t *ix, int32_t 
  * stream and returns the accumulated device milliseconds and launch count of kernel `kernel_id`
  * (launch counts are kept even while timing is disabled). m3s_timing_enable(…, on) also resets both. */
 enum {
-    M3S_K_WALK = 0,      /* D0a frame walk (one thread per file) */
+    M3S_K_WALK = 0,      /* D0a frame walk (one warp per file, speculative 32-frame windows) */
+    M3S_K_FSCAN,         /* D0a' per-file scans: payload prefix, carried table_select[2], reveal offsets */
     M3S_K_SIDEINFO,      /* D0b side-info parse + D4 reveal bits (one thread per frame) */
     M3S_K_STRIP,         /* main-data compaction through the bit reservoir */
     M3S_K_HUFF,          /* D1 scalefactor + Huffman decode */

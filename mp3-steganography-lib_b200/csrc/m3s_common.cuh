@@ -24,6 +24,7 @@ struct M3sFileRec {
     int32_t flags;        // M3S_FILE_* bits
     int32_t channels;
     int32_t pad;
+    int64_t tmp_base;     // first slot of the file in the walk's temporary frame-position array
 };
 
 // Written by the walk kernel, one per file.
@@ -162,7 +163,7 @@ struct m3s_ctx {
     const uint8_t *d_bytes = nullptr;  // device pointer to the batch bytes (caller's or staged)
     std::vector<M3sFileRec> files;
     std::vector<M3sFileOut> fouts;
-    M3sBuf b_stage_in, b_files, b_fouts, b_fr_pos, b_fr_P, b_fr_meta, b_fr_carry, b_fr_reveal, b_fr_file;
+    M3sBuf b_stage_in, b_files, b_fouts, b_tmp_pos, b_fr_pos, b_fr_P, b_fr_meta, b_fr_carry, b_fr_reveal, b_fr_file;
     M3sBuf b_units, b_sf, b_S, b_spec, b_tabids, b_reveal, b_work, b_pcm_stage, b_spec_export;
     // ---- encode state
     M3sBuf e_pcm, e_clips, e_mdct, e_ix, e_info, e_gran, e_out, e_payload, e_misc, e_pad;

@@ -264,7 +264,7 @@ extern "C" int m3s_destroy(m3s_handle_t h)
     if (!h) return M3S_ERR_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    M3sBuf *bufs[] = {&h->b_stage_in, &h->b_files, &h->b_fouts, &h->b_fr_pos, &h->b_fr_P, &h->b_fr_meta, &h->b_fr_carry,
+    M3sBuf *bufs[] = {&h->b_stage_in, &h->b_files, &h->b_fouts, &h->b_tmp_pos, &h->b_fr_pos, &h->b_fr_P, &h->b_fr_meta, &h->b_fr_carry,
                       &h->b_fr_reveal, &h->b_fr_file, &h->b_units, &h->b_sf, &h->b_S, &h->b_spec, &h->b_tabids,
                       &h->b_reveal, &h->b_work, &h->b_pcm_stage, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
                       &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad};
@@ -361,7 +361,7 @@ extern "C" int m3s_timing_get(m3s_handle_t h, int kernel_id, double *total_ms, i
 
 extern "C" const char *m3s_kernel_name(int kernel_id)
 {
-    static const char *names[M3S_K_COUNT] = {"k_walk", "k_sideinfo", "k_strip", "k_huff", "k_spec_export", "k_hybrid",
+    static const char *names[M3S_K_COUNT] = {"k_walk", "k_fscan", "k_sideinfo", "k_strip", "k_huff", "k_spec_export", "k_hybrid",
                                              "k_enc_analysis", "k_enc_rate", "k_enc_resolve", "k_enc_pack", "k_enc_aux"};
     return kernel_id >= 0 && kernel_id < M3S_K_COUNT ? names[kernel_id] : "?";
 }

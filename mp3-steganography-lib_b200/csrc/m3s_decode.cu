@@ -54,84 +54,240 @@ __device__ __forceinline__ int parse_header(uint32_t b1, uint32_t b2, uint32_t b
 }
 
 // ================================================================================================
-// D0a: sequential frame walk, one thread per file (MP3_Parser.py:57-85).  Pass 1 (WRITE=false) only
-// counts; pass 2 also emits per-frame records, the carried table_select[2] (A.D3) and reveal offsets.
+// D0a: frame walk, one WARP per file (MP3_Parser.py:57-85).  The chain offset -> header -> frame size ->
+// next offset is serial, so the warp hides the memory latency by speculation: lane k prefetches a 64-byte
+// window where frame k of the next 32 is expected for a constant frame size (its start can only drift by
+// the <= 31 padding bytes of the frames before it), then the 32 headers are resolved from shared memory
+// with no further global round trip.  A header outside its window (VBR, bitrate change) is fetched
+// directly.  Writes file-relative frame positions to a temporary array and per-file totals.
 // ================================================================================================
-template <bool WRITE>
-__global__ void k_walk(const uint8_t *__restrict__ bytes, const M3sFileRec *__restrict__ files, M3sFileOut *fouts,
-                       int n_files, int64_t *fr_pos, uint32_t *fr_P, uint32_t *fr_meta, uint32_t *fr_carry,
-                       uint32_t *fr_reveal, int32_t *fr_file)
+#define WALK_WARPS 4
+#define WALK_WIN 64
+#define WALK_STRIDE 17  // words per lane window (64 B + 4 B pad: conflict-free)
+
+__device__ __forceinline__ uint4 load16_clipped(const uint8_t *bytes, int64_t p, int64_t fend, int64_t total_bytes)
 {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    // 16 bytes at p (p + addr 16-aligned); bytes at or beyond fend read as zero; never touches memory beyond total_bytes
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p >= fend) return v;
+    if (p >= 0 && p + 16 <= total_bytes) {
+        v = __ldg((const uint4 *)(bytes + p));
+        if (p + 16 > fend) {
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int64_t q = p + 4 * i;
+                if (q >= fend) w[i] = 0u;
+                else if (q + 4 > fend) w[i] &= 0xFFFFFFFFu >> (8 * (int)(q + 4 - fend));
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int i = 0; i < 16; i++) {
+            int64_t q = p + i;
+            if (q >= 0 && q < fend) w[i >> 2] |= (uint32_t)__ldg(bytes + q) << (8 * (i & 3));
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(32 * WALK_WARPS)
+k_walk(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec *__restrict__ files, M3sFileOut *fouts,
+       int n_files, uint32_t *__restrict__ tmp_pos)
+{
+    __shared__ uint32_t s_win[WALK_WARPS][32 * WALK_STRIDE];
+    const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;
+    const int f = blockIdx.x * WALK_WARPS + wip;
     if (f >= n_files) return;
-    M3sFileRec fr = files[f];
-    int64_t off = fr.audio, fend = fr.end;
+    const M3sFileRec fr = files[f];
+    int64_t off = fr.audio;
+    const int64_t fend = fr.end;
     M3sFileOut o;
     o.payload_total = 0; o.n_frames = 0; o.status = 0; o.sample_rate = 0; o.channels = 0; o.bitrate = 0; o.reveal_len = 0;
     if (!(fend - off >= 2 && ldb(bytes, off, fend) == 0xFF && ldb(bytes, off + 1, fend) >= 0xE0)) {
         o.status = M3S_FILE_NO_SYNC;
-        fouts[f] = o;
+        if (lane == 0) fouts[f] = o;
         return;
     }
-    uint32_t carry = 0;  // table_select[2] currently held in each (gr, ch) slot, 5 bits per slot
-    uint32_t reveal = 0, P = 0;
-    int n = 0;
-    int64_t g = fr.frame_base;
-    while (fend > off + 4) {
-        uint32_t b0 = ldb(bytes, off, fend), b1 = ldb(bytes, off + 1, fend), b2 = ldb(bytes, off + 2, fend),
-                 b3 = ldb(bytes, off + 3, fend);
-        if (!(b0 == 0xFF && b1 >= 0xE0)) { o.status |= M3S_FILE_TRAILING_JUNK; break; }
-        M3sHdr h;
-        if (parse_header(b1, b2, b3, h) < 0) { o.status |= M3S_FILE_UNSUPPORTED; break; }
-        int64_t avail = fend - off;
-        int fs = h.frame_size < avail ? h.frame_size : (int)avail;
-        int payload = fs - h.hdrlen;
-        if (payload < 0) payload = 0;
-        if (WRITE) {
-            int64_t si = off + 4 + (h.crc_present ? 2 : 0);
-            int rb = h.mono ? 18 : 20;
-            int nz = 0;
-            for (int gr = 0; gr < 2; gr++)
-                for (int ch = 0; ch < (h.mono ? 1 : 2); ch++) {
-                    int slot = 2 * gr + ch;
-                    uint32_t ws = bits_at(bytes, si, fend, rb + 33, 1);
-                    uint32_t t0, t1, t2;
-                    if (ws) {
-                        t0 = bits_at(bytes, si, fend, rb + 37, 5);
-                        t1 = bits_at(bytes, si, fend, rb + 42, 5);
-                        t2 = (carry >> (5 * slot)) & 31u;
-                    } else {
-                        t0 = bits_at(bytes, si, fend, rb + 34, 5);
-                        t1 = bits_at(bytes, si, fend, rb + 39, 5);
-                        t2 = bits_at(bytes, si, fend, rb + 44, 5);
-                        carry = (carry & ~(31u << (5 * slot))) | (t2 << (5 * slot));
-                    }
-                    nz += (t0 != 0) + (t1 != 0) + (t2 != 0);
-                    rb += 59;
-                }
-            fr_pos[g] = off;
-            fr_P[g] = P;
-            fr_meta[g] = (uint32_t)payload | (h.crc_present ? M3S_META_CRC : 0) | ((uint32_t)h.mode << M3S_META_MODE_SHIFT) |
-                         (h.ms ? M3S_META_MS : 0) | ((uint32_t)h.sr_idx << M3S_META_SR_SHIFT) | (h.mono ? M3S_META_MONO : 0) |
-                         (n == 0 ? M3S_META_FIRST : 0) | ((uint32_t)h.hdrlen << M3S_META_HDR_SHIFT);
-            fr_carry[g] = carry;
-            fr_reveal[g] = reveal;
-            fr_file[g] = f;
-            reveal += nz;
-        }
-        P += payload;
-        o.sample_rate = h.sr;
-        o.channels = h.mono ? 1 : 2;
-        o.bitrate = h.bitrate;
-        n++;
-        g++;
-        off += h.frame_size;
+    uint32_t *win = s_win[wip];
+    const uint8_t *winb = (const uint8_t *)win;
+    const int64_t align_fix = (int64_t)((uintptr_t)bytes & 15);  // windows are aligned in the address space
+    int fs_guess = 0;
+    {
+        M3sHdr h0;
+        if (parse_header(ldb(bytes, off + 1, fend), ldb(bytes, off + 2, fend), ldb(bytes, off + 3, fend), h0) == 0)
+            fs_guess = (144 * h0.bitrate) / h0.sr;
     }
-    if (WRITE && (o.status & M3S_FILE_TRAILING_JUNK) && n > 0) fr_meta[g - 1] |= M3S_META_DUP;
+    int64_t P = 0;
+    int n = 0;
+    bool done = false;
+    while (!done) {
+        // ---- speculative prefetch
+        const int64_t want = off + (int64_t)lane * fs_guess;
+        const int64_t wbase = ((want + align_fix) & ~(int64_t)15) - align_fix;  // <= want, 16-aligned address
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 v = load16_clipped(bytes, wbase + 16 * q, fend, total_bytes);
+            uint32_t *d = win + lane * WALK_STRIDE + 4 * q;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        __syncwarp();
+        // ---- resolve up to 32 frames (uniform control flow)
+        uint32_t mypos = 0;
+        int got = 0;
+        for (int k = 0; k < 32; k++) {
+            if (!(fend > off + 4)) { done = true; break; }
+            const int64_t kbase = __shfl_sync(0xFFFFFFFFu, wbase, k);
+            uint32_t b0, b1, b2, b3;
+            const int64_t d = off - kbase;
+            if (d >= 0 && d + 4 <= WALK_WIN) {
+                const uint8_t *q = winb + k * (4 * WALK_STRIDE) + d;
+                b0 = q[0]; b1 = q[1]; b2 = q[2]; b3 = q[3];
+            } else {
+                b0 = ldb(bytes, off, fend); b1 = ldb(bytes, off + 1, fend); b2 = ldb(bytes, off + 2, fend); b3 = ldb(bytes, off + 3, fend);
+            }
+            if (!(b0 == 0xFF && b1 >= 0xE0)) { o.status |= M3S_FILE_TRAILING_JUNK; done = true; break; }
+            M3sHdr h;
+            if (parse_header(b1, b2, b3, h) < 0) { o.status |= M3S_FILE_UNSUPPORTED; done = true; break; }
+            const int64_t avail = fend - off;
+            const int fs = h.frame_size < avail ? h.frame_size : (int)avail;
+            int payload = fs - h.hdrlen;
+            if (payload < 0) payload = 0;
+            if (lane == k) mypos = (uint32_t)(off - fr.begin);
+            got++;
+            P += payload;
+            o.sample_rate = h.sr;
+            o.channels = h.mono ? 1 : 2;
+            o.bitrate = h.bitrate;
+            fs_guess = (144 * h.bitrate) / h.sr;
+            off += h.frame_size;
+        }
+        if (lane < got) tmp_pos[fr.tmp_base + n + lane] = mypos;
+        n += got;
+        __syncwarp();
+    }
     o.n_frames = n;
     o.payload_total = P;
-    o.reveal_len = reveal;
-    fouts[f] = o;
+    if (lane == 0) fouts[f] = o;
+}
+
+// ================================================================================================
+// D0a': per-file scans over the frames found by the walk, one warp per file, one frame per lane:
+// payload prefix (position in the header-stripped stream), the carried table_select[2] of window-switched
+// granules (A.D3: FrameSideInformation.py:104-107 parses only two selects, the third keeps its old value)
+// and the reveal-bit offset (number of non-zero table ids in earlier frames, util.py:67-81).
+// ================================================================================================
+#define FSCAN_STRIDE 17  // words per lane (64-byte window + pad: conflict-free)
+
+__device__ __forceinline__ uint32_t sbits(const uint8_t *w, int bitoff, int n)  // n <= 16, MSB first, from a staged window
+{
+    const uint8_t *q = w + (bitoff >> 3);
+    uint32_t v = ((uint32_t)q[0] << 16) | ((uint32_t)q[1] << 8) | (uint32_t)q[2];
+    return (v >> (24 - (bitoff & 7) - n)) & ((1u << n) - 1u);
+}
+
+__global__ void __launch_bounds__(32 * WALK_WARPS)
+k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec *__restrict__ files, M3sFileOut *fouts,
+        int n_files, const uint32_t *__restrict__ tmp_pos, int64_t *__restrict__ fr_pos, uint32_t *__restrict__ fr_P,
+        uint32_t *__restrict__ fr_meta, uint32_t *__restrict__ fr_carry, uint32_t *__restrict__ fr_reveal,
+        int32_t *__restrict__ fr_file)
+{
+    __shared__ uint32_t s_win[WALK_WARPS][32 * FSCAN_STRIDE + 4];
+    const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;
+    const int f = blockIdx.x * WALK_WARPS + wip;
+    if (f >= n_files) return;
+    const M3sFileRec fr = files[f];
+    const int64_t fend = fr.end;
+    const int64_t align_fix = (int64_t)((uintptr_t)bytes & 15);
+    uint32_t *win = s_win[wip] + lane * FSCAN_STRIDE;
+    const bool junk = (fr.flags & M3S_FILE_TRAILING_JUNK) != 0;
+    uint32_t carry_in = 0;   // 5 bits per (gr, ch) slot
+    uint32_t P_in = 0, reveal_in = 0;
+    for (int n0 = 0; n0 < fr.n_frames; n0 += 32) {
+        const int n = n0 + lane;
+        const bool valid = n < fr.n_frames;
+        uint32_t payload = 0, meta = 0, nzfix = 0, t2pack = 0, wsmask = 0xFu;
+        int64_t pos = 0;
+        uint32_t nz01 = 0;
+        if (valid) {
+            pos = fr.begin + (int64_t)tmp_pos[fr.tmp_base + n];
+            const int64_t wbase = ((pos + align_fix) & ~(int64_t)15) - align_fix;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // 64 bytes from wbase always cover header + CRC + side info (pos - wbase <= 15, <= 38 bytes)
+                const uint4 v = load16_clipped(bytes, wbase + 16 * q, fend, total_bytes);
+                win[4 * q + 0] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
+            }
+        }
+        __syncwarp();
+        if (valid) {
+            const int64_t wbase = ((pos + align_fix) & ~(int64_t)15) - align_fix;
+            const int d = (int)(pos - wbase);
+            const uint8_t *wb = (const uint8_t *)win + d;
+            M3sHdr h;
+            parse_header(wb[1], wb[2], wb[3], h);  // validated by the walk
+            const int64_t avail = fend - pos;
+            const int fs = h.frame_size < avail ? h.frame_size : (int)avail;
+            int pl = fs - h.hdrlen;
+            if (pl < 0) pl = 0;
+            payload = (uint32_t)pl;
+            meta = (uint32_t)pl | (h.crc_present ? M3S_META_CRC : 0) | ((uint32_t)h.mode << M3S_META_MODE_SHIFT) |
+                   (h.ms ? M3S_META_MS : 0) | ((uint32_t)h.sr_idx << M3S_META_SR_SHIFT) | (h.mono ? M3S_META_MONO : 0) |
+                   (n == 0 ? M3S_META_FIRST : 0) | ((uint32_t)h.hdrlen << M3S_META_HDR_SHIFT) |
+                   ((junk && n == fr.n_frames - 1) ? M3S_META_DUP : 0);
+            const int si = 4 + (h.crc_present ? 2 : 0);
+            int rb = h.mono ? 18 : 20;
+            wsmask = 0xFu;
+            for (int gr = 0; gr < 2; gr++)
+                for (int ch = 0; ch < (h.mono ? 1 : 2); ch++) {
+                    const int slot = 2 * gr + ch;
+                    uint32_t ws, t0, t1, t2 = 0;
+                    const uint8_t *sp = wb + si;
+                    ws = sbits(sp, rb + 33, 1);
+                    if (ws) { t0 = sbits(sp, rb + 37, 5); t1 = sbits(sp, rb + 42, 5); }
+                    else { t0 = sbits(sp, rb + 34, 5); t1 = sbits(sp, rb + 39, 5); t2 = sbits(sp, rb + 44, 5); }
+                    nz01 += (t0 != 0) + (t1 != 0);
+                    if (!ws) { wsmask &= ~(1u << slot); t2pack |= t2 << (5 * slot); }
+                    rb += 59;
+                }
+            nzfix = h.mono ? 0x5u : 0xFu;  // slots that exist in this frame
+        }
+        // ---- carry scan: carry after frame k, slot s = t2 of the latest frame <= k that parsed slot s without window switching
+        uint32_t carry = 0;
+        uint32_t nz = nz01;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const uint32_t upd = __ballot_sync(0xFFFFFFFFu, valid && !((wsmask >> s) & 1u));
+            const uint32_t le = upd & (0xFFFFFFFFu >> (31 - lane));
+            const int src = le ? 31 - __clz(le) : 0;
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, (t2pack >> (5 * s)) & 31u, src);
+            const uint32_t c = le ? v : (carry_in >> (5 * s)) & 31u;
+            carry |= c << (5 * s);
+            if (valid && ((nzfix >> s) & 1u)) nz += c != 0;  // effective region-2 id of the slot: own value or the stale one
+        }
+        // ---- prefix sums of payload and non-zero table count
+        uint32_t pP = payload, pR = nz;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, pP, dlt), b = __shfl_up_sync(0xFFFFFFFFu, pR, dlt);
+            if (lane >= dlt) { pP += a; pR += b; }
+        }
+        if (valid) {
+            const int64_t g = fr.frame_base + n;
+            fr_pos[g] = pos;
+            fr_P[g] = P_in + pP - payload;
+            fr_meta[g] = meta;
+            fr_carry[g] = carry;
+            fr_reveal[g] = reveal_in + pR - nz;
+            fr_file[g] = f;
+        }
+        carry_in = __shfl_sync(0xFFFFFFFFu, carry, 31);  // lanes past the last frame update nothing: same carry as the last frame
+        P_in += __shfl_sync(0xFFFFFFFFu, pP, 31);
+        reveal_in += __shfl_sync(0xFFFFFFFFu, pR, 31);
+        __syncwarp();
+    }
+    if (lane == 0) fouts[f].reveal_len = (int32_t)reveal_in;
 }
 
 // ================================================================================================
@@ -821,16 +977,28 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
         f.end = file_off[i + 1];
         f.audio = file_off[i] + (audio_start ? audio_start[i] : 0);
         if (f.audio > f.end) f.audio = f.end;
-        f.frame_base = 0; f.s_base = 0; f.pcm_base = 0; f.n_frames = 0; f.flags = 0; f.channels = 0; f.pad = 0;
+        f.frame_base = 0; f.s_base = 0; f.pcm_base = 0; f.n_frames = 0; f.flags = 0; f.channels = 0; f.pad = 0; f.tmp_base = 0;
     }
     int rc;
     if ((rc = m3s_buf_reserve(h, h->b_files, sizeof(M3sFileRec) * n_files))) return rc;
     if ((rc = m3s_buf_reserve(h, h->b_fouts, sizeof(M3sFileOut) * n_files))) return rc;
     M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
-    const int wb = 32, wg = (n_files + wb - 1) / wb;
+    // ---- walk: positions of every frame (file-relative) into a temporary array sized by the smallest legal frame (96 bytes)
+    {
+        int64_t tb = 0;
+        for (int i = 0; i < n_files; i++) {
+            h->files[i].tmp_base = tb;
+            tb += (h->files[i].end - h->files[i].audio) / 96 + 2;
+        }
+        if ((rc = m3s_buf_reserve(h, h->b_tmp_pos, sizeof(uint32_t) * (size_t)(tb + 32)))) return rc;
+        for (int i = 0; i < n_files; i++)
+            if (h->files[i].end - h->files[i].begin > 0xFFFFFFFFLL) return m3s_fail(h, M3S_ERR_ARG, "decode_scan: file %d exceeds 4 GiB", i);
+    }
+    M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
+    const int wg = (n_files + WALK_WARPS - 1) / WALK_WARPS;
     M3S_KBEGIN(h, M3S_K_WALK);
-        k_walk<false><<<wg, wb, 0, h->stream>>>(h->d_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p, n_files,
-                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_walk<<<wg, 32 * WALK_WARPS, 0, h->stream>>>(h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p,
+                                                   n_files, (uint32_t *)h->b_tmp_pos.p);
     M3S_LAUNCH_CHECK(h);
     M3S_CUDA(h, cudaMemcpyAsync(h->fouts.data(), h->b_fouts.p, sizeof(M3sFileOut) * n_files, cudaMemcpyDeviceToHost, h->stream));
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -839,6 +1007,7 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
         M3sFileRec &f = h->files[i];
         f.frame_base = fb;
         f.n_frames = h->fouts[i].n_frames;
+        f.flags = h->fouts[i].status;
         fb += f.n_frames;
         sb += 512;  // zero pad in front: a main_data_begin that reaches before the first frame reads zeros
         f.s_base = sb;
@@ -857,10 +1026,11 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     if ((rc = m3s_buf_reserve(h, h->b_tabids, 12 * nf))) return rc;
     if ((rc = m3s_buf_reserve(h, h->b_reveal, 12 * nf))) return rc;
     M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
-    M3S_KBEGIN(h, M3S_K_WALK);
-        k_walk<true><<<wg, wb, 0, h->stream>>>(h->d_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p, n_files,
-                                           (int64_t *)h->b_fr_pos.p, (uint32_t *)h->b_fr_P.p, (uint32_t *)h->b_fr_meta.p,
-                                           (uint32_t *)h->b_fr_carry.p, (uint32_t *)h->b_fr_reveal.p, (int32_t *)h->b_fr_file.p);
+    M3S_KBEGIN(h, M3S_K_FSCAN);
+    k_fscan<<<wg, 32 * WALK_WARPS, 0, h->stream>>>(h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p,
+                                                    n_files, (const uint32_t *)h->b_tmp_pos.p, (int64_t *)h->b_fr_pos.p,
+                                                    (uint32_t *)h->b_fr_P.p, (uint32_t *)h->b_fr_meta.p, (uint32_t *)h->b_fr_carry.p,
+                                                    (uint32_t *)h->b_fr_reveal.p, (int32_t *)h->b_fr_file.p);
     M3S_LAUNCH_CHECK(h);
     if (fb > 0) {
         M3S_KBEGIN(h, M3S_K_SIDEINFO);

@@ -43,7 +43,7 @@ SYMBOLS = [
     ("m3s_timing_get", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), _c_i64p]),
     ("m3s_kernel_name", ctypes.c_char_p, [ctypes.c_int]),
 ]
-M3S_K_COUNT = 11
+M3S_K_COUNT = 12
 
 _lib = None
 
