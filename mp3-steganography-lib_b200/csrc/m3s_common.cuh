@@ -166,7 +166,9 @@ struct m3s_ctx {
     M3sBuf b_stage_in, b_files, b_fouts, b_tmp_pos, b_fr_pos, b_fr_P, b_fr_meta, b_fr_carry, b_fr_reveal, b_fr_file;
     M3sBuf b_units, b_sf, b_S, b_spec, b_tabids, b_reveal, b_work, b_pcm_stage, b_spec_export;
     // ---- encode state
-    M3sBuf e_pcm, e_clips, e_mdct, e_ix, e_info, e_gran, e_out, e_payload, e_misc, e_pad;
+    M3sBuf e_pcm, e_clips, e_mdct, e_ix, e_info, e_gran, e_out, e_payload, e_misc, e_pad, e_tabs, e_state, e_lastix, e_scfsi, e_work;
+    bool enc_taps_ok = false;
+    int64_t enc_chunk_budget = 0;   // frames of intermediates kept per chunk (0 = default; M3S_ENC_CHUNK_FRAMES overrides)
     int64_t enc_total_frames = 0;
     int32_t enc_n_clips = 0;
     std::vector<int64_t> enc_frame_base;

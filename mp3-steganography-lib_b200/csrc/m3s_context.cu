@@ -1,6 +1,7 @@
 // m3s_context.cu -- handle lifetime, device table construction, error plumbing.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "m3s_common.cuh"
@@ -230,6 +231,7 @@ extern "C" int m3s_create(int device, m3s_handle_t *out)
         return M3S_ERR_CUDA;
     }
     h->stream = h->own_stream;
+    if (const char *cb = getenv("M3S_ENC_CHUNK_FRAMES")) h->enc_chunk_budget = atoll(cb);
     M3sDevTables *T = new M3sDevTables();
     memset(T, 0, sizeof *T);
     build_tables(T);
@@ -267,7 +269,8 @@ extern "C" int m3s_destroy(m3s_handle_t h)
     M3sBuf *bufs[] = {&h->b_stage_in, &h->b_files, &h->b_fouts, &h->b_tmp_pos, &h->b_fr_pos, &h->b_fr_P, &h->b_fr_meta, &h->b_fr_carry,
                       &h->b_fr_reveal, &h->b_fr_file, &h->b_units, &h->b_sf, &h->b_S, &h->b_spec, &h->b_tabids,
                       &h->b_reveal, &h->b_work, &h->b_pcm_stage, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
-                      &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad};
+                      &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad, &h->e_tabs, &h->e_state,
+                      &h->e_lastix, &h->e_scfsi, &h->e_work};
     for (M3sBuf *b : bufs) free_buf(*b);
     timing_resolve(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

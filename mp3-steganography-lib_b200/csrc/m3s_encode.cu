@@ -1,5 +1,765 @@
-// m3s_encode.cu -- encode half (placeholder while the decode half is being validated on hardware)
+// m3s_encode.cu -- encode half of the hot path (reference: mp3stego/encoder/MP3_Encoder.py, a port of Shine).
+//
+//   E1 k_enc_analysis  polyphase analysis + MDCT + alias butterflies, exact 32-bit fixed point; also the per-granule
+//                      spectral statistics the rate loop and scfsi need (xrmax, en_tot, en[21]).           (:322-370, :652-758, :817-861)
+//   E2 k_enc_rate      per-granule quantisation / rate loop with table selection and the stego table swap.
+//                      One WARP per clip walks the clip's granules in the reference's order (frame, ch, gr), because
+//                      hide_str_offset and the stale address1/2/3 (SURVEY A.E5/A.E6) chain every granule to the one
+//                      before it; the 576 coefficients of a granule are spread over the 32 lanes.                  (:760-1264)
+//   E3 k_enc_pack      header, side info and Huffman bit packing, one warp per frame (frames are self-contained:
+//                      main_data_begin = 0 and every frame is filled to its nominal size by stuffing).            (:1266-1552)
+//
+// All arithmetic is integer and bit-exact with the reference; the only floating point is the reference's own
+// double-precision fallback in quantize (:401-407) and the padding recurrence (:504-513, :630-632) done on the host.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "m3s_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// device records
+// ------------------------------------------------------------------------------------------------
+struct M3sEncClip {
+    int64_t pcm_base;      // element offset of the clip's first sample (interleaved int16 stereo)
+    int64_t frame_base;    // global frame index of the clip's first frame (in the whole batch)
+    int64_t out_base;      // byte offset of the clip's MP3 in the output buffer
+    int64_t out_len;       // bytes the reference's bit writer emits (whole 32-bit words only, A.E8)
+    int64_t payload_base;  // first payload char
+    int64_t payload_len;   // number of payload chars ('0'/'1'); 0 = plain encode
+    int32_t n_frames;
+    int32_t pad;
+};
+
+struct M3sEncState {       // E2 state carried from chunk to chunk (and between frames inside the kernel)
+    int64_t hide_off;      // MP3Encoder.hide_str_offset
+    int32_t a1[4], a2[4], a3[4], step[4];  // per (gr, ch) slot: address1..3 (stale when big_values == 0, A.E6), quantizerStepSize
+};
+
+struct __align__(16) M3sEncStats {  // per granule-channel, written by E1
+    int32_t xrmax;
+    int8_t en_tot;
+    int8_t en[21];
+    int8_t pad[6];
+};
+
+struct M3sEncWork {        // E1 work item: a run of granules of one clip
+    int32_t clip;
+    int32_t g_first;       // first granule (2 * frame + gr) whose MDCT this CTA emits
+    int32_t count;
+    int32_t pad;
+};
+
+#define ENC_INFO_FIELDS 16
+#define ENC_RUN 36         // granules per E1 CTA (one warm-up granule of filterbank per run: 2.8 %)
+
+struct EncTables {         // small read-only tables of E2/E3, built on the host once per handle
+    uint32_t hl4[256];     // code lengths of books 13 | 15 << 8 | 16 << 16 | 24 << 24 at [x * 16 + y]
+    uint32_t en_thresh[32];  // smallest temp with en(temp) >= j - 20  (calc_scfsi's truncated log, :836-857)
+    uint8_t hlc1[2][16];   // count1 tables A / B code lengths
+};
+
+__device__ __forceinline__ int32_t mulr32(int32_t a, int32_t b)  // util.mulr (util.py:129-133)
+{
+    return (int32_t)(((int64_t)a * (int64_t)b + 0x80000000LL) >> 32);
+}
+__device__ __forceinline__ int32_t mulsr32(int32_t a, int32_t b)  // util.mulsr (util.py:135-139)
+{
+    return (int32_t)(((int64_t)a * (int64_t)b + 0x40000000LL) >> 31);
+}
+
+// ================================================================================================
+// E1: analysis filterbank + MDCT
+// ================================================================================================
+#define ANA_THREADS 288
+
+__global__ void __launch_bounds__(ANA_THREADS)
+k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ clips, const M3sEncWork *__restrict__ work,
+               const M3sDevTables *__restrict__ T, const EncTables *__restrict__ ET, int sr_idx, int64_t chunk_frame0,
+               int32_t *__restrict__ mdct, M3sEncStats *__restrict__ stats)
+{
+    __shared__ int32_t s_x[2][1056];        // per channel: 480 samples of history + 576 new, as int16 << 16
+    __shared__ int32_t s_win[512];
+    __shared__ __align__(16) int32_t s_tmp[18][64];
+    __shared__ int32_t s_sb[2][2][18][32];  // [ch][ping-pong][slot][band]
+    __shared__ int32_t s_cos[18][36];
+    __shared__ int32_t s_mf[576];
+    __shared__ uint32_t s_bins[24];         // 0..20 band energies, 21 total, 22 xrmax
+    __shared__ uint8_t s_sfb[576];
+    __shared__ int32_t s_ca[8], s_cs[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const M3sEncWork wk = work[blockIdx.x];
+    const M3sEncClip cl = clips[wk.clip];
+    for (int i = tid; i < 512; i += ANA_THREADS) s_win[i] = T->enwindow[i];
+    for (int i = tid; i < 18 * 36; i += ANA_THREADS) (&s_cos[0][0])[i] = (&T->enc_cosl[0][0])[i];
+    for (int i = tid; i < 576; i += ANA_THREADS) s_sfb[i] = T->long_sfb_of[sr_idx][i];
+    if (tid < 8) { s_ca[tid] = T->enc_ca[tid]; s_cs[tid] = T->enc_cs[tid]; }
+    for (int i = tid; i < 2 * 2 * 18 * 32; i += ANA_THREADS) (&s_sb[0][0][0][0])[i] = 0;
+    int32_t fl[64];  // row `lane` of the polyphase matrix
+#pragma unroll
+    for (int j = 0; j < 64; j++) fl[j] = T->enc_fl[lane][j];
+    __syncthreads();
+
+    const uint32_t *pcm32 = (const uint32_t *)(pcm + cl.pcm_base);  // one stereo sample per word (pcm_base is even)
+    const int g_begin = wk.g_first > 0 ? wk.g_first - 1 : 0;
+    const int g_end = wk.g_first + wk.count;
+    int pp = 0;
+    for (int G = g_begin; G < g_end; G++) {
+        // ---- PCM window: samples [576 G - 480, 576 G + 576) of both channels
+        const int64_t t0 = (int64_t)G * 576 - 480;
+        if (G == g_begin) {
+            for (int i = tid; i < 1056; i += ANA_THREADS) {
+                const int64_t t = t0 + i;
+                const uint32_t w = t >= 0 ? __ldg(pcm32 + t) : 0u;
+                s_x[0][i] = (int32_t)(w << 16);
+                s_x[1][i] = (int32_t)(w & 0xFFFF0000u);
+            }
+        } else {
+            int32_t keep0[2], keep1[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int i = tid + q * ANA_THREADS;
+                if (i < 480) { keep0[q] = s_x[0][576 + i]; keep1[q] = s_x[1][576 + i]; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int i = tid + q * ANA_THREADS;
+                if (i < 480) { s_x[0][i] = keep0[q]; s_x[1][i] = keep1[q]; }
+            }
+            for (int i = tid; i < 576; i += ANA_THREADS) {
+                const uint32_t w = __ldg(pcm32 + t0 + 480 + i);
+                s_x[0][480 + i] = (int32_t)(w << 16);
+                s_x[1][480 + i] = (int32_t)(w & 0xFFFF0000u);
+            }
+        }
+        __syncthreads();
+        const bool emit = G >= wk.g_first;
+        for (int ch = 1; ch >= 0; ch--) {  // the reference walks ch = nch-1 .. 0 (:661); the channels are independent
+            // ---- windowing: y_i = sum_k mul(x[t = 32 s + 31 - i - 64 k], enwindow[i + 64 k])   (:337-356)
+            for (int o = tid; o < 18 * 64; o += ANA_THREADS) {
+                const int s = o >> 6, i = o & 63;
+                const int32_t *xp = &s_x[ch][480 + 32 * s + 31 - i];
+                uint32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc += (uint32_t)__mulhi(xp[-64 * k], s_win[i + 64 * k]);
+                s_tmp[s][i] = (int32_t)acc;
+            }
+            __syncthreads();
+            // ---- matrixing: s_b = sum_j mul(fl[b][j], y_j); odd bands of odd slots negated   (:358-368, :678-679)
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int s = 2 * warp + q;
+                const int4 *y4 = (const int4 *)s_tmp[s];
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j4 = 0; j4 < 16; j4++) {
+                    const int4 y = y4[j4];
+                    acc += (uint32_t)__mulhi(fl[4 * j4 + 0], y.x);
+                    acc += (uint32_t)__mulhi(fl[4 * j4 + 1], y.y);
+                    acc += (uint32_t)__mulhi(fl[4 * j4 + 2], y.z);
+                    acc += (uint32_t)__mulhi(fl[4 * j4 + 3], y.w);
+                }
+                if ((s & 1) && (lane & 1)) acc = 0u - acc;
+                s_sb[ch][pp][s][lane] = (int32_t)acc;
+            }
+            __syncthreads();
+            if (emit) {
+                // ---- MDCT: X[b][k] = sum_j mul(in[j], cos_l[k][j]), in = 18 previous + 18 current subband samples   (:683-701)
+                if (tid < 24) s_bins[tid] = 0u;
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int k = 2 * warp + q;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int j = 0; j < 18; j++) acc += (uint32_t)__mulhi(s_sb[ch][pp ^ 1][j][lane], s_cos[k][j]);
+#pragma unroll
+                    for (int j = 0; j < 18; j++) acc += (uint32_t)__mulhi(s_sb[ch][pp][j][lane], s_cos[k][18 + j]);
+                    s_mf[lane * 18 + k] = (int32_t)acc;
+                }
+                __syncthreads();
+                // ---- alias butterflies between neighbouring bands, cmuls with >> 31   (:704-744, util.py:145-155)
+                if (tid < 248) {
+                    const int band = 1 + (tid >> 3), k = tid & 7;
+                    const int64_t are = s_mf[band * 18 + k], aim = s_mf[(band - 1) * 18 + 17 - k];
+                    const int64_t bre = s_cs[k], bim = s_ca[k];
+                    s_mf[band * 18 + k] = (int32_t)((are * bre - aim * bim) >> 31);
+                    s_mf[(band - 1) * 18 + 17 - k] = (int32_t)((are * bim + aim * bre) >> 31);
+                }
+                __syncthreads();
+                // ---- store + statistics: xrmax, en_tot, en[sfb]   (:772-776, :836-857)
+                const int frame = G >> 1, gr = G & 1;
+                const int64_t gslot = (((int64_t)(cl.frame_base + frame) - chunk_frame0) * 2 + ch) * 2 + gr;
+                int32_t *dst = mdct + gslot * 576;
+                uint32_t tot = 0, mx = 0;
+                for (int i = tid; i < 576; i += ANA_THREADS) {
+                    const int32_t v = s_mf[i];
+                    dst[i] = v;
+                    const uint32_t e = (uint32_t)(mulsr32(v, v) >> 10);
+                    const int sfb = s_sfb[i];
+                    if (sfb < 21) atomicAdd(&s_bins[sfb], e);
+                    tot += e;
+                    const uint32_t a = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+                    mx = a > mx ? a : mx;
+                }
+                tot = __reduce_add_sync(0xFFFFFFFFu, tot);
+                mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+                if (lane == 0) { atomicAdd(&s_bins[21], tot); atomicMax(&s_bins[22], mx); }
+                __syncthreads();
+                if (tid < 22) {
+                    const uint32_t temp = s_bins[tid];
+                    int en = 0;
+                    if (temp) {
+                        en = -21;
+                        for (int j = 0; j < 31; j++) en += ET->en_thresh[j] <= temp;
+                    }
+                    M3sEncStats *st = stats + gslot;
+                    if (tid == 21) { st->en_tot = (int8_t)en; st->xrmax = (int32_t)s_bins[22]; }
+                    else st->en[tid] = (int8_t)en;
+                }
+            }
+            __syncthreads();
+        }
+        pp ^= 1;
+    }
+}
+
+// ================================================================================================
+// E2: rate loop, one warp per clip
+// ================================================================================================
+struct RateSmem {
+    uint16_t i2i[10000];
+    uint32_t hl4[256];
+    int32_t steptabi[128];
+    double steptab[128];
+    uint16_t sfb[24];
+    uint16_t linmax[32];
+    uint8_t linbits[32];
+    uint8_t subdv[23][2];
+    uint8_t pair[32][2];
+    uint8_t hlc1[2][16];
+};
+
+struct GranInfo {  // the reference's gr_info fields the probes rewrite (MP3_Encoder.py:76-104)
+    int bv, count1, c1sel, r0, r1, ts0, ts1, ts2;
+};
+
+// quantize() of the single largest coefficient: decides `quantize(...) > 8192` without touching the other 575
+// (ix is monotone in |xr| for a fixed step, and an overflowing probe's ix is never read again).   (:374-415)
+__device__ __forceinline__ int quant_one(const RateSmem &S, int32_t xabs, int step)
+{
+    const int32_t scalei = S.steptabi[step + 127];
+    const int32_t ln = mulr32(xabs, scalei);
+    if (ln < 10000) return S.i2i[ln];
+    const double dbl = __dmul_rn(__dmul_rn((double)xabs, S.steptab[step + 127]), 4.656612875e-10);
+    return (int)__dsqrt_rn(__dmul_rn(__dsqrt_rn(dbl), dbl));
+}
+
+__device__ __forceinline__ int quant_max(const RateSmem &S, int32_t xrmax, int step)
+{
+    const int32_t scalei = S.steptabi[step + 127];
+    if (mulr32(xrmax, scalei) > 165140) return 16384;
+    return quant_one(S, xrmax, step);
+}
+
+__device__ __forceinline__ int table_cost(const RateSmem &S, int t, uint32_t lo, uint32_t hi, uint32_t cnt)
+{
+    // count_bit() of table t over a region from the region's pooled sums   (:215-263)
+    const int nsign = cnt & 0xFFFF, n15 = cnt >> 16;
+    if (t == 0) return 0;
+    if (t == 13) return (int)(lo & 0xFFFF) + nsign;
+    if (t == 15) return (int)(hi & 0xFFFF) + nsign;
+    return (int)(t < 24 ? (lo >> 16) : (hi >> 16)) + nsign + (int)S.linbits[t] * n15;
+}
+
+// new_choose_table (:1170-1264) on pooled sums; `k` = payload bits already consumed by earlier regions of this probe
+__device__ __forceinline__ int choose_table(const RateSmem &S, int mx, uint32_t lo, uint32_t hi, uint32_t cnt, bool hiding,
+                                            int k, int hn, uint32_t hb)
+{
+    if (mx == 0) return 0;
+    int choice;
+    if (mx < 15) {
+        choice = 13;  // the count-down search always stops at 13 (A.E4); only its 13-vs-15 arm is live
+        if (table_cost(S, 15, lo, hi, cnt) <= table_cost(S, 13, lo, hi, cnt)) choice = 15;
+    } else {
+        const int m = mx - 15;
+        int c0 = 0, c1 = 0;
+        for (int i = 15; i < 24; i++) if ((int)S.linmax[i] >= m) { c0 = i; break; }
+        for (int i = 24; i < 32; i++) if ((int)S.linmax[i] >= m) { c1 = i; break; }
+        choice = c0;
+        if (table_cost(S, c1, lo, hi, cnt) < table_cost(S, c0, lo, hi, cnt)) choice = c1;
+    }
+    if (hiding && k < hn) choice = S.pair[choice][(hb >> k) & 1u];
+    return choice;
+}
+
+// calc_run_len + count1_bit_count + subdivide + big_v_tab_select + big_v_bit_count for the quantised values held
+// pair-interleaved in the warp (lane L holds pairs 32 j + L).  Returns the bit count; updates gi and the slot addresses.
+__device__ __forceinline__ int probe_bits(const RateSmem &S, const uint32_t (&qx)[9], const uint32_t (&qy)[9], int lane, GranInfo &gi,
+                                          int &a1, int &a2, int &a3, bool hiding, int hn, uint32_t hb)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    // ---- calc_run_len (:266-291)
+    uint32_t lastnz = 0, lastbig = 0, nzmask = 0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        const uint32_t p = 32 * j + lane;
+        if (qx[j] | qy[j]) lastnz = p + 1;
+        if (qx[j] > 1) lastbig = 2 * p + 1;
+        if (qy[j] > 1) lastbig = 2 * p + 2;
+        nzmask |= (uint32_t)(qx[j] != 0) << (2 * j) | (uint32_t)(qy[j] != 0) << (2 * j + 1);
+    }
+    lastnz = __reduce_max_sync(FULL, lastnz);
+    lastbig = __reduce_max_sync(FULL, lastbig);
+    const int i_end = 2 * (int)lastnz;
+    gi.count1 = (i_end - (int)lastbig) >> 2;
+    gi.bv = (i_end - 4 * gi.count1) >> 1;
+    // ---- count1_bit_count (:171-211): quads start at pair bv; the partner pair lives in the next lane
+    const uint32_t nb = __shfl_sync(FULL, nzmask, (lane + 1) & 31);
+    uint32_t c1s = 0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        const int rel = 32 * j + lane - gi.bv;
+        if (rel >= 0 && rel < 2 * gi.count1 && !(rel & 1)) {
+            const uint32_t me = (nzmask >> (2 * j)) & 3u;
+            const uint32_t nx = lane < 31 ? (nb >> (2 * j)) & 3u : (nb >> (2 * j + 2)) & 3u;
+            const uint32_t idx = me | (nx << 2);  // v + 2 w + 4 x + 8 y
+            const uint32_t nn = __popc(idx);
+            c1s += (S.hlc1[0][idx] + nn) | ((S.hlc1[1][idx] + nn) << 16);
+        }
+    }
+    c1s = __reduce_add_sync(FULL, c1s);
+    int bits;
+    if ((c1s & 0xFFFF) < (c1s >> 16)) { gi.c1sel = 0; bits = c1s & 0xFFFF; }
+    else { gi.c1sel = 1; bits = c1s >> 16; }
+    // ---- subdivide (:998-1036); with big_values == 0 the addresses keep their old values (A.E6)
+    if (gi.bv == 0) { gi.r0 = 0; gi.r1 = 0; }
+    else {
+        const int bvr = 2 * gi.bv;
+        const int anz = __popc(__ballot_sync(FULL, lane < 23 && (int)S.sfb[lane] < bvr));
+        int tc = S.subdv[anz][0];
+        while (tc > 0 && (int)S.sfb[tc + 1] > bvr) tc--;
+        gi.r0 = tc;
+        a1 = S.sfb[tc + 1];
+        const int base = tc + 1;
+        tc = S.subdv[anz][1];
+        while (tc > 0 && (int)S.sfb[min(base + tc + 1, 23)] > bvr) tc--;
+        gi.r1 = tc;
+        a2 = S.sfb[min(base + tc + 1, 23)];
+        a3 = bvr;
+    }
+    // ---- pooled region sums: [0, a1) [a1, a2) [a2, 2 bv)   (:1147-1168, :294-318)
+    const int e2 = 2 * gi.bv;
+    uint32_t lo0 = 0, hi0 = 0, cn0 = 0, lo1 = 0, hi1 = 0, cn1 = 0, lo2 = 0, hi2 = 0, cn2 = 0, m0 = 0, m1 = 0, m2 = 0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        const int e = 2 * (32 * j + lane);
+        const uint32_t x = qx[j], y = qy[j];
+        const uint32_t w = S.hl4[min(x, 15u) * 16 + min(y, 15u)];
+        const uint32_t wl = w & 0x00FF00FFu, wh = (w >> 8) & 0x00FF00FFu;
+        const uint32_t cn = (uint32_t)(x != 0) + (uint32_t)(y != 0) + (((uint32_t)(x > 14) + (uint32_t)(y > 14)) << 16);
+        const uint32_t mx = max(x, y);
+        if (e < a1) { lo0 += wl; hi0 += wh; cn0 += cn; m0 = max(m0, mx); }
+        else if (e < a2) { lo1 += wl; hi1 += wh; cn1 += cn; m1 = max(m1, mx); }
+        else if (e < e2) { lo2 += wl; hi2 += wh; cn2 += cn; m2 = max(m2, mx); }
+    }
+    m0 = __reduce_max_sync(FULL, m0); m1 = __reduce_max_sync(FULL, m1); m2 = __reduce_max_sync(FULL, m2);
+    lo0 = __reduce_add_sync(FULL, lo0); hi0 = __reduce_add_sync(FULL, hi0); cn0 = __reduce_add_sync(FULL, cn0);
+    lo1 = __reduce_add_sync(FULL, lo1); hi1 = __reduce_add_sync(FULL, hi1); cn1 = __reduce_add_sync(FULL, cn1);
+    lo2 = __reduce_add_sync(FULL, lo2); hi2 = __reduce_add_sync(FULL, hi2); cn2 = __reduce_add_sync(FULL, cn2);
+    // ---- big_v_tab_select with the stego swap; the payload index advances past non-zero tables only
+    int k = 0;
+    gi.ts0 = a1 <= 0 ? 0 : choose_table(S, (int)m0, lo0, hi0, cn0, hiding, k, hn, hb);
+    if (gi.ts0 > 0) k++;
+    gi.ts1 = a2 <= a1 ? 0 : choose_table(S, (int)m1, lo1, hi1, cn1, hiding, k, hn, hb);
+    if (gi.ts1 > 0) k++;
+    gi.ts2 = e2 <= a2 ? 0 : choose_table(S, (int)m2, lo2, hi2, cn2, hiding, k, hn, hb);
+    bits += table_cost(S, gi.ts0, lo0, hi0, cn0) + table_cost(S, gi.ts1, lo1, hi1, cn1) + table_cost(S, gi.ts2, lo2, hi2, cn2);
+    return bits;
+}
+
+// quantize() of all 576 values (:374-415); returns nothing: callers know from quant_max() that the maximum is <= 8192
+__device__ __forceinline__ void quantize_all(const RateSmem &S, const uint32_t (&ax)[9], const uint32_t (&ay)[9], int step,
+                                             uint32_t (&qx)[9], uint32_t (&qy)[9])
+{
+    const int32_t scalei = S.steptabi[step + 127];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        const int32_t lx = mulr32((int32_t)ax[j], scalei), ly = mulr32((int32_t)ay[j], scalei);
+        qx[j] = lx < 10000 ? (uint32_t)S.i2i[lx] : (uint32_t)quant_one(S, (int32_t)ax[j], step);
+        qy[j] = ly < 10000 ? (uint32_t)S.i2i[ly] : (uint32_t)quant_one(S, (int32_t)ay[j], step);
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ states, const M3sDevTables *__restrict__ T,
+           const EncTables *__restrict__ ET, const uint32_t *__restrict__ byteoff, const uint8_t *__restrict__ payload,
+           int sr_idx, int whole_slots, int32_t chunk_first, int32_t chunk_frames, int64_t chunk_frame0,
+           const int32_t *__restrict__ mdct, const M3sEncStats *__restrict__ stats, uint32_t *__restrict__ ixout,
+           int32_t *__restrict__ info, uint8_t *__restrict__ scfsi_out, uint32_t *__restrict__ last_ix)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RateSmem &S = *reinterpret_cast<RateSmem *>(smem_raw);
+    const int lane = threadIdx.x;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    for (int i = lane; i < 10000; i += 32) S.i2i[i] = (uint16_t)T->int2idx[i];
+    for (int i = lane; i < 256; i += 32) S.hl4[i] = ET->hl4[i];
+    for (int i = lane; i < 128; i += 32) { S.steptabi[i] = T->steptabi[i]; S.steptab[i] = T->steptab[i]; }
+    if (lane < 24) S.sfb[lane] = lane < 23 ? T->sfb_long[sr_idx][lane] : 576;
+    S.linmax[lane] = T->enc_linmax[lane];
+    S.linbits[lane] = T->enc_linbits[lane];
+    if (lane < 23) { S.subdv[lane][0] = T->subdv[lane][0]; S.subdv[lane][1] = T->subdv[lane][1]; }
+    S.pair[lane][0] = T->pair[lane][0];
+    S.pair[lane][1] = T->pair[lane][1];
+    if (lane < 16) { S.hlc1[0][lane] = ET->hlc1[0][lane]; S.hlc1[1][lane] = ET->hlc1[1][lane]; }
+    __syncwarp();
+
+    const int c = blockIdx.x;
+    const M3sEncClip cl = clips[c];
+    M3sEncState st = states[c];
+    const bool hiding = cl.payload_len > 0;
+    const int f_end = min(cl.n_frames, chunk_first + chunk_frames);
+    for (int f = chunk_first; f < f_end; f++) {
+        const int padding = (int)(byteoff[f + 1] - byteoff[f]) - whole_slots;
+        const int bits_per_frame = 8 * (whole_slots + padding);
+        const int mean_bits = (bits_per_frame - 288) / 2;          // :634-636 (side info 8 * (4 + 32) bits)
+        const int max_bits = min(mean_bits / 2, 4095);             // :894-912 with the reservoir never enabled (A.E7)
+        const int64_t fl_ = cl.frame_base + f - chunk_frame0;      // frame slot in the chunk buffers
+        int p23[4];                                                // by slot = 2 * gr + ch
+        int32_t rec[4][ENC_INFO_FIELDS];
+        int resv = 0;
+        for (int ch = 0; ch < 2; ch++) {
+            for (int gr = 0; gr < 2; gr++) {
+                const int slot = 2 * gr + ch;
+                const int64_t gslot = (fl_ * 2 + ch) * 2 + gr;
+                const int2 *xr = (const int2 *)(mdct + gslot * 576);
+                uint32_t ax[9], ay[9], sg = 0;
+#pragma unroll
+                for (int j = 0; j < 9; j++) {
+                    const int2 v = __ldg(xr + 32 * j + lane);
+                    ax[j] = v.x < 0 ? (uint32_t)(-(int64_t)v.x) : (uint32_t)v.x;
+                    ay[j] = v.y < 0 ? (uint32_t)(-(int64_t)v.y) : (uint32_t)v.y;
+                    sg |= (uint32_t)(v.x < 0) << (2 * j) | (uint32_t)(v.y < 0) << (2 * j + 1);
+                }
+                const int32_t xrmax = stats[gslot].xrmax;
+                GranInfo gi;
+                gi.bv = 0; gi.count1 = 0; gi.c1sel = 0; gi.r0 = 0; gi.r1 = 0; gi.ts0 = 0; gi.ts1 = 0; gi.ts2 = 0;
+                int a1 = st.a1[slot], a2 = st.a2[slot], a3 = st.a3[slot], step = st.step[slot];
+                int part23 = 0;
+                uint32_t *ixd = ixout + gslot * 288;
+                if (xrmax) {
+                    // payload bits this granule can consume: bits[hide_off .. hide_off + 2]   (:1154-1168)
+                    int hn = 0;
+                    uint32_t hb = 0;
+                    if (hiding) {
+                        const int64_t left = cl.payload_len - st.hide_off;
+                        hn = left > 3 ? 3 : (left < 0 ? 0 : (int)left);
+                        const bool one = lane < hn && __ldg(payload + cl.payload_base + st.hide_off + lane) == '1';
+                        hb = __ballot_sync(FULL, one);
+                    }
+                    uint32_t qx[9], qy[9];
+                    // ---- bin_search_step_size (:958-996)
+                    int next = -120, count = 120;
+                    do {
+                        const int half = count / 2;
+                        int bit;
+                        if (quant_max(S, xrmax, next + half) > 8192) bit = 100000;
+                        else {
+                            quantize_all(S, ax, ay, next + half, qx, qy);
+                            bit = probe_bits(S, qx, qy, lane, gi, a1, a2, a3, hiding, hn, hb);
+                        }
+                        if (bit < max_bits) count = half;
+                        else { next += half; count -= half; }
+                    } while (count > 1);
+                    step = next;
+                    // ---- inner_loop (:1064-1095)
+                    int bits;
+                    do {
+                        while (quant_max(S, xrmax, step + 1) > 8192) step++;
+                        step++;
+                        quantize_all(S, ax, ay, step, qx, qy);
+                        bits = probe_bits(S, qx, qy, lane, gi, a1, a2, a3, hiding, hn, hb);
+                    } while (bits > max_bits);
+                    part23 = bits;
+                    st.hide_off += (gi.ts0 > 0) + (gi.ts1 > 0) + (gi.ts2 > 0);   // :808-809
+                    // ---- signed ix as format_bitstream leaves it (:1272-1276)
+#pragma unroll
+                    for (int j = 0; j < 9; j++) {
+                        const int vx = ((sg >> (2 * j)) & 1u) ? -(int)qx[j] : (int)qx[j];
+                        const int vy = ((sg >> (2 * j + 1)) & 1u) ? -(int)qy[j] : (int)qy[j];
+                        ixd[32 * j + lane] = ((uint32_t)vx & 0xFFFFu) | ((uint32_t)vy << 16);
+                    }
+                } else {
+                    // silent granule: l3_enc keeps the previous frame's values of this slot (never coded: big_values = count1 = 0)
+                    const uint32_t *src = f > chunk_first ? ixout + (gslot - 4) * 288
+                                                          : (f > 0 ? last_ix + ((int64_t)c * 4 + (2 * ch + gr)) * 288 : nullptr);
+#pragma unroll
+                    for (int j = 0; j < 9; j++) ixd[32 * j + lane] = src ? src[32 * j + lane] : 0u;
+                }
+                st.a1[slot] = a1; st.a2[slot] = a2; st.a3[slot] = a3; st.step[slot] = step;
+                p23[slot] = part23;
+                resv += mean_bits / 2 - part23;   // :812 (mean_bits is even: bits_per_frame and 288 are multiples of 8)
+                int32_t *r = rec[slot];
+                r[0] = part23; r[1] = gi.bv; r[2] = gi.count1; r[3] = step + 210; r[4] = gi.ts0; r[5] = gi.ts1; r[6] = gi.ts2;
+                r[7] = gi.r0; r[8] = gi.r1; r[9] = gi.c1sel; r[10] = a1; r[11] = a2; r[12] = a3; r[13] = step; r[14] = padding;
+                r[15] = 0;
+            }
+            // ---- calc_scfsi for this channel (:862-892): needs the statistics of both granules
+            if (lane == 0) {
+                const M3sEncStats s0 = stats[(fl_ * 2 + ch) * 2 + 0], s1 = stats[(fl_ * 2 + ch) * 2 + 1];
+                int condition = 2 + (s0.xrmax != 0) + (s1.xrmax != 0);
+                if (abs((int)s0.en_tot - (int)s1.en_tot) < 10) condition++;
+                int tp = 0;
+                for (int sfb = 0; sfb < 21; sfb++) tp += abs((int)s0.en[sfb] - (int)s1.en[sfb]);
+                if (tp < 100) condition++;
+                const int band[5] = {0, 6, 11, 16, 21};
+                for (int b = 0; b < 4; b++) {
+                    int sum0 = 0;
+                    for (int sfb = band[b]; sfb < band[b + 1]; sfb++) sum0 += abs((int)s0.en[sfb] - (int)s1.en[sfb]);
+                    scfsi_out[(fl_ * 2 + ch) * 4 + b] = (condition == 6 && sum0 < 10) ? 1 : 0;   // xm[] is all zero: sum1 = 0
+                }
+            }
+        }
+        // ---- resv_frame_end (:1097-1145): every unused bit of the frame becomes stuffing
+        int stuffing = resv;
+        if (stuffing > 0) {
+            if (p23[0] + stuffing < 4095) p23[0] += stuffing;
+            else {
+                const int order[4] = {0, 1, 2, 3};  // gr0ch0, gr0ch1, gr1ch0, gr1ch1 == slot order
+                for (int q = 0; q < 4 && stuffing > 0; q++) {
+                    const int s = order[q];
+                    const int t = min(4095 - p23[s], stuffing);
+                    p23[s] += t;
+                    stuffing -= t;
+                }
+            }
+        }
+        if (lane < 4) {                         // info layout [frame][gr][ch] == slot order
+            int32_t *d = info + (fl_ * 4 + lane) * ENC_INFO_FIELDS;
+            for (int q = 1; q < ENC_INFO_FIELDS - 1; q++) d[q] = rec[lane][q];
+            d[0] = p23[lane];
+            d[15] = (int32_t)st.hide_off;
+        }
+        __syncwarp();
+    }
+    // ---- hand the state to the next chunk
+    if (f_end > chunk_first && f_end < cl.n_frames) {
+        const int64_t fl_ = cl.frame_base + (f_end - 1) - chunk_frame0;
+        for (int ch = 0; ch < 2; ch++)
+            for (int gr = 0; gr < 2; gr++) {
+                const uint32_t *src = ixout + ((fl_ * 2 + ch) * 2 + gr) * 288;
+                uint32_t *dst = last_ix + ((int64_t)c * 4 + (2 * ch + gr)) * 288;
+                for (int j = 0; j < 9; j++) dst[32 * j + lane] = src[32 * j + lane];
+            }
+    }
+    if (lane == 0) states[c] = st;
+}
+
+// ================================================================================================
+// E3: bit packing, one warp per frame
+// ================================================================================================
+#define PACK_WARPS 8
+#define PACK_WORDS 364   // >= 1441 bytes (320 kbps at 32 kHz, padded)
+
+struct PackSmem {
+    uint32_t code[1410];
+    uint16_t hoff[34];
+    uint8_t linbits[34];
+    uint16_t sfb[24];
+    uint32_t frame[PACK_WARPS][PACK_WORDS];
+    uint32_t ix[PACK_WARPS][288];
+};
+
+// append `n` (<= 32) bits of `v` at bit position `pos` of a big-endian word buffer (bit 0 = MSB of word 0)
+__device__ __forceinline__ void put_bits_at(uint32_t *buf, int pos, uint32_t v, int n)
+{
+    if (n == 0) return;
+    const int w = pos >> 5, o = pos & 31;
+    const uint64_t x = ((uint64_t)(n < 32 ? (v & ((1u << n) - 1u)) : v)) << (64 - n - o);
+    atomicOr(&buf[w], (uint32_t)(x >> 32));
+    if ((uint32_t)x) atomicOr(&buf[w + 1], (uint32_t)x);
+}
+
+__global__ void __launch_bounds__(32 * PACK_WARPS)
+k_enc_pack(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ frame_clip, const M3sDevTables *__restrict__ T,
+           const uint32_t *__restrict__ byteoff, int sr_idx, int bitrate_idx, int whole_slots, int64_t chunk_frame0,
+           int64_t chunk_total_frames, const uint32_t *__restrict__ ixin, const int32_t *__restrict__ info,
+           const uint8_t *__restrict__ scfsi, uint8_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PackSmem &S = *reinterpret_cast<PackSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    for (int i = tid; i < 1410; i += 32 * PACK_WARPS) S.code[i] = T->enc_hpacked[i];
+    if (tid < 34) { S.hoff[tid] = T->enc_hoff[tid]; S.linbits[tid] = T->enc_linbits[tid]; }
+    if (tid < 24) S.sfb[tid] = tid < 23 ? T->sfb_long[sr_idx][tid] : 576;
+    __syncthreads();
+    const int64_t fl_ = (int64_t)blockIdx.x * PACK_WARPS + warp;
+    if (fl_ >= chunk_total_frames) return;
+    const int c = frame_clip[fl_];
+    const M3sEncClip cl = clips[c];
+    const int f = (int)(chunk_frame0 + fl_ - cl.frame_base);
+    const int fbytes = (int)(byteoff[f + 1] - byteoff[f]);
+    const int padding = fbytes - whole_slots;
+    uint32_t *buf = S.frame[warp];
+    for (int i = lane; i < PACK_WORDS; i += 32) buf[i] = 0u;
+    __syncwarp();
+    const int32_t *inf = info + fl_ * 4 * ENC_INFO_FIELDS;
+    // ---- header + side info: 288 bits = words 0..8   (:1281-1337)
+    if (lane == 0) {
+        int pos = 0;
+        auto put = [&](uint32_t v, int n) { put_bits_at(buf, pos, v, n); pos += n; };
+        put(0x7ff, 11); put(3, 2); put(1, 2); put(1, 1); put((uint32_t)bitrate_idx, 4); put((uint32_t)(sr_idx % 3), 2);
+        put((uint32_t)padding, 1); put(0, 1); put(0, 2); put(0, 2); put(0, 1); put(1, 1); put(0, 2);
+        put(0, 9); put(0, 3);
+        for (int ch = 0; ch < 2; ch++)
+            for (int b = 0; b < 4; b++) put(scfsi[(fl_ * 2 + ch) * 4 + b], 1);
+        for (int gr = 0; gr < 2; gr++)
+            for (int ch = 0; ch < 2; ch++) {
+                const int32_t *r = inf + (2 * gr + ch) * ENC_INFO_FIELDS;
+                put((uint32_t)r[0], 12); put((uint32_t)r[1], 9); put((uint32_t)r[3], 8); put(0, 4); put(0, 1);
+                put((uint32_t)r[4], 5); put((uint32_t)r[5], 5); put((uint32_t)r[6], 5); put((uint32_t)r[7], 4); put((uint32_t)r[8], 3);
+                put(0, 1); put(0, 1); put((uint32_t)r[9], 1);
+            }
+    }
+    // ---- main data: (gr0,ch0) (gr0,ch1) (gr1,ch0) (gr1,ch1), each exactly part2_3_length bits   (:1339-1446)
+    int start = 288;
+    for (int gr = 0; gr < 2; gr++)
+        for (int ch = 0; ch < 2; ch++) {
+            const int32_t *r = inf + (2 * gr + ch) * ENC_INFO_FIELDS;
+            const int part23 = r[0], bv = r[1], count1 = r[2], ts[3] = {r[4], r[5], r[6]}, c1sel = r[9];
+            const int r1 = S.sfb[r[7] + 1], r2 = S.sfb[min(r[7] + 1 + r[8] + 1, 23)];
+            const uint32_t *src = ixin + ((fl_ * 2 + ch) * 2 + gr) * 288;
+            uint32_t *ix = S.ix[warp];
+            for (int j = 0; j < 9; j++) ix[32 * j + lane] = __ldg(src + 32 * j + lane);
+            __syncwarp();
+            int pos = start;
+            // big values: pair p carries code(+signs) or code, linbits, signs   (:1448-1513)
+            for (int j = 0; j < 9; j++) {
+                const int p = 32 * j + lane;
+                uint64_t bitsv = 0;
+                int nb = 0;
+                if (p < bv) {
+                    const int e = 2 * p;
+                    const int t = ts[(e >= r1) + (e >= r2)];
+                    if (t) {
+                        const uint32_t wv = ix[p];
+                        int x = (int)(int16_t)(wv & 0xFFFFu), y = (int)(int16_t)(wv >> 16);
+                        const uint32_t sx = x > 0 ? 0u : 1u, sy = y > 0 ? 0u : 1u;
+                        x = x < 0 ? -x : x;
+                        y = y < 0 ? -y : y;
+                        if (t > 15) {
+                            const int lin = S.linbits[t];
+                            uint32_t ext = 0;
+                            int xbits = 0, lbx = 0, lby = 0;
+                            if (x > 14) { lbx = x - 15; x = 15; }
+                            if (y > 14) { lby = y - 15; y = 15; }
+                            const uint32_t cw = S.code[S.hoff[t] + x * 16 + y];
+                            if (x > 14) { ext |= (uint32_t)lbx; xbits += lin; }
+                            if (x != 0) { ext = (ext << 1) | sx; xbits += 1; }
+                            if (y > 14) { ext = (ext << lin) | (uint32_t)lby; xbits += lin; }
+                            if (y != 0) { ext = (ext << 1) | sy; xbits += 1; }
+                            bitsv = ((uint64_t)(cw >> 8) << xbits) | ext;
+                            nb = (int)(cw & 0xFF) + xbits;
+                        } else {
+                            const int dim = t < 2 ? 2 : (t < 4 ? 3 : (t < 7 ? 4 : (t < 10 ? 6 : (t < 13 ? 8 : 16))));
+                            const uint32_t cw = S.code[S.hoff[t] + x * dim + y];
+                            uint32_t code = cw >> 8;
+                            nb = (int)(cw & 0xFF);
+                            if (x != 0) { code = (code << 1) | sx; nb++; }
+                            if (y != 0) { code = (code << 1) | sy; nb++; }
+                            bitsv = code;
+                        }
+                    }
+                }
+                int inc = nb;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += v;
+                }
+                const int at = pos + inc - nb;
+                if (nb > 32) { put_bits_at(buf, at, (uint32_t)(bitsv >> 32), nb - 32); put_bits_at(buf, at + nb - 32, (uint32_t)bitsv, 32); }
+                else put_bits_at(buf, at, (uint32_t)bitsv, nb);
+                pos += __shfl_sync(FULL, inc, 31);
+                if (32 * (j + 1) >= bv) break;
+            }
+            // count1 quads (:1515-1547): p = v + 2 w + 4 x + 8 y on magnitudes, then the signs of the non-zero ones
+            for (int m0 = 0; m0 < count1; m0 += 32) {
+                const int m = m0 + lane;
+                uint32_t code = 0;
+                int nb = 0;
+                if (m < count1) {
+                    const uint32_t w0 = ix[bv + 2 * m], w1 = ix[bv + 2 * m + 1];
+                    int q[4] = {(int)(int16_t)(w0 & 0xFFFFu), (int)(int16_t)(w0 >> 16), (int)(int16_t)(w1 & 0xFFFFu), (int)(int16_t)(w1 >> 16)};
+                    uint32_t sgn = 0, idx = 0;
+                    int ns = 0;
+#pragma unroll
+                    for (int z = 0; z < 4; z++) {
+                        const int a = q[z] < 0 ? -q[z] : q[z];
+                        idx |= (uint32_t)(a & 1) << z;   // magnitudes are 0 or 1 in the count1 region
+                        if (a) { sgn = (sgn << 1) | (q[z] > 0 ? 0u : 1u); ns++; }
+                    }
+                    const uint32_t cw = S.code[S.hoff[32 + c1sel] + idx];
+                    code = ((cw >> 8) << ns) | sgn;
+                    nb = (int)(cw & 0xFF) + ns;
+                }
+                int inc = nb;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, inc, d);
+                    if (lane >= d) inc += v;
+                }
+                put_bits_at(buf, pos + inc - nb, code, nb);
+                pos += __shfl_sync(FULL, inc, 31);
+            }
+            // stuffing with one-bits up to part2_3_length (:1433-1446)
+            const int end = start + part23;
+            for (int b = pos + 32 * lane; b < end; b += 32 * 32) put_bits_at(buf, b, 0xFFFFFFFFu, min(32, end - b));
+            start = end;
+            __syncwarp();
+        }
+    __syncwarp();
+    // ---- copy out, clipped to what the reference's word-granular writer emits for the whole clip (A.E8)
+    const int64_t fo = byteoff[f];
+    const uint8_t *bb = (const uint8_t *)buf;
+    for (int i = lane; i < fbytes; i += 32)
+        if (fo + i < cl.out_len) out[cl.out_base + fo + i] = bb[i ^ 3];   // big-endian words -> byte stream
+}
+
+// ================================================================================================
+// host orchestration
+// ================================================================================================
+static const int kBitrates[16] = {-1, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, -1};
+
+static int sr_index_of(int sr) { return sr == 44100 ? 0 : sr == 48000 ? 1 : sr == 32000 ? 2 : -1; }
+static int br_index_of(int br)
+{
+    for (int i = 1; i < 15; i++)
+        if (kBitrates[i] == br) return i;
+    return -1;
+}
+
+// byte offset of every frame of a clip: whole_slots + padding, padding from the reference's float64 slot-lag recurrence (:504-513, :630-632)
+static void padding_prefix(int sample_rate, int bitrate_kbps, int64_t n_frames, std::vector<uint32_t> &off, int &whole)
+{
+    const double avg = (2.0 * 576 / (double)sample_rate) * (1000 * (double)bitrate_kbps / 8.0);
+    whole = (int)avg;
+    const double frac = avg - (double)whole;
+    double slot_lag = -frac;
+    off.assign((size_t)n_frames + 1, 0u);
+    int padding = 0;
+    for (int64_t f = 0; f < n_frames; f++) {
+        if (frac != 0) {
+            padding = slot_lag <= (frac - 1.0) ? 1 : 0;
+            slot_lag += padding - frac;
+        }
+        off[f + 1] = off[f] + (uint32_t)(whole + padding);
+    }
+}
 
 extern "C" int64_t m3s_encode_bound(int64_t n_samples, int32_t sample_rate, int32_t bitrate_kbps)
 {
@@ -9,13 +769,208 @@ extern "C" int64_t m3s_encode_bound(int64_t n_samples, int32_t sample_rate, int3
     return frames * fs + 8;
 }
 
-extern "C" int m3s_encode(m3s_handle_t h, const int16_t *, int, const int64_t *, const int64_t *, int32_t, int32_t, int32_t,
-                          const uint8_t *, const int64_t *, uint8_t *, const int64_t *, const int64_t *, int64_t *, int64_t *)
+static void build_enc_tables(const M3sDevTables *T, EncTables *E)
 {
-    return m3s_fail(h, M3S_ERR_STATE, "m3s_encode: not built yet");
+    memset(E, 0, sizeof *E);
+    const int books[4] = {13, 15, 16, 24};
+    for (int i = 0; i < 256; i++) {
+        uint32_t w = 0;
+        for (int b = 0; b < 4; b++) w |= (T->enc_hpacked[T->enc_hoff[books[b]] + i] & 0xFFu) << (8 * b);
+        E->hl4[i] = w;
+    }
+    for (int i = 0; i < 16; i++) {
+        E->hlc1[0][i] = (uint8_t)(T->enc_hpacked[T->enc_hoff[32] + i] & 0xFF);
+        E->hlc1[1][i] = (uint8_t)(T->enc_hpacked[T->enc_hoff[33] + i] & 0xFF);
+    }
+    // en(temp) = (int32)(log(temp * 4.768371584e-7) / 0.69314718) is monotone in temp: tabulate where it steps (host libm,
+    // the same one the reference's numbers come from) so that the device needs no log at all
+    auto en_of = [](uint32_t temp) { return (int)(log((double)temp * 4.768371584e-7) / 0.69314718); };
+    for (int j = 0; j < 32; j++) {
+        const int target = j - 20;
+        uint32_t lo = 1, hi = 0x7FFFFFFFu;
+        if (en_of(hi) < target) { E->en_thresh[j] = 0xFFFFFFFFu; continue; }
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (en_of(mid) >= target) hi = mid;
+            else lo = mid + 1;
+        }
+        E->en_thresh[j] = lo;
+    }
 }
 
-extern "C" int m3s_encode_taps(m3s_handle_t h, int32_t *, int32_t *, int32_t *, int32_t *)
+extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int64_t *pcm_off, const int64_t *n_samples,
+                          int32_t n_clips, int32_t sample_rate, int32_t bitrate_kbps, const uint8_t *payload_bits,
+                          const int64_t *payload_off, uint8_t *mp3_out, const int64_t *mp3_off, const int64_t *mp3_cap,
+                          int64_t *out_len, int64_t *hide_str_offset_out)
 {
-    return m3s_fail(h, M3S_ERR_STATE, "m3s_encode_taps: not built yet");
+    if (!h) return M3S_ERR_ARG;
+    h->enc_taps_ok = false;
+    if (!pcm || !n_samples || n_clips <= 0 || !mp3_out || !mp3_off) return m3s_fail(h, M3S_ERR_ARG, "encode: null argument");
+    if ((uintptr_t)pcm & 3) return m3s_fail(h, M3S_ERR_ARG, "encode: pcm must be 4-byte aligned (one stereo sample per word)");
+    const int sri = sr_index_of(sample_rate), bri = br_index_of(bitrate_kbps);
+    if (sri < 0) return m3s_fail(h, M3S_ERR_ARG, "encode: sample rate %d is not an MPEG-1 rate", sample_rate);
+    if (bri < 0) return m3s_fail(h, M3S_ERR_ARG, "encode: bitrate %d is not an MPEG-1 Layer III rate (WAV_Reader.py:112-114)", bitrate_kbps);
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    // ---- clip table
+    std::vector<M3sEncClip> clips(n_clips);
+    int64_t total_frames = 0, pcm_elems = 0, max_frames = 0, out_total = 0, pay_total = 0;
+    for (int i = 0; i < n_clips; i++) {
+        if (n_samples[i] < 0 || n_samples[i] % 1152) return m3s_fail(h, M3S_ERR_ARG, "encode: clip %d has %lld samples per channel, not a multiple of 1152 (the reference raises IndexError, MP3_Encoder.py:611-614)", i, (long long)n_samples[i]);
+        M3sEncClip &c = clips[i];
+        c.pcm_base = pcm_off ? pcm_off[i] : pcm_elems;
+        if (c.pcm_base & 1) return m3s_fail(h, M3S_ERR_ARG, "encode: pcm_off must be even (stereo samples)");
+        c.n_frames = (int32_t)(n_samples[i] / 1152);
+        c.frame_base = total_frames;
+        c.out_base = mp3_off[i];
+        c.payload_base = payload_bits && payload_off ? payload_off[i] : 0;
+        c.payload_len = payload_bits && payload_off ? payload_off[i + 1] - payload_off[i] : 0;
+        c.pad = 0;
+        total_frames += c.n_frames;
+        pcm_elems = std::max(pcm_elems, c.pcm_base + 2 * n_samples[i]);
+        max_frames = std::max<int64_t>(max_frames, c.n_frames);
+        pay_total = std::max(pay_total, c.payload_base + c.payload_len);
+    }
+    std::vector<uint32_t> byteoff;
+    int whole = 0;
+    padding_prefix(sample_rate, bitrate_kbps, max_frames, byteoff, whole);
+    for (int i = 0; i < n_clips; i++) {
+        M3sEncClip &c = clips[i];
+        c.out_len = (int64_t)(byteoff[c.n_frames] / 4) * 4;
+        if (mp3_cap && mp3_cap[i] < c.out_len) return m3s_fail(h, M3S_ERR_CAPACITY, "encode: clip %d needs %lld output bytes, capacity %lld", i, (long long)c.out_len, (long long)mp3_cap[i]);
+        out_total = std::max(out_total, c.out_base + c.out_len);
+        if (out_len) out_len[i] = c.out_len;
+        if (hide_str_offset_out) hide_str_offset_out[i] = 0;
+    }
+    if (total_frames == 0) return M3S_OK;
+    // ---- encoder constant tables (once per handle)
+    if (!h->e_tabs.p) {
+        std::vector<uint8_t> hostT(sizeof(M3sDevTables));
+        M3S_CUDA(h, cudaMemcpy(hostT.data(), h->d_tab, sizeof(M3sDevTables), cudaMemcpyDeviceToHost));
+        EncTables E;
+        build_enc_tables((const M3sDevTables *)hostT.data(), &E);
+        if ((rc = m3s_buf_reserve(h, h->e_tabs, sizeof(EncTables)))) return rc;
+        M3S_CUDA(h, cudaMemcpy(h->e_tabs.p, &E, sizeof E, cudaMemcpyHostToDevice));
+    }
+    // ---- inputs
+    const int16_t *d_pcm = pcm;
+    if (mem == M3S_MEM_HOST) {
+        if ((rc = m3s_buf_reserve(h, h->e_pcm, (size_t)pcm_elems * 2 + 16))) return rc;
+        M3S_CUDA(h, cudaMemcpyAsync(h->e_pcm.p, pcm, (size_t)pcm_elems * 2, cudaMemcpyHostToDevice, h->stream));
+        d_pcm = (const int16_t *)h->e_pcm.p;
+    }
+    uint8_t *d_out = mp3_out;
+    if (mem == M3S_MEM_HOST) {
+        if ((rc = m3s_buf_reserve(h, h->e_out, (size_t)out_total + 16))) return rc;
+        d_out = (uint8_t *)h->e_out.p;
+    }
+    if ((rc = m3s_buf_reserve(h, h->e_payload, (size_t)pay_total + 16))) return rc;
+    if (pay_total > 0) M3S_CUDA(h, cudaMemcpyAsync(h->e_payload.p, payload_bits, (size_t)pay_total, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = m3s_buf_reserve(h, h->e_clips, sizeof(M3sEncClip) * n_clips))) return rc;
+    M3S_CUDA(h, cudaMemcpyAsync(h->e_clips.p, clips.data(), sizeof(M3sEncClip) * n_clips, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = m3s_buf_reserve(h, h->e_pad, sizeof(uint32_t) * byteoff.size()))) return rc;
+    M3S_CUDA(h, cudaMemcpyAsync(h->e_pad.p, byteoff.data(), sizeof(uint32_t) * byteoff.size(), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = m3s_buf_reserve(h, h->e_state, sizeof(M3sEncState) * n_clips))) return rc;
+    M3S_CUDA(h, cudaMemsetAsync(h->e_state.p, 0, sizeof(M3sEncState) * n_clips, h->stream));
+    if ((rc = m3s_buf_reserve(h, h->e_lastix, (size_t)n_clips * 4 * 288 * 4))) return rc;
+
+    // ---- chunking: all clips advance together through windows of `cf` frames so that the intermediates
+    //      (MDCT spectra 9.2 KB/frame, quantised values 4.6 KB/frame) stay bounded while every clip keeps its warp busy
+    const int64_t budget_frames = h->enc_chunk_budget > 0 ? h->enc_chunk_budget : (1 << 19);
+    int64_t cf = std::max<int64_t>(1, budget_frames / n_clips);
+    if (cf >= max_frames) cf = max_frames;
+    const bool single_chunk = cf >= max_frames;
+    int64_t chunk_cap = 0;
+    for (int i = 0; i < n_clips; i++) chunk_cap += std::min<int64_t>(cf, clips[i].n_frames);
+    if ((rc = m3s_buf_reserve(h, h->e_mdct, (size_t)chunk_cap * 4 * 576 * 4))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->e_ix, (size_t)chunk_cap * 4 * 288 * 4))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->e_info, (size_t)chunk_cap * 4 * ENC_INFO_FIELDS * 4))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->e_gran, (size_t)chunk_cap * 4 * sizeof(M3sEncStats)))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->e_scfsi, (size_t)chunk_cap * 8))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->e_misc, (size_t)chunk_cap * 4))) return rc;
+
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
+    std::vector<M3sEncWork> work;
+    std::vector<int32_t> frame_clip;
+    std::vector<M3sEncClip> cclips(n_clips);
+    for (int64_t c0 = 0; c0 < max_frames; c0 += cf) {
+        // frames [c0, c0 + cf) of every clip; within the chunk buffers clip i's frames start at chunk-local base
+        work.clear();
+        frame_clip.clear();
+        int64_t base = 0;
+        cclips = clips;
+        for (int i = 0; i < n_clips; i++) {
+            const int64_t nfc = std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0));
+            // chunk-local frame slot of clip frame f is  base + (f - c0)  ==  (frame_base' + f) - chunk_frame0 with frame_base' = base - c0, chunk_frame0 = 0
+            cclips[i].frame_base = base - c0;
+            for (int64_t g = 2 * c0; g < 2 * (c0 + nfc); g += ENC_RUN) {
+                M3sEncWork w;
+                w.clip = i; w.g_first = (int32_t)g; w.count = (int32_t)std::min<int64_t>(ENC_RUN, 2 * (c0 + nfc) - g); w.pad = 0;
+                work.push_back(w);
+            }
+            for (int64_t k = 0; k < nfc; k++) frame_clip.push_back(i);
+            base += nfc;
+        }
+        const int64_t chunk_total = base;
+        if (chunk_total == 0) break;
+        if ((rc = m3s_buf_reserve(h, h->e_work, sizeof(M3sEncWork) * work.size()))) return rc;
+        M3S_CUDA(h, cudaMemcpyAsync(h->e_work.p, work.data(), sizeof(M3sEncWork) * work.size(), cudaMemcpyHostToDevice, h->stream));
+        M3S_CUDA(h, cudaMemcpyAsync(h->e_misc.p, frame_clip.data(), sizeof(int32_t) * frame_clip.size(), cudaMemcpyHostToDevice, h->stream));
+        M3S_CUDA(h, cudaMemcpyAsync(h->e_clips.p, cclips.data(), sizeof(M3sEncClip) * n_clips, cudaMemcpyHostToDevice, h->stream));
+        M3S_KBEGIN(h, M3S_K_ENC_ANALYSIS);
+        k_enc_analysis<<<(unsigned)work.size(), ANA_THREADS, 0, h->stream>>>(
+            d_pcm, (const M3sEncClip *)h->e_clips.p, (const M3sEncWork *)h->e_work.p, h->d_tab, (const EncTables *)h->e_tabs.p, sri, 0,
+            (int32_t *)h->e_mdct.p, (M3sEncStats *)h->e_gran.p);
+        M3S_LAUNCH_CHECK(h);
+        M3S_KBEGIN(h, M3S_K_ENC_RATE);
+        k_enc_rate<<<(unsigned)n_clips, 32, sizeof(RateSmem), h->stream>>>(
+            (const M3sEncClip *)h->e_clips.p, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p,
+            (const uint32_t *)h->e_pad.p, (const uint8_t *)h->e_payload.p, sri, whole, (int32_t)c0, (int32_t)cf, 0,
+            (const int32_t *)h->e_mdct.p, (const M3sEncStats *)h->e_gran.p, (uint32_t *)h->e_ix.p, (int32_t *)h->e_info.p,
+            (uint8_t *)h->e_scfsi.p, (uint32_t *)h->e_lastix.p);
+        M3S_LAUNCH_CHECK(h);
+        M3S_KBEGIN(h, M3S_K_ENC_PACK);
+        k_enc_pack<<<(unsigned)((chunk_total + PACK_WARPS - 1) / PACK_WARPS), 32 * PACK_WARPS, sizeof(PackSmem), h->stream>>>(
+            (const M3sEncClip *)h->e_clips.p, (const int32_t *)h->e_misc.p, h->d_tab, (const uint32_t *)h->e_pad.p, sri, bri, whole, 0,
+            chunk_total, (const uint32_t *)h->e_ix.p, (const int32_t *)h->e_info.p, (const uint8_t *)h->e_scfsi.p, d_out);
+        M3S_LAUNCH_CHECK(h);
+        // the host vectors above are reused by the next chunk: their copies must have been consumed
+        M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    // ---- results
+    std::vector<M3sEncState> states(n_clips);
+    M3S_CUDA(h, cudaMemcpyAsync(states.data(), h->e_state.p, sizeof(M3sEncState) * n_clips, cudaMemcpyDeviceToHost, h->stream));
+    if (mem == M3S_MEM_HOST) M3S_CUDA(h, cudaMemcpyAsync(mp3_out, d_out, (size_t)out_total, cudaMemcpyDeviceToHost, h->stream));
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (hide_str_offset_out)
+        for (int i = 0; i < n_clips; i++) hide_str_offset_out[i] = states[i].hide_off;
+    h->enc_taps_ok = single_chunk;
+    h->enc_total_frames = total_frames;
+    h->enc_n_clips = n_clips;
+    return M3S_OK;
+}
+
+extern "C" int m3s_encode_taps(m3s_handle_t h, int32_t *mdct, int32_t *ix, int32_t *info, int32_t *scfsi)
+{
+    if (!h) return M3S_ERR_ARG;
+    if (!h->enc_taps_ok) return m3s_fail(h, M3S_ERR_STATE, "encode_taps: the last m3s_encode ran in several chunks (or failed); taps need a single-chunk batch");
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    const int64_t nf = h->enc_total_frames;
+    if (mdct) M3S_CUDA(h, cudaMemcpyAsync(mdct, h->e_mdct.p, (size_t)nf * 4 * 576 * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (info) M3S_CUDA(h, cudaMemcpyAsync(info, h->e_info.p, (size_t)nf * 4 * ENC_INFO_FIELDS * 4, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int16_t> ix16;
+    std::vector<uint8_t> sc8;
+    if (ix) {
+        ix16.resize((size_t)nf * 4 * 576);
+        M3S_CUDA(h, cudaMemcpyAsync(ix16.data(), h->e_ix.p, ix16.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (scfsi) {
+        sc8.resize((size_t)nf * 8);
+        M3S_CUDA(h, cudaMemcpyAsync(sc8.data(), h->e_scfsi.p, sc8.size(), cudaMemcpyDeviceToHost, h->stream));
+    }
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (ix) for (size_t i = 0; i < ix16.size(); i++) ix[i] = ix16[i];
+    if (scfsi) for (size_t i = 0; i < sc8.size(); i++) scfsi[i] = sc8[i];
+    return M3S_OK;
 }
