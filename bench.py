@@ -1,17 +1,22 @@
 #!/usr/bin/env python3
-"""bench.py -- throughput of the mp3stego hot path on B200 (contract: see the task brief / DESIGN.md "Measurement").
+"""bench.py -- throughput of the mp3stego hot path on B200 (contract: task brief; DESIGN.md "Measurement").
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            product arm (CUDA path through the C ABI)
   python bench.py --impl reference [...]                          CPU arm: the oracle port on all host cores
   torchrun --nproc-per-node N ... bench.py --gpus N ...           one rank per GPU, files sharded by rank (weak scaling)
 
-A step is ONE pass of decode+reveal over the whole per-GPU corpus (BASELINE.json configs[1]: 1,000 synthetic
-320 kbps 44.1 kHz stereo 3-minute MP3s = 6.89 M frames), processed in HBM-sized waves of files.
-  value        frames/s with the MP3 bytes already resident in HBM (device pointers through the C ABI)
-  e2e          the same through the C ABI with HOST buffers: H2D of the MP3 bytes and D2H of PCM + reveal bits timed
-  roofline     the dominant kernel's algorithmic bytes (5,652.9 B/frame) over its mean device time
-  cpu_baseline the oracle port on one host core over a bounded sample of the same corpus
-  encode_hide  (second half of the metric) BASELINE.json configs[2]: WAV -> 128 kbps MP3 hiding a full-capacity payload
+Corpus (per GPU, synthetic): `--files` tone+noise 44.1 kHz stereo WAVs of `--frames` frames, generated
+on the device; the decode corpus is those WAVs encoded to 320 kbps by the product's own encoder (bit-exact with the
+reference encoder -- tests/test_parity_encode.py), one MP3 per file.
+
+A step is ONE pass over the whole per-GPU corpus, processed in waves of `--wave` files:
+  decode+reveal (the JSON line's metric; BASELINE.json configs[1]: 1,000 x 3-minute 320 kbps files = 6.89 M frames)
+      value        frames/s with the MP3 bytes resident in HBM (device pointers through the C ABI)
+      e2e          the same through the C ABI with HOST buffers: H2D of MP3 bytes, D2H of PCM + table ids + reveal bits
+      roofline     dominant kernel: algorithmic bytes (5,652.9 B/frame) over its mean device time
+      cpu_baseline the oracle port on one host core over a bounded sample of the same corpus
+  encode+hide  (key "encode_hide"; configs[2]: the same WAVs -> 128 kbps hiding a random payload beyond capacity)
+      the same five figures for the encoder.
 The oracle is used ONLY by the cpu_baseline / --impl reference legs.
 """
 import argparse
@@ -33,6 +38,7 @@ for p in (ROOT, PKG):
 DEC_BYTES_PER_FRAME = 1044.9 + 4608.0   # compressed frame @320k + int16 stereo PCM
 ENC_BYTES_PER_FRAME = 4608.0 + 417.96   # int16 stereo PCM + compressed frame @128k
 FRAMES_PER_FILE = 6890                  # 3 minutes at 44.1 kHz (7,937,280 samples)
+PAYLOAD_BITS_PER_FRAME = 14             # measured capacity is 11-12 bits/frame: the payload always exceeds it
 
 
 def log(*a):
@@ -40,73 +46,45 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------------
-# corpus
+# synthetic corpus
 # ------------------------------------------------------------------------------------------------
-def _frame_sizes(mp3: bytes):
-    """Byte offsets / sizes of the MPEG-1 Layer III frames of a clean CBR clip (host-side header walk)."""
-    rates = [0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320]
-    srs = [44100, 48000, 32000]
-    off, out = 0, []
-    while off + 4 < len(mp3) and mp3[off] == 0xFF and mp3[off + 1] >= 0xE0:
-        b2 = mp3[off + 2]
-        fs = 144000 * rates[b2 >> 4] // srs[(b2 >> 2) & 3] + ((b2 >> 1) & 1)
-        out.append((off, fs))
-        off += fs
-    return out
+def synth_pcm_host(n_frames, seed):
+    """SURVEY.md 8(d) tone+noise clip on the host (cpu / reference legs): int16 [n, 2]."""
+    rng = np.random.default_rng(seed)
+    n = n_frames * 1152
+    t = np.arange(n) / 44100.0
+    f = rng.uniform(100, 5000, size=2)
+    x = np.stack([0.4 * np.sin(2 * np.pi * f[c] * t) + 0.05 * rng.standard_normal(n) for c in range(2)], axis=1)
+    return (x * 32767).astype(np.int16)
 
 
-def _pad_clip(mp3: bytes) -> bytes:
-    """The reference's bit writer drops the last 0-3 bytes (4-byte flush, MP3_Encoder.py:1370-1392): pad the last
-    frame back to its nominal size so that clips can be laid end to end as one valid stream."""
-    fr = _frame_sizes(mp3)
-    end = fr[-1][0] + fr[-1][1]
-    return mp3 + b"\x00" * max(0, end - len(mp3))
-
-
-def fixture_clips_320():
-    """Reference-encoded 320 kbps clips committed under tests/golden (every frame has main_data_begin = 0)."""
-    g = os.path.join(ROOT, "tests", "golden")
-    clips = [open(os.path.join(g, n), "rb").read() for n in
-             ("test.mp3", "ref_test_enc320.mp3", "ref_test_hid.mp3", "ref_test_cleared.mp3", "ref_test_hid_long.mp3")]
-    for n in ("ref_synth_s12_320_plain.npz", "ref_synth_s12_320_hide.npz"):
-        clips.append(np.load(os.path.join(g, n))["mp3"].tobytes())
-    return [np.frombuffer(_pad_clip(c), np.uint8) for c in clips], [len(_frame_sizes(c)) for c in clips]
-
-
-def synth_pcm_device(torch, n_files, n_frames, seed0, device):
-    """SURVEY.md 8(d) tone+noise WAVs generated on the device (setup only; torch is plumbing here):
-    L/R = 0.4 sin(2 pi f t) + 0.05 N(0,1), f ~ U[100, 5000] Hz, *32767 -> int16, interleaved stereo."""
+def synth_pcm_device(torch, n_files, n_frames, seed, device):
+    """The same recipe on the device (setup only; torch is plumbing): int16 [n_files, 2 * n] interleaved stereo."""
     n = n_frames * 1152
     g = torch.Generator(device=device)
-    g.manual_seed(seed0)
-    f = torch.rand((n_files, 1, 2), generator=g, device=device) * 4900.0 + 100.0
-    t = (torch.arange(n, device=device, dtype=torch.float64) / 44100.0).reshape(1, n, 1)
-    x = 0.4 * torch.sin((2 * np.pi) * f.double() * t).float()
-    x += 0.05 * torch.randn((n_files, n, 2), generator=g, device=device)
-    return (x * 32767.0).to(torch.int16).reshape(n_files, n * 2)
+    g.manual_seed(seed)
+    f = torch.rand((n_files, 1, 2), generator=g, device=device, dtype=torch.float64) * 4900.0 + 100.0
+    out = torch.empty((n_files, n, 2), dtype=torch.int16, device=device)
+    step = max(1, (1 << 26) // max(n, 1))
+    idx = torch.arange(n, device=device, dtype=torch.float64).reshape(1, n, 1)
+    for lo in range(0, n_files, step):
+        hi = min(n_files, lo + step)
+        ph = torch.remainder(f[lo:hi] * (idx / 44100.0), 1.0).float()        # phase in turns, reduced in float64
+        x = 0.4 * torch.sin(ph * (2 * np.pi))
+        x += 0.05 * torch.randn((hi - lo, n, 2), generator=g, device=device)
+        out[lo:hi] = (x * 32767.0).to(torch.int16)
+    return out.reshape(n_files, n * 2)
 
 
-def build_corpus_host(n_files, frames_per_file, seed):
-    """Concatenate fixture clips (random order per file) into n_files streams of ~frames_per_file frames."""
-    clips, nfr = fixture_clips_320()
+def random_payload_bits(n_files, bits_per_file, seed):
+    """Random 7-bit ASCII (rng.integers(32, 127)) as '0'/'1' chars, all files end to end + offsets."""
     rng = np.random.default_rng(seed)
-    files, frames = [], []
-    for _ in range(n_files):
-        parts, tot = [], 0
-        while tot < frames_per_file:
-            i = int(rng.integers(0, len(clips)))
-            if tot + nfr[i] > frames_per_file:
-                # finish with leading frames of a clip
-                fs = _frame_sizes(clips[i].tobytes())
-                k = frames_per_file - tot
-                parts.append(clips[i][: fs[k - 1][0] + fs[k - 1][1]])
-                tot += k
-            else:
-                parts.append(clips[i])
-                tot += nfr[i]
-        files.append(np.concatenate(parts))
-        frames.append(tot)
-    return files, frames
+    nbytes = (bits_per_file + 7) // 8
+    chars = rng.integers(32, 127, size=(n_files, nbytes), dtype=np.uint8)
+    bits = np.unpackbits(chars, axis=1)[:, :bits_per_file]
+    packed = (bits + ord("0")).astype(np.uint8).reshape(-1)
+    off = np.arange(n_files + 1, dtype=np.int64) * bits_per_file
+    return packed, off
 
 
 # ------------------------------------------------------------------------------------------------
@@ -137,21 +115,23 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, reasons = [], set()
+        sm, power, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
                 sm.append(float(r[0]))
                 out["sm_max_mhz"] = float(r[1])
+                power.append(float(r[2]))
                 for k, nme in enumerate(names):
                     if r[3 + k].strip().lower().startswith("active"):
                         reasons.add(nme)
             except (ValueError, IndexError):
                 continue
         if sm:
-            hi = [v for v in sm if v >= 0.5 * max(sm)]   # samples under load
+            hi = [v for v, p in zip(sm, power) if p >= 0.6 * max(power)] or sm   # samples under load
             out["sm_mhz"] = float(np.median(hi))
             out["samples"] = len(sm)
+            out["power_w_max"] = max(power)
         out["reasons"] = sorted(reasons)
         return out
 
@@ -165,19 +145,54 @@ def _cpu_decode_worker(blob):
     return int(r["n_frames"]), len(r["bits"])
 
 
-def cpu_decode_sample(blobs, procs):
-    """Decode+reveal `blobs` with the oracle on `procs` processes; returns (frames, seconds)."""
+def _cpu_encode_worker(args):
+    from oracle import oracle as O
+    pcm, bitrate, bits = args
+    r = O.encode(pcm, 44100, bitrate, bits, taps=False)
+    return int(r["n_frames"]), r["mp3"]
+
+
+def _pool_map(fn, items, procs):
+    if procs <= 1:
+        return [fn(i) for i in items]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(procs) as pool:
+        return pool.map(fn, items, chunksize=1)
+
+
+def cpu_sample_clips(n_clips, n_frames, seed):
     from oracle import oracle as O
     O.build()
+    pcms = [synth_pcm_host(n_frames, seed + i) for i in range(n_clips)]
+    return pcms
+
+
+def cpu_baselines(n_frames, procs, n_clips):
+    """Encode+hide @128k and decode+reveal @320k of n_clips tone+noise clips with the oracle on `procs` processes.
+    Returns {"decode": (frames, s), "encode": (frames, s)}."""
+    pcms = cpu_sample_clips(n_clips, n_frames, 4242)
+    packed, off = random_payload_bits(n_clips, PAYLOAD_BITS_PER_FRAME * n_frames, 7)
+    bits = [packed[off[i]:off[i + 1]].tobytes().decode("ascii") for i in range(n_clips)]
+    mp3s = [m for _, m in _pool_map(_cpu_encode_worker, [(p, 320, "") for p in pcms], procs)]   # decode inputs (untimed)
     t0 = time.perf_counter()
-    if procs <= 1:
-        res = [_cpu_decode_worker(b) for b in blobs]
-    else:
-        import multiprocessing as mp
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_cpu_decode_worker, blobs, chunksize=1)
-    dt = time.perf_counter() - t0
-    return sum(r[0] for r in res), dt
+    res = _pool_map(_cpu_encode_worker, [(p, 128, b) for p, b in zip(pcms, bits)], procs)
+    t_enc = time.perf_counter() - t0
+    f_enc = sum(r[0] for r in res)
+    t0 = time.perf_counter()
+    res = _pool_map(_cpu_decode_worker, mp3s, procs)
+    t_dec = time.perf_counter() - t0
+    f_dec = sum(r[0] for r in res)
+    return {"decode": (f_dec, t_dec), "encode": (f_enc, t_enc)}
+
+
+def corpus_config(args):
+    return {"workload": f"configs[1]: batch decode+reveal of {args.files} synthetic 320 kbps 44.1 kHz stereo "
+                        f"{args.frames * 1152 / 44100.0:.0f}-s MP3s per GPU ({args.files * args.frames} frames); "
+                        f"encode_hide = configs[2]: the same WAVs -> 128 kbps hiding random ASCII beyond capacity",
+            "files_per_gpu": args.files, "frames_per_file": args.frames, "wave_files": args.wave,
+            "l2": "inputs larger than L2 (every wave streams >= 0.9 GB of MP3 / >= 4 GB of PCM)",
+            "corpus": "tone+noise WAVs (SURVEY 8d) generated on device; MP3s produced from them by the product encoder "
+                      "(byte-identical to the reference encoder's output)"}
 
 
 def run_reference_arm(args):
@@ -185,39 +200,52 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames_per_blob = 1378  # one fifth of a 3-minute file per worker per step keeps a step to a few seconds
-    files, frames = build_corpus_host(cores, frames_per_blob, seed=12345)
-    blobs = [f.tobytes() for f in files]
+    n_frames = 689      # one tenth of a 3-minute file per worker per step keeps a step to a few seconds
     for _ in range(args.warmup):
-        cpu_decode_sample(blobs[: max(1, cores // 4)], cores)
-    tot_f, tot_t = 0, 0.0
+        cpu_baselines(60, cores, cores)
+    dec_f = dec_t = enc_f = enc_t = 0.0
     for _ in range(args.steps):
-        f, t = cpu_decode_sample(blobs, cores)
-        tot_f += f
-        tot_t += t
-    v = tot_f / tot_t
-    sample = f"{cores} clips x {frames_per_blob} frames of the 320 kbps corpus per step, one process per host core"
+        r = cpu_baselines(n_frames, cores, cores)
+        dec_f += r["decode"][0]; dec_t += r["decode"][1]
+        enc_f += r["encode"][0]; enc_t += r["encode"][1]
+    v = dec_f / dec_t
+    sample = f"{cores} clips x {n_frames} frames of the tone+noise corpus per step, one oracle process per host core"
     line = {"impl": "reference", "metric": "decode+reveal throughput (MP3 frames/s)", "value": v, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dec_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": corpus_config(args),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "audio_seconds_per_s": v * 1152 / 44100.0}
+            "audio_seconds_per_s": v * 1152 / 44100.0,
+            "encode_hide": {"value": enc_f / enc_t, "unit": "frames/s", "ms_per_step": 1e3 * enc_t / args.steps,
+                            "e2e": {"value": enc_f / enc_t, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                            "cpu_baseline": {"value": enc_f / enc_t, "unit": "frames/s", "cores": cores, "kind": "port",
+                                             "sample": sample}}}
     print(json.dumps(line), flush=True)
-
-
-def corpus_config(args):
-    return {"workload": f"configs[1]: batch decode+reveal of {args.files} synthetic 320 kbps 44.1 kHz stereo "
-                        f"{args.frames * 1152 / 44100.0:.0f}-s MP3s per GPU ({args.files * args.frames} frames)",
-            "files_per_gpu": args.files, "frames_per_file": args.frames, "wave_files": args.wave,
-            "l2": "inputs larger than L2 (each wave reads >= 0.9 GB of MP3 and writes >= 4 GB of PCM)",
-            "corpus": "reference-encoded 320 kbps clips (tests/golden) laid end to end in seeded random order"}
 
 
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
+def roofline_of(ktimes, names, frames_total, bytes_per_frame, peak, peak_src, steps, whole_frac):
+    ks = {k: v for k, v in ktimes.items() if k in names}
+    if not ks:
+        return None
+    dom, (ms_total, n_l) = max(ks.items(), key=lambda kv: kv[1][0])
+    fpl = frames_total / n_l
+    ach = bytes_per_frame * fpl / (ms_total / n_l * 1e-3) / 1e9
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom, {}).get("bytes_per_frame")
+        traffic = None if t is None else t * fpl
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": ms_total / n_l, "frames_per_launch": fpl,
+            "algorithmic_bytes_per_frame": bytes_per_frame,
+            "kernel_ms_per_step": {k: v[0] / steps for k, v in sorted(ks.items())}, "whole_path_frac": whole_frac}
+
+
 def run_product_arm(args):
     import torch
     import __graft_entry__ as ge
@@ -236,54 +264,79 @@ def run_product_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- corpus: per-rank shard of files (weak scaling: every rank holds `files` files)
-    t0 = time.perf_counter()
-    files, frames = build_corpus_host(args.files, args.frames, seed=1000 + rank)
-    sizes = np.array([len(f) for f in files], np.int64)
-    n_waves = (args.files + args.wave - 1) // args.wave
-    waves = []
-    for w in range(n_waves):
-        lo, hi = w * args.wave, min(args.files, (w + 1) * args.wave)
-        off = np.concatenate([[0], np.cumsum(sizes[lo:hi])])
-        host = torch.empty(int(off[-1]) + 64, dtype=torch.uint8, pin_memory=True)
-        hv = host.numpy()
-        for i in range(lo, hi):
-            hv[off[i - lo]: off[i - lo + 1]] = files[i]
-        waves.append(dict(off=off, host=host, dev=host.to(dev), frames=int(sum(frames[lo:hi])), n=hi - lo))
-    del files
-    total_frames = sum(w["frames"] for w in waves)
-    max_wave_frames = max(w["frames"] for w in waves)
-    log(f"[rank {rank}] corpus: {args.files} files, {total_frames} frames, {sizes.sum() / 1e9:.2f} GB in {n_waves} waves "
-        f"({time.perf_counter() - t0:.1f}s)")
-
     h = _lib.Handle(local)
     stream = torch.cuda.Stream(device=dev)   # the library launches on this stream, and so do the timing events
     h.set_stream(stream.cuda_stream)
-    pcm_dev = torch.empty(max_wave_frames * 1152 * 2 + 64, dtype=torch.int16, device=dev)
-    pcm_host = torch.empty(max_wave_frames * 1152 * 2 + 64, dtype=torch.int16, pin_memory=True)
+
+    # ---- corpus: per-rank shard of files (weak scaling: every rank holds `files` files), in waves
+    t0 = time.perf_counter()
+    nw = (args.files + args.wave - 1) // args.wave
+    n_samp = args.frames * 1152
+    waves = []
+    pay_bits = PAYLOAD_BITS_PER_FRAME * args.frames
+    for w in range(nw):
+        lo, hi = w * args.wave, min(args.files, (w + 1) * args.wave)
+        nf = hi - lo
+        pcm = synth_pcm_device(torch, nf, args.frames, 100000 * rank + 1000 + w, dev).reshape(-1)
+        torch.cuda.synchronize()
+        ns = [n_samp] * nf
+        res = h.encode(pcm, ns, 44100, 320, compact=True)                    # decode corpus (setup, untimed)
+        off = np.concatenate([res["mp3_off"], [res["mp3_off"][-1] + res["out_len"][-1]]]).astype(np.int64)
+        mp3 = res["mp3"][: int(off[-1]) + 16].clone()
+        pay, pay_off = random_payload_bits(nf, pay_bits, 31 * rank + w)
+        waves.append(dict(n=nf, frames=nf * args.frames, ns=ns, pcm_dev=pcm, pcm_host=pcm.cpu().pin_memory(),
+                          mp3_dev=mp3, mp3_host=mp3.cpu().pin_memory(), off=off, pay=pay, pay_off=pay_off))
+        del res
+    total_frames = sum(w["frames"] for w in waves)
+    max_wave_frames = max(w["frames"] for w in waves)
+    mp3_bytes = int(sum(w["off"][-1] for w in waves))
+    log(f"[rank {rank}] corpus: {args.files} files x {args.frames} frames = {total_frames} frames, "
+        f"{mp3_bytes / 1e9:.2f} GB MP3 @320k, {total_frames * 4608 / 1e9:.2f} GB PCM, {nw} waves ({time.perf_counter() - t0:.1f}s)")
+
+    pcm_out_dev = torch.empty(max_wave_frames * 1152 * 2 + 64, dtype=torch.int16, device=dev)
+    pcm_out_host = torch.empty(max_wave_frames * 1152 * 2 + 64, dtype=torch.int16, pin_memory=True)
     ids_dev = torch.empty(max_wave_frames * 12, dtype=torch.uint8, device=dev)
     bits_dev = torch.empty(max_wave_frames * 12, dtype=torch.uint8, device=dev)
     ids_host = np.zeros(max_wave_frames * 12, np.uint8)
     bits_host = np.zeros(max_wave_frames * 12, np.uint8)
-    reveal_total = [0]
+    enc_cap = int(max(_lib.load().m3s_encode_bound(n_samp, 44100, 128) * w["n"] for w in waves)) + 64
+    enc_out_dev = torch.empty(enc_cap, dtype=torch.uint8, device=dev)
+    enc_out_host = torch.empty(enc_cap, dtype=torch.uint8, pin_memory=True)
+    check = {}
 
-    def step_device():
+    def dec_device():
         n = 0
         for w in waves:
-            sc = h.decode_scan(w["dev"], w["off"])
+            sc = h.decode_scan(w["mp3_dev"], w["off"])
             ln = h.decode_reveal_into(ids_dev, bits_dev)
-            h.decode_run(pcm=pcm_dev)
+            h.decode_run(pcm=pcm_out_dev)
             n += int(sc["n_frames"].sum())
-            reveal_total[0] = int(ln.sum())
+            check["reveal_bits"] = int(ln.sum())
         return n
 
-    def step_host():
+    def dec_host():
         n = 0
         for w in waves:
-            sc = h.decode_scan(w["host"], w["off"])
+            sc = h.decode_scan(w["mp3_host"], w["off"])
             h.decode_reveal_into(ids_host, bits_host)
-            h.decode_run(pcm=pcm_host)
+            h.decode_run(pcm=pcm_out_host)
             n += int(sc["n_frames"].sum())
+        return n
+
+    def enc_device():
+        n = 0
+        for w in waves:
+            r = h.encode(w["pcm_dev"], w["ns"], 44100, 128, payload_packed=(w["pay"], w["pay_off"]), mp3_out=enc_out_dev)
+            n += w["frames"]
+            check["hide_off"] = int(r["hide_str_offset"].sum())
+            check["enc_bytes"] = int(r["out_len"].sum())
+        return n
+
+    def enc_host():
+        n = 0
+        for w in waves:
+            h.encode(w["pcm_host"], w["ns"], 44100, 128, payload_packed=(w["pay"], w["pay_off"]), mp3_out=enc_out_host)
+            n += w["frames"]
         return n
 
     def barrier():
@@ -293,7 +346,6 @@ def run_product_arm(args):
 
     def timed(fn, steps):
         barrier()
-        h.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         t0 = time.perf_counter()
@@ -303,36 +355,12 @@ def run_product_arm(args):
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        ms = max(e0.elapsed_time(e1), 0.0)
-        t = torch.tensor([ms / 1e3, wall], dtype=torch.float64, device=dev)
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3, wall], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         barrier()
         return n, float(t[0].item()), float(t[1].item())
 
-    # ---- warm-up, then the timed device-resident region
-    for _ in range(args.warmup):
-        step_device()
-    h.timing_enable(True)
-    l0 = h.launches
-    clocks = ClockSampler(local)
-    n_dev, t_dev, wall_dev = timed(step_device, args.steps)
-    clk = clocks.stop()
-    launches = h.launches - l0
-    ktimes = h.timing()
-    h.timing_enable(False)
-    assert n_dev == total_frames * args.steps, (n_dev, total_frames)
-
-    # ---- end-to-end through the C ABI with host buffers
-    step_host()
-    n_e2e, t_e2e, _ = timed(step_host, args.steps)
-    h2d = int(sizes.sum())
-    d2h = int(total_frames * 1152 * 2 * 2 + 2 * 12 * total_frames)
-
-    value = world * n_dev / t_dev
-    e2e_value = world * n_e2e / t_e2e
-
-    # ---- roofline of the dominant kernel
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -340,47 +368,68 @@ def run_product_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
-    dom = max(ktimes.items(), key=lambda kv: kv[1][0]) if ktimes else (None, (0.0, 0))
-    roof = None
-    if dom[0]:
-        ms_total, n_l = dom[1]
-        frames_per_launch = n_dev / n_l
-        ach = DEC_BYTES_PER_FRAME * frames_per_launch / (ms_total / n_l * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom[0], {}).get("bytes_per_frame")
-            if traffic is not None:
-                traffic = traffic * frames_per_launch
-        except Exception:
-            pass
-        roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": ms_total / n_l,
-                "frames_per_launch": frames_per_launch, "algorithmic_bytes_per_frame": DEC_BYTES_PER_FRAME,
-                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(ktimes.items())},
-                "whole_path_frac": value / world * DEC_BYTES_PER_FRAME / 1e9 / peak}
+    DEC_K = ("k_walk", "k_fscan", "k_sideinfo", "k_strip", "k_huff", "k_hybrid")
+    ENC_K = ("k_enc_analysis", "k_enc_rate", "k_enc_pack")
+
+    def measure(dev_fn, host_fn, knames, bpf):
+        for _ in range(args.warmup):
+            dev_fn()
+        h.timing_enable(True)
+        l0 = h.launches
+        clocks = ClockSampler(local)
+        n_dev, t_dev, wall = timed(dev_fn, args.steps)
+        clk = clocks.stop()
+        launches = h.launches - l0
+        kt = h.timing()
+        h.timing_enable(False)
+        assert n_dev == total_frames * args.steps, (n_dev, total_frames)
+        host_fn()
+        n_e2e, t_e2e, _ = timed(host_fn, args.steps)
+        value = world * n_dev / t_dev
+        roof = roofline_of(kt, knames, n_dev, bpf, peak, peak_src, args.steps, value / world * bpf / 1e9 / peak)
+        return dict(value=value, ms_per_step=1e3 * t_dev / args.steps, e2e_value=world * n_e2e / t_e2e,
+                    e2e_ms=1e3 * t_e2e / args.steps, launches=int(launches), clocks=clk, roofline=roof, wall=wall)
+
+    D = measure(dec_device, dec_host, DEC_K, DEC_BYTES_PER_FRAME)
+    log(f"[rank {rank}] decode+reveal: {D['value']:.4g} frames/s device-resident, {D['e2e_value']:.4g} e2e")
+    E = None
+    if not args.no_encode:
+        E = measure(enc_device, enc_host, ENC_K, ENC_BYTES_PER_FRAME)
+        log(f"[rank {rank}] encode+hide:   {E['value']:.4g} frames/s device-resident, {E['e2e_value']:.4g} e2e")
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline: the oracle port on one host core over a bounded sample of the same corpus
-    sample_files, _ = build_corpus_host(1, min(args.frames, 6890 * 3), seed=777)
-    sample_files = [sample_files[0].tobytes()] * (3 if args.frames >= 6890 else 1)
-    cf, ct = cpu_decode_sample(sample_files, 1)
-    cpu = {"value": cf / ct, "unit": "frames/s", "cores": 1, "kind": "port",
-           "sample": f"{len(sample_files)} x {cf // len(sample_files)}-frame 320 kbps files of the same corpus, "
-                     f"oracle/mp3stego_oracle.c decode+reveal, 1 thread of {os.cpu_count()} host cores, {ct:.1f} s"}
+    # ---- CPU baseline: the oracle port on one host core over a bounded sample of the same kind of corpus
+    cb = cpu_baselines(min(args.frames, 6890), 1, 3 if args.frames >= 2000 else 1)
+    ncore = os.cpu_count()
 
-    line = {"metric": "decode+reveal throughput (MP3 frames/s)", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+    def cpu_obj(key, what):
+        f, t = cb[key]
+        return {"value": f / t, "unit": "frames/s", "cores": 1, "kind": "port",
+                "sample": f"{what} of {f} frames (tone+noise clips of {min(args.frames, 6890)} frames), oracle/mp3stego_oracle.c, "
+                          f"1 thread of {ncore} host cores, {t:.1f} s"}
+
+    line = {"metric": "decode+reveal throughput (MP3 frames/s)", "value": D["value"], "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": D["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": corpus_config(args),
-            "audio_seconds_per_s": value * 1152 / 44100.0,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "wall_s_timed_region": wall_dev, "reveal_bits_last_wave": reveal_total[0]}
+            "audio_seconds_per_s": D["value"] * 1152 / 44100.0,
+            "e2e": {"value": D["e2e_value"], "unit": "frames/s", "h2d_bytes_per_step": mp3_bytes,
+                    "d2h_bytes_per_step": int(total_frames * (1152 * 2 * 2 + 24)), "ms_per_step": D["e2e_ms"]},
+            "gpu_launches": D["launches"] + (E["launches"] if E else 0), "clocks": D["clocks"], "roofline": D["roofline"],
+            "cpu_baseline": cpu_obj("decode", "decode+reveal @320k"),
+            "check": check}
+    if E:
+        line["encode_hide"] = {
+            "metric": "encode+hide throughput (MP3 frames/s)", "value": E["value"], "unit": "frames/s", "dtype": "int32",
+            "ms_per_step": E["ms_per_step"], "audio_seconds_per_s": E["value"] * 1152 / 44100.0,
+            "e2e": {"value": E["e2e_value"], "unit": "frames/s", "h2d_bytes_per_step": int(total_frames * 4608 + len(waves[0]["pay"]) * nw),
+                    "d2h_bytes_per_step": int(check.get("enc_bytes", 0) * nw), "ms_per_step": E["e2e_ms"]},
+            "gpu_launches": E["launches"], "clocks": E["clocks"], "roofline": E["roofline"],
+            "cpu_baseline": cpu_obj("encode", "encode+hide @128k")}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -395,6 +444,7 @@ def main():
     ap.add_argument("--files", type=int, default=1000, help="files per GPU")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_FILE, help="frames per file")
     ap.add_argument("--wave", type=int, default=125, help="files per wave (bounds the device workspaces)")
+    ap.add_argument("--no-encode", action="store_true", help="skip the encode+hide half")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -58,7 +58,10 @@ enum {
 
 /* flags for m3s_decode_run */
 enum {
-    M3S_DEC_PCM_FLOAT = 1        /* pcm buffer is float32 (pre-int16 samples) instead of int16 */
+    M3S_DEC_PCM_FLOAT = 1,       /* pcm buffer is float32 (pre-int16 samples) instead of int16 */
+    M3S_DEC_EXACT = 2            /* run requantize..synthesis in float64 like the reference (Frame.py is float64 end to end):
+                                    int16 PCM then equals the reference's sample for sample in practice, which the hide / clear
+                                    composites need to reproduce the reference's MP3 bytes; the default FP32 path is within 1 LSB */
 };
 
 /* ---------------------------------------------------------------- lifetime */
@@ -126,6 +129,9 @@ M3S_API int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t *pc
  *   hide_str_offset_out  [n_clips] host: MP3Encoder.hide_str_offset after the last frame
  */
 M3S_API int64_t m3s_encode_bound(int64_t n_samples, int32_t sample_rate, int32_t bitrate_kbps);
+/* Exact number of bytes MP3Encoder emits for a clip of n_samples per channel: the sum of the padded frame sizes
+ * (slot-lag recurrence, MP3_Encoder.py:504-513,630-632) rounded DOWN to whole 32-bit words (:1370-1392). <0 on bad arguments. */
+M3S_API int64_t m3s_encode_size(int64_t n_samples, int32_t sample_rate, int32_t bitrate_kbps);
 M3S_API int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int64_t *pcm_off, const int64_t *n_samples,
                        int32_t n_clips, int32_t sample_rate, int32_t bitrate_kbps, const uint8_t *payload_bits,
                        const int64_t *payload_off, uint8_t *mp3_out, const int64_t *mp3_off, const int64_t *mp3_cap,

@@ -131,6 +131,18 @@ struct M3sDevTables {
     uint16_t enc_linmax[34];
 };
 
+// float64 copies of the hybrid-synthesis tables for the `exact` decode instantiation (M3S_DEC_EXACT)
+struct M3sDevTablesD {
+    double pow43[256];
+    double quarter[4];
+    double imdct_cos36[36][18];
+    double imdct_cos12[12][8];
+    double sine_block[4][36];
+    double synth_n[64][32];
+    double synth_d[512];
+    double alias_cs[8], alias_ca[8];
+};
+
 // ------------------------------------------------------------------------------------------------
 // host context
 // ------------------------------------------------------------------------------------------------
@@ -153,6 +165,7 @@ struct m3s_ctx {
     double k_ms[M3S_K_COUNT] = {0};
     int64_t k_launches[M3S_K_COUNT] = {0};
     M3sDevTables *d_tab = nullptr;
+    M3sDevTablesD *d_tab_f64 = nullptr;
     int sm_count = 148;
 
     // ---- decode state (valid between m3s_decode_scan and the next scan)

@@ -129,9 +129,38 @@ static int build_huff_lut(M3sDevTables *T)
     return next;
 }
 
-static void build_tables(M3sDevTables *T)
+// requantize / IMDCT / synthesis constants, generated in double with the reference's formulas and stored as R
+template <typename TAB, typename R>
+static void build_hybrid_tables(TAB *T)
 {
     const double PI = 3.141592653589793;
+    for (int i = 0; i < 256; i++) T->pow43[i] = (R)pow((double)i, 4.0 / 3.0);
+    for (int i = 0; i < 4; i++) T->quarter[i] = (R)pow(2.0, i / 4.0);
+    for (int i = 0; i < 36; i++)
+        for (int k = 0; k < 18; k++) T->imdct_cos36[i][k] = (R)cos(PI / 72.0 * (2 * i + 1 + 18) * (2 * k + 1));
+    for (int i = 0; i < 12; i++)
+        for (int k = 0; k < 8; k++) T->imdct_cos12[i][k] = k < 6 ? (R)cos(PI / 24.0 * (2 * i + 1 + 6) * (2 * k + 1)) : (R)0;
+    double sb[4][36];  // Frame.py:32-62
+    memset(sb, 0, sizeof sb);
+    for (int i = 0; i < 36; i++) sb[0][i] = sin(PI / 36.0 * (i + 0.5));
+    for (int i = 0; i < 18; i++) sb[1][i] = sin(PI / 36.0 * (i + 0.5));
+    for (int i = 18; i < 24; i++) sb[1][i] = 1.0;
+    for (int i = 24; i < 30; i++) sb[1][i] = sin(PI / 12.0 * (i - 18.0 + 0.5));
+    for (int i = 30; i < 36; i++) sb[1][i] = 1.0;  // sic: the reference's start window ends in ones
+    for (int i = 0; i < 12; i++) sb[2][i] = sin(PI / 12.0 * (i + 0.5));
+    for (int i = 6; i < 12; i++) sb[3][i] = sin(PI / 12.0 * (i - 6.0 + 0.5));
+    for (int i = 12; i < 18; i++) sb[3][i] = 1.0;
+    for (int i = 18; i < 36; i++) sb[3][i] = sin(PI / 36.0 * (i + 0.5));
+    for (int b = 0; b < 4; b++)
+        for (int i = 0; i < 36; i++) T->sine_block[b][i] = (R)sb[b][i];
+    for (int i = 0; i < 64; i++)
+        for (int j = 0; j < 32; j++) T->synth_n[i][j] = (R)cos((16.0 + i) * (2.0 * j + 1.0) * (PI / 64.0));
+    for (int i = 0; i < 512; i++) T->synth_d[i] = (R)M3S_SYNTH_WINDOW[i];
+    for (int i = 0; i < 8; i++) { T->alias_cs[i] = (R)M3S_ALIAS_CS[i]; T->alias_ca[i] = (R)M3S_ALIAS_CA[i]; }
+}
+
+static void build_tables(M3sDevTables *T)
+{
     for (int s = 0; s < 3; s++) {
         for (int i = 0; i < 23; i++) T->sfb_long[s][i] = M3S_SFB_LONG[23 * s + i];
         for (int i = 0; i < 14; i++) T->sfb_short[s][i] = M3S_SFB_SHORT[14 * s + i];
@@ -160,29 +189,7 @@ static void build_tables(M3sDevTables *T)
     }
     for (int i = 0; i < 16; i++) { T->slen[i][0] = M3S_SLEN[2 * i]; T->slen[i][1] = M3S_SLEN[2 * i + 1]; }
     for (int i = 0; i < 22; i++) T->pretab[i] = M3S_PRETAB[i];
-    for (int i = 0; i < 256; i++) T->pow43[i] = (float)pow((double)i, 4.0 / 3.0);
-    for (int i = 0; i < 4; i++) T->quarter[i] = (float)pow(2.0, i / 4.0);
-    for (int i = 0; i < 36; i++)
-        for (int k = 0; k < 18; k++) T->imdct_cos36[i][k] = (float)cos(PI / 72.0 * (2 * i + 1 + 18) * (2 * k + 1));
-    for (int i = 0; i < 12; i++)
-        for (int k = 0; k < 8; k++) T->imdct_cos12[i][k] = k < 6 ? (float)cos(PI / 24.0 * (2 * i + 1 + 6) * (2 * k + 1)) : 0.f;
-    double sb[4][36];  // Frame.py:32-62
-    memset(sb, 0, sizeof sb);
-    for (int i = 0; i < 36; i++) sb[0][i] = sin(PI / 36.0 * (i + 0.5));
-    for (int i = 0; i < 18; i++) sb[1][i] = sin(PI / 36.0 * (i + 0.5));
-    for (int i = 18; i < 24; i++) sb[1][i] = 1.0;
-    for (int i = 24; i < 30; i++) sb[1][i] = sin(PI / 12.0 * (i - 18.0 + 0.5));
-    for (int i = 30; i < 36; i++) sb[1][i] = 1.0;  // sic: the reference's start window ends in ones
-    for (int i = 0; i < 12; i++) sb[2][i] = sin(PI / 12.0 * (i + 0.5));
-    for (int i = 6; i < 12; i++) sb[3][i] = sin(PI / 12.0 * (i - 6.0 + 0.5));
-    for (int i = 12; i < 18; i++) sb[3][i] = 1.0;
-    for (int i = 18; i < 36; i++) sb[3][i] = sin(PI / 36.0 * (i + 0.5));
-    for (int b = 0; b < 4; b++)
-        for (int i = 0; i < 36; i++) T->sine_block[b][i] = (float)sb[b][i];
-    for (int i = 0; i < 64; i++)
-        for (int j = 0; j < 32; j++) T->synth_n[i][j] = (float)cos((16.0 + i) * (2.0 * j + 1.0) * (PI / 64.0));
-    for (int i = 0; i < 512; i++) T->synth_d[i] = (float)M3S_SYNTH_WINDOW[i];
-    for (int i = 0; i < 8; i++) { T->alias_cs[i] = (float)M3S_ALIAS_CS[i]; T->alias_ca[i] = (float)M3S_ALIAS_CA[i]; }
+    build_hybrid_tables<M3sDevTables, float>(T);
     // encoder
     memcpy(T->enwindow, M3S_ENWINDOW, sizeof T->enwindow);
     memcpy(T->enc_fl, M3S_ENC_FL, sizeof T->enc_fl);
@@ -243,6 +250,13 @@ extern "C" int m3s_create(int device, m3s_handle_t *out)
     cudaError_t e = cudaMalloc(&h->d_tab, sizeof(M3sDevTables));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_tab, T, sizeof(M3sDevTables), cudaMemcpyHostToDevice);
     delete T;
+    if (e == cudaSuccess) {
+        M3sDevTablesD *TD = new M3sDevTablesD();
+        build_hybrid_tables<M3sDevTablesD, double>(TD);
+        e = cudaMalloc(&h->d_tab_f64, sizeof(M3sDevTablesD));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_tab_f64, TD, sizeof(M3sDevTablesD), cudaMemcpyHostToDevice);
+        delete TD;
+    }
     if (e != cudaSuccess) {
         cudaStreamDestroy(h->own_stream);
         delete h;
@@ -275,6 +289,7 @@ extern "C" int m3s_destroy(m3s_handle_t h)
     timing_resolve(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->d_tab) cudaFree(h->d_tab);
+    if (h->d_tab_f64) cudaFree(h->d_tab_f64);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return M3S_OK;

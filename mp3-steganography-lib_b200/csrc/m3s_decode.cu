@@ -682,18 +682,19 @@ struct M3sWork {
 
 #define HYB_THREADS 256
 
+template <typename R>
 struct HybSmem {
-    float xr[2][576];
-    float prev[2][2][576];
-    float tt[2][18][32];
-    float v[2][33][64];
-    float cos36[36][18];
-    float cos12[12][8];
-    float sine[4][36];
-    float d[512];
-    float pow43[256];
-    float cs[8], ca[8];
-    float quarter[4];
+    R xr[2][576];
+    R prev[2][2][576];
+    R tt[2][18][32];
+    R v[2][33][64];
+    R cos36[36][18];
+    R cos12[12][8];
+    R sine[4][36];
+    R d[512];
+    R pow43[256];
+    R cs[8], ca[8];
+    R quarter[4];
     uint16_t reorder[576];
     uint8_t long_sfb[576];
     uint8_t short_sfw[576];
@@ -709,36 +710,51 @@ __device__ __forceinline__ float pow2i(int e)  // 2^e for e in the normal float 
     return __int_as_float((e + 127) << 23);
 }
 
-template <bool FLOAT_OUT>
+// requantize magnitude |x|^(4/3) * 2^(e4/4)   (Frame.py:210-215).  FP32: table / cbrt and exact powers of two;
+// FP64 (the `exact` instantiation used by the single-file facade): double-precision pow for the large values.
+__device__ __forceinline__ float requant_mag(const HybSmem<float> &sm, int ax, int e4)
+{
+    float m = ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax);
+    return m * (sm.quarter[e4 & 3] * pow2i(e4 >> 2));
+}
+__device__ __forceinline__ double requant_mag(const HybSmem<double> &sm, int ax, int e4)
+{
+    const double a = ax < 256 ? sm.pow43[ax] : pow((double)ax, 4.0 / 3.0);
+    return a * (sm.quarter[e4 & 3] * scalbn(1.0, e4 >> 2));
+}
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+
+template <typename R, typename TAB, bool FLOAT_OUT>
 __global__ void __launch_bounds__(HYB_THREADS)
 k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
          const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
-         void *__restrict__ pcm_out)
+         const TAB *__restrict__ TF, void *__restrict__ pcm_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HybSmem &sm = *reinterpret_cast<HybSmem *>(smem_raw);
+    HybSmem<R> &sm = *reinterpret_cast<HybSmem<R> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const M3sWork wk = work[blockIdx.x];
     const int nch = wk.channels;
 
     // ---- one-time table staging
-    for (int i = tid; i < 36 * 18; i += HYB_THREADS) (&sm.cos36[0][0])[i] = (&T->imdct_cos36[0][0])[i];
-    for (int i = tid; i < 12 * 8; i += HYB_THREADS) (&sm.cos12[0][0])[i] = (&T->imdct_cos12[0][0])[i];
-    for (int i = tid; i < 4 * 36; i += HYB_THREADS) (&sm.sine[0][0])[i] = (&T->sine_block[0][0])[i];
-    for (int i = tid; i < 512; i += HYB_THREADS) sm.d[i] = T->synth_d[i];
-    for (int i = tid; i < 256; i += HYB_THREADS) sm.pow43[i] = T->pow43[i];
-    if (tid < 8) { sm.cs[tid] = T->alias_cs[tid]; sm.ca[tid] = T->alias_ca[tid]; }
-    if (tid < 4) sm.quarter[tid] = T->quarter[tid];
+    for (int i = tid; i < 36 * 18; i += HYB_THREADS) (&sm.cos36[0][0])[i] = (&TF->imdct_cos36[0][0])[i];
+    for (int i = tid; i < 12 * 8; i += HYB_THREADS) (&sm.cos12[0][0])[i] = (&TF->imdct_cos12[0][0])[i];
+    for (int i = tid; i < 4 * 36; i += HYB_THREADS) (&sm.sine[0][0])[i] = (&TF->sine_block[0][0])[i];
+    for (int i = tid; i < 512; i += HYB_THREADS) sm.d[i] = TF->synth_d[i];
+    for (int i = tid; i < 256; i += HYB_THREADS) sm.pow43[i] = TF->pow43[i];
+    if (tid < 8) { sm.cs[tid] = TF->alias_cs[tid]; sm.ca[tid] = TF->alias_ca[tid]; }
+    if (tid < 4) sm.quarter[tid] = TF->quarter[tid];
     if (tid < 22) sm.pretab[tid] = T->pretab[tid];
     if (tid == 0) sm.sr_loaded = -1;
-    for (int i = tid; i < 2 * 2 * 576; i += HYB_THREADS) (&sm.prev[0][0][0])[i] = 0.f;
-    for (int i = tid; i < 2 * 33 * 64; i += HYB_THREADS) (&sm.v[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * 2 * 576; i += HYB_THREADS) (&sm.prev[0][0][0])[i] = (R)0;
+    for (int i = tid; i < 2 * 33 * 64; i += HYB_THREADS) (&sm.v[0][0][0])[i] = (R)0;
     // matrixing row held in registers: output index i = (warp & 1) * 32 + lane
-    float nrow[32];
+    R nrow[32];
     {
         const int i = (warp & 1) * 32 + lane;
 #pragma unroll
-        for (int j = 0; j < 32; j++) nrow[j] = T->synth_n[i][j];
+        for (int j = 0; j < 32; j++) nrow[j] = TF->synth_n[i][j];
     }
     __syncthreads();
 
@@ -767,10 +783,10 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
             // ------------------------------------------------ requantize + MS + reorder (fused)
             for (int p = tid; p < 288; p += HYB_THREADS) {
                 const uint4 w4 = ((const uint4 *)spec)[g * 288 + p];
-                float val[2][2];
+                R val[2][2];
 #pragma unroll
                 for (int ch = 0; ch < 2; ch++) {
-                    if (ch >= nch) { val[ch][0] = val[ch][1] = 0.f; continue; }
+                    if (ch >= nch) { val[ch][0] = val[ch][1] = (R)0; continue; }
                     const int slot = 2 * gr + ch;
                     const uint32_t wv = slot == 0 ? w4.x : (slot == 1 ? w4.y : (slot == 2 ? w4.z : w4.w));
                     const M3sUnitRec &r = sm.rec[slot];
@@ -792,17 +808,16 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                             e4 = gg - 210 - mult4 * ((int)sf[sfb] + (int)M3S_UB_PREFLAG(r.b) * (int)sm.pretab[sfb]);
                         }
                         const int ax = x < 0 ? -x : x;
-                        float m = ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax);
-                        m *= sm.quarter[e4 & 3] * pow2i(e4 >> 2);
+                        const R m = requant_mag(sm, ax, e4);
                         val[ch][h] = x < 0 ? -m : m;
                     }
                 }
                 if (ms && nch == 2) {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
-                        const float mm = val[0][h], ss = val[1][h];
-                        val[0][h] = (mm + ss) * 0.70710678118654752f;
-                        val[1][h] = (mm - ss) * 0.70710678118654752f;
+                        const R mm = val[0][h], ss = val[1][h];
+                        val[0][h] = (mm + ss) * (R)0.70710678118654752;   // (M + S) / SQRT2, Frame.py:568-572
+                        val[1][h] = (mm - ss) * (R)0.70710678118654752;
                     }
                 }
 #pragma unroll
@@ -827,7 +842,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                 if (M3S_UA_BT(r.a) == 2 || M3S_UB_MIXED(r.b)) continue;
                 const int sb = 1 + (r_ >> 3), i = r_ & 7;
                 const int o1 = 18 * sb - i - 1, o2 = 18 * sb + i;
-                const float s1 = sm.xr[ch][o1], s2 = sm.xr[ch][o2];
+                const R s1 = sm.xr[ch][o1], s2 = sm.xr[ch][o2];
                 sm.xr[ch][o1] = s1 * sm.cs[i] - s2 * sm.ca[i];
                 sm.xr[ch][o2] = s2 * sm.cs[i] + s1 * sm.ca[i];
             }
@@ -838,39 +853,39 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                 if (ch < nch) {
                     const M3sUnitRec &r = sm.rec[2 * gr + ch];
                     const int bt = M3S_UA_BT(r.a);
-                    float x[18];
+                    R x[18];
 #pragma unroll
                     for (int k = 0; k < 18; k++) x[k] = sm.xr[ch][18 * sb + k];
-                    const float *pv = sm.prev[pp][ch];
-                    float *pn = sm.prev[pp ^ 1][ch];
+                    const R *pv = sm.prev[pp][ch];
+                    R *pn = sm.prev[pp ^ 1][ch];
 #pragma unroll
                     for (int ii = 0; ii < 9; ii++) {
                         const int i = 9 * q + ii;
-                        float acc = 0.f;
+                        R acc = (R)0;
                         if (bt != 2) {
 #pragma unroll
-                            for (int k = 0; k < 18; k++) acc = fmaf(x[k], sm.cos36[i][k], acc);
+                            for (int k = 0; k < 18; k++) acc = fma_t(x[k], sm.cos36[i][k], acc);
                             acc *= sm.sine[bt][i];
                         } else if (i >= 6 && i < 30) {
                             // three 12-point windows placed at 6/12/18 with overlap (Frame.py:135-148)
                             const int w_hi = (i - 6) / 6;            // window whose first half covers i
                             const int i_hi = i - 6 - 6 * w_hi;       // 0..5
                             if (w_hi < 3) {
-                                float a2 = 0.f;
+                                R a2 = (R)0;
 #pragma unroll
-                                for (int k = 0; k < 6; k++) a2 = fmaf(sm.xr[ch][18 * sb + 6 * w_hi + k], sm.cos12[i_hi][k], a2);
+                                for (int k = 0; k < 6; k++) a2 = fma_t(sm.xr[ch][18 * sb + 6 * w_hi + k], sm.cos12[i_hi][k], a2);
                                 acc += a2 * sm.sine[2][i_hi];
                             }
                             const int w_lo = w_hi - 1;               // window whose second half covers i
                             if (w_lo >= 0) {
-                                float a2 = 0.f;
+                                R a2 = (R)0;
 #pragma unroll
-                                for (int k = 0; k < 6; k++) a2 = fmaf(sm.xr[ch][18 * sb + 6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
+                                for (int k = 0; k < 6; k++) a2 = fma_t(sm.xr[ch][18 * sb + 6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
                                 acc += a2 * sm.sine[2][i_hi + 6];
                             }
                         }
                         if (i < 18) {
-                            float o = acc + pv[18 * sb + i];
+                            R o = acc + pv[18 * sb + i];
                             if ((sb & 1) && (i & 1)) o = -o;
                             sm.tt[ch][i][sb] = o;
                         } else pn[18 * sb + (i - 18)] = acc;
@@ -883,15 +898,25 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                 const int i = (warp & 1) * 32 + lane, tg = warp >> 1;
                 for (int cidx = tg; cidx < nch * 18; cidx += 4) {
                     const int ch = cidx / 18, t = cidx - 18 * ch;
-                    const float4 *s4 = (const float4 *)sm.tt[ch][t];
-                    float acc = 0.f;
+                    R acc = (R)0;
+                    if constexpr (sizeof(R) == 4) {
+                        const float4 *s4 = (const float4 *)sm.tt[ch][t];
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; j4++) {
-                        const float4 s = s4[j4];
-                        acc = fmaf(s.x, nrow[4 * j4 + 0], acc);
-                        acc = fmaf(s.y, nrow[4 * j4 + 1], acc);
-                        acc = fmaf(s.z, nrow[4 * j4 + 2], acc);
-                        acc = fmaf(s.w, nrow[4 * j4 + 3], acc);
+                        for (int j4 = 0; j4 < 8; j4++) {
+                            const float4 s = s4[j4];
+                            acc = fma_t((R)s.x, nrow[4 * j4 + 0], acc);
+                            acc = fma_t((R)s.y, nrow[4 * j4 + 1], acc);
+                            acc = fma_t((R)s.z, nrow[4 * j4 + 2], acc);
+                            acc = fma_t((R)s.w, nrow[4 * j4 + 3], acc);
+                        }
+                    } else {
+                        const double2 *s2 = (const double2 *)sm.tt[ch][t];
+#pragma unroll
+                        for (int j2 = 0; j2 < 16; j2++) {
+                            const double2 s = s2[j2];
+                            acc = fma_t((R)s.x, nrow[2 * j2 + 0], acc);
+                            acc = fma_t((R)s.y, nrow[2 * j2 + 1], acc);
+                        }
                     }
                     sm.v[ch][15 + t][i] = acc;
                 }
@@ -900,15 +925,15 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
             // ------------------------------------------------ windowing + output
             for (int o = tid; o < 576; o += HYB_THREADS) {
                 const int t = o >> 5, i = o & 31;
-                float s[2] = {0.f, 0.f};
+                R s[2] = {(R)0, (R)0};
 #pragma unroll
                 for (int ch = 0; ch < 2; ch++) {
                     if (ch >= nch) continue;
-                    float acc = 0.f;
+                    R acc = (R)0;
 #pragma unroll
                     for (int m = 0; m < 8; m++) {
-                        acc = fmaf(sm.v[ch][15 + t - 2 * m][i], sm.d[64 * m + i], acc);
-                        acc = fmaf(sm.v[ch][15 + t - 2 * m - 1][32 + i], sm.d[64 * m + 32 + i], acc);
+                        acc = fma_t(sm.v[ch][15 + t - 2 * m][i], sm.d[64 * m + i], acc);
+                        acc = fma_t(sm.v[ch][15 + t - 2 * m - 1][32 + i], sm.d[64 * m + 32 + i], acc);
                     }
                     s[ch] = acc;
                 }
@@ -918,11 +943,13 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                         const int64_t row = (g - wk.g_first + rep) * 1152 + gr * 576 + o;
                         if (FLOAT_OUT) {
                             float *po = (float *)pcm_out + wk.pcm_elem + row * nch;
-                            po[0] = s[0];
-                            if (nch == 2) po[1] = s[1];
+                            po[0] = (float)s[0];
+                            if (nch == 2) po[1] = (float)s[1];
                         } else {
                             // (pcm * 32767).astype(int16): truncate toward zero, keep the low 16 bits (A.D8)
-                            const int a0 = __float2int_rz(s[0] * 32767.f), a1 = __float2int_rz(s[1] * 32767.f);
+                            int a0, a1;
+                            if constexpr (sizeof(R) == 4) { a0 = __float2int_rz(s[0] * 32767.f); a1 = __float2int_rz(s[1] * 32767.f); }
+                            else { a0 = __double2int_rz(s[0] * 32767.0); a1 = __double2int_rz(s[1] * 32767.0); }
                             if (nch == 2)
                                 ((uint32_t *)pcm_out)[(wk.pcm_elem >> 1) + row] = ((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16);
                             else
@@ -1141,19 +1168,22 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
         if (mem == M3S_MEM_HOST)
             M3S_CUDA(h, cudaMemcpyAsync(spectra, d_sp, (size_t)nf * 4 * 576 * 2, cudaMemcpyDeviceToHost, h->stream));
     }
-    const size_t smem = sizeof(HybSmem);
-    if (fl) {
-        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        M3S_KBEGIN(h, M3S_K_HYBRID);
-        k_hybrid<true><<<(unsigned)work.size(), HYB_THREADS, smem, h->stream>>>(
-            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)h->b_units.p, (const uint8_t *)h->b_sf.p,
-            (const uint32_t *)h->b_fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, d_pcm);
+    const bool exact = (flags & M3S_DEC_EXACT) != 0;
+#define M3S_LAUNCH_HYBRID(R, TAB, FL, tabptr)                                                                              \
+    do {                                                                                                                   \
+        const size_t smem = sizeof(HybSmem<R>);                                                                            \
+        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid<R, TAB, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        M3S_KBEGIN(h, M3S_K_HYBRID);                                                                                       \
+        k_hybrid<R, TAB, FL><<<(unsigned)work.size(), HYB_THREADS, smem, h->stream>>>(                                     \
+            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)h->b_units.p, (const uint8_t *)h->b_sf.p,                   \
+            (const uint32_t *)h->b_fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, (tabptr), d_pcm);                    \
+    } while (0)
+    if (exact) {
+        if (fl) M3S_LAUNCH_HYBRID(double, M3sDevTablesD, true, h->d_tab_f64);
+        else M3S_LAUNCH_HYBRID(double, M3sDevTablesD, false, h->d_tab_f64);
     } else {
-        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        M3S_KBEGIN(h, M3S_K_HYBRID);
-        k_hybrid<false><<<(unsigned)work.size(), HYB_THREADS, smem, h->stream>>>(
-            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)h->b_units.p, (const uint8_t *)h->b_sf.p,
-            (const uint32_t *)h->b_fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, d_pcm);
+        if (fl) M3S_LAUNCH_HYBRID(float, M3sDevTables, true, h->d_tab);
+        else M3S_LAUNCH_HYBRID(float, M3sDevTables, false, h->d_tab);
     }
     M3S_LAUNCH_CHECK(h);
     if (mem == M3S_MEM_HOST)

@@ -769,6 +769,15 @@ extern "C" int64_t m3s_encode_bound(int64_t n_samples, int32_t sample_rate, int3
     return frames * fs + 8;
 }
 
+extern "C" int64_t m3s_encode_size(int64_t n_samples, int32_t sample_rate, int32_t bitrate_kbps)
+{
+    if (n_samples < 0 || n_samples % 1152 || sr_index_of(sample_rate) < 0 || br_index_of(bitrate_kbps) < 0) return -1;
+    std::vector<uint32_t> off;
+    int whole = 0;
+    padding_prefix(sample_rate, bitrate_kbps, n_samples / 1152, off, whole);
+    return (int64_t)(off.back() / 4) * 4;
+}
+
 static void build_enc_tables(const M3sDevTables *T, EncTables *E)
 {
     memset(E, 0, sizeof *E);

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmp3stego_b200.so")
 M3S_MEM_HOST, M3S_MEM_DEVICE = 0, 1
 M3S_FILE_NO_SYNC, M3S_FILE_UNSUPPORTED, M3S_FILE_TRAILING_JUNK = 1, 2, 4
 M3S_DEC_PCM_FLOAT = 1
+M3S_DEC_EXACT = 2
 
 _c_i64p = ctypes.POINTER(ctypes.c_int64)
 _c_i32p = ctypes.POINTER(ctypes.c_int32)
@@ -33,6 +34,7 @@ SYMBOLS = [
     ("m3s_decode_run", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, ctypes.c_void_p,
                                       ctypes.c_uint32]),
     ("m3s_encode_bound", ctypes.c_int64, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
+    ("m3s_encode_size", ctypes.c_int64, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     ("m3s_encode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, _c_i64p, ctypes.c_int32,
                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, _c_i64p, ctypes.c_void_p, _c_i64p,
                                   _c_i64p, _c_i64p, _c_i64p]),
@@ -185,7 +187,7 @@ class Handle:
         self._check(rc, "m3s_decode_reveal")
         return ln
 
-    def decode_run(self, pcm=None, pcm_off=None, spectra=False, as_float=False):
+    def decode_run(self, pcm=None, pcm_off=None, spectra=False, as_float=False, exact=False):
         """D1-D3 of the last scan.  With pcm=None a host numpy buffer is allocated and returned."""
         sc = self._scan
         elems = sc["pcm_rows"] * np.maximum(sc["channels"], 1)
@@ -199,20 +201,28 @@ class Handle:
             sp = np.zeros((max(total_frames, 1), 2, 2, 576), np.int16)
         elif spectra is not False and spectra is not None:
             sp = spectra
-        rc = self._L.m3s_decode_run(self._h, _ptr(pcm), _mem_of(pcm), po_p, _ptr(sp), M3S_DEC_PCM_FLOAT if as_float else 0)
+        rc = self._L.m3s_decode_run(self._h, _ptr(pcm), _mem_of(pcm), po_p, _ptr(sp),
+                                    (M3S_DEC_PCM_FLOAT if as_float else 0) | (M3S_DEC_EXACT if exact else 0))
         self._check(rc, "m3s_decode_run")
         return pcm, sp
 
     # ------------------------------------------------------------------ encode
-    def encode(self, pcm, n_samples, sample_rate, bitrate_kbps, payloads=None, pcm_off=None, mp3_out=None, taps=False):
-        """E1-E3 over a batch of int16 stereo clips laid end to end in `pcm` (numpy or torch, host or cuda)."""
+    def encode(self, pcm, n_samples, sample_rate, bitrate_kbps, payloads=None, pcm_off=None, mp3_out=None, taps=False,
+               compact=False, payload_packed=None):
+        """E1-E3 over a batch of int16 stereo clips laid end to end in `pcm` (numpy or torch, host or cuda).
+        compact=True lays the MP3s back to back at their exact sizes (m3s_encode_size), so that (mp3, mp3_off + [end])
+        can be fed straight to decode_scan.  payload_packed = (uint8 array of '0'/'1' chars, offsets[n+1]) avoids re-joining."""
         L = self._L
         n = len(n_samples)
         ns, ns_p = _i64(n_samples)
         if pcm_off is None:
             pcm_off = np.concatenate([[0], np.cumsum(ns * 2)])[:-1]
         po, po_p = _i64(pcm_off)
-        bounds = np.array([L.m3s_encode_bound(int(s), sample_rate, bitrate_kbps) for s in ns], np.int64)
+        size_fn = L.m3s_encode_size if compact else L.m3s_encode_bound
+        uniq = {int(s): size_fn(int(s), sample_rate, bitrate_kbps) for s in set(int(v) for v in ns)}
+        bounds = np.array([uniq[int(s)] for s in ns], np.int64)
+        if (bounds < 0).any():
+            raise M3SError("encode: unsupported sample count / sample rate / bitrate")
         mo, mo_p = _i64(np.concatenate([[0], np.cumsum(bounds)])[:-1])
         mc, mc_p = _i64(bounds)
         mem = _mem_of(pcm)
@@ -222,7 +232,11 @@ class Handle:
                 mp3_out = torch.zeros(int(bounds.sum()) + 16, dtype=torch.uint8, device=pcm.device)
             else:
                 mp3_out = np.zeros(int(bounds.sum()) + 16, np.uint8)
-        if payloads is not None and any(len(p) for p in payloads):
+        if payload_packed is not None:
+            pl = payload_packed[0]
+            ploff, ploff_p = _i64(payload_packed[1])
+            pl_p = _ptr(pl)
+        elif payloads is not None and any(len(p) for p in payloads):
             pl = np.frombuffer("".join(payloads).encode("ascii"), dtype=np.uint8).copy()
             ploff, ploff_p = _i64(np.concatenate([[0], np.cumsum([len(p) for p in payloads])]))
             pl_p = _ptr(pl)

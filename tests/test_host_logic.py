@@ -1,0 +1,87 @@
+"""CPU: host-side logic of the Python mirror (no GPU): WAV writer/reader, ID3 skip, reveal parse, message framing."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_path, load_npz
+
+
+def test_write_wav_matches_reference_bytes(tmp_path, built):
+    """MP3Parser.write_to_wav (scipy.io.wavfile.write) byte layout: the reference's out.wav, by sha256."""
+    from mp3stego_b200.wavio import write_wav
+    fac = json.load(open(golden_path("ref_facade.json")))
+    z = load_npz("ref_test_mp3.npz")
+    p = tmp_path / "out.wav"
+    write_wav(str(p), 44100, z["pcm16"])
+    raw = open(p, "rb").read()
+    assert len(raw) == fac["out_wav_bytes"]
+    assert hashlib.sha256(raw).hexdigest() == fac["out_wav_sha256"]
+    assert raw == open(golden_path("ref_test_out.wav"), "rb").read()
+
+
+def test_wav_reader_fields_and_errors(tmp_path, built):
+    from mp3stego_b200.wavio import WavReader, write_wav
+    w = WavReader(golden_path("ref_test_out.wav"), 128)
+    assert (w.samplerate, w.num_of_channels, w.num_of_samples, w.bitrate) == (44100, 2, 41472, 128)
+    assert w.mpeg_mode == 0 and w.original == 1 and w.copyright == 0 and w.emphasis == 0
+    assert len(w.buffer) == 41472 * 2 and w.buffer.dtype == np.int16
+    assert w.get_buffer_pos(1) == 1
+    bad = tmp_path / "bad.wav"
+    bad.write_bytes(b"not a wave file at all" * 10)
+    with pytest.raises(SystemExit, match="Bad WAVE file."):
+        WavReader(str(bad))
+    with pytest.raises(SystemExit, match="Unsupported bitrate configuration."):
+        WavReader(golden_path("ref_test_out.wav"), 100)
+    p = tmp_path / "sr.wav"
+    write_wav(str(p), 22050, np.zeros((1152, 2), np.int16))
+    with pytest.raises(SystemExit, match="Unsupported sampling frequency."):
+        WavReader(str(p))
+
+
+def test_id3_offset_rule(built, oracle):
+    from mp3stego_b200.decoder import id3_offset
+    body = bytes(range(200))
+    for flags, extra in ((0x00, 10), (0x10, 20), (0x40, 10)):
+        tag = b"ID3\x04\x00" + bytes([flags]) + bytes([0, 0, 1, 0x48])
+        data = tag + body
+        assert id3_offset(data) == 128 + 0x48 + extra == oracle.id3_offset(data)
+    assert id3_offset(b"ID3\x04\x00\x01\x00\x00\x01\x48" + body) == 0   # protected low flag bit set: tag ignored
+    assert id3_offset(b"\xff\xfb\x90\x00" + body) == 0
+    assert id3_offset(b"ID") == 0
+
+
+def test_reveal_parse_matches_reference_rule(built, oracle):
+    from mp3stego_b200.decoder import parse_reveal
+    from mp3stego_b200.steganography import str_to_binary_str
+    assert str_to_binary_str("3#ddd") == oracle.str_to_bits("3#ddd")
+    assert str_to_binary_str("é#") == "1100001110101001" + "00100011"
+    cases = ["3#ddd", "3#dddXYZ", "10#short", "#abc", "x#abc", "", "12", "0#"]
+    for c in cases:
+        bits = str_to_binary_str(c) + "101"   # trailing partial byte is dropped
+        assert parse_reveal(bits) == oracle.reveal_parse(bits)
+    assert parse_reveal(str_to_binary_str("3#dddXYZ")) == "ddd"
+    assert parse_reveal(str_to_binary_str("10#short")) == "short"
+    assert parse_reveal(str_to_binary_str("x#abc")) == ""      # non-numeric prefix: length 0 and the prefix itself counts as empty
+    z = load_npz("ref_test_mp3.npz")
+    assert parse_reveal(str(z["bits"])) == ""
+
+
+def test_facade_path_checks(tmp_path, built):
+    """The facade's sys.exit messages (steganography.py:63-78) fire before any GPU work."""
+    from mp3stego_b200 import Steganography
+    s = Steganography(quiet=True)
+    with pytest.raises(SystemExit, match="not found"):
+        s.decode_mp3_to_wav(str(tmp_path / "missing.mp3"))
+    f = tmp_path / "a.txt"
+    f.write_bytes(b"x")
+    with pytest.raises(SystemExit, match="input_file_path must be mp3 file"):
+        s.decode_mp3_to_wav(str(f))
+    with pytest.raises(SystemExit, match="wav_file_path must be wav file"):
+        s.encode_wav_to_mp3(str(f), str(tmp_path / "o.mp3"))
+    m = tmp_path / "a.mp3"
+    m.write_bytes(open(golden_path("test.mp3"), "rb").read())
+    with pytest.raises(SystemExit, match="txt_file_path must be txt file"):
+        s.reveal_massage(str(m), str(tmp_path / "o.bin"))
