@@ -93,3 +93,24 @@ def test_facade_composites(oracle):
     el = oracle.encode(wav, 44100, 320, long_bits, taps=False)
     assert hashlib.sha256(el["mp3"]).hexdigest() == fac["hid_long_sha256"]
     assert (el["hide_str_offset"] < len(long_bits) - 1) == fac["hide_long_returns"]
+
+
+STREAM_CASES = ["long_alltables", "reservoir", "short_mixed", "ms_stereo", "is_only_bit", "mono_crc_48k", "vbr_32k_pad",
+                "loud_wrap"]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES)
+def test_decode_writer_streams(oracle, case):
+    """BASELINE configs[3]: streams from the test-bitstream writer (tests/golden/make_streams.py) that use what the
+    reference encoder cannot emit -- all Huffman tables, scalefactors + scfsi, short / mixed / start / stop blocks, MS
+    stereo (and the ignored intensity bit), the bit reservoir, CRC, mono, 32/48 kHz, VBR, padding, int16 wrap -- against
+    the unmodified reference decoder's output."""
+    z = load_npz(f"ref_stream_{case}.npz")
+    r = oracle.decode(open(golden_path(f"stream_{case}.mp3"), "rb").read())
+    assert r["n_frames"] == int(z["n_frames"])
+    assert r["bit_rate"] == int(z["bitrate"]) and r["sampling_rate"] == int(z["sampling_rate"])
+    assert np.array_equal(r["spectra"], z["spectra"].astype(np.int32))
+    k = z["tables"].shape[1]
+    assert np.array_equal(r["tables"][:, :k], z["tables"]) and not r["tables"][:, k:].any()
+    assert r["bits"] == str(z["bits"])
+    assert np.array_equal(r["pcm16"].reshape(z["pcm16"].shape), z["pcm16"])

@@ -76,6 +76,38 @@ def test_synth_vs_reference_golden(handle, case):
     assert np.abs(got["pcm"].astype(np.int32) - z["dec_pcm16"].astype(np.int32)).max() <= PCM_TOL_LSB
 
 
+STREAM_CASES = ["long_alltables", "reservoir", "short_mixed", "ms_stereo", "is_only_bit", "mono_crc_48k", "vbr_32k_pad",
+                "loud_wrap"]
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("case", STREAM_CASES)
+def test_writer_streams_vs_reference_golden(handle, case, exact):
+    """BASELINE configs[3]: short / mixed blocks, MS stereo, scalefactors, scfsi, all tables, reservoir, CRC, mono, VBR
+    (tests/golden/make_streams.py) against what the unmodified reference decoder produced.  FP32: <= 1 LSB (modulo the
+    reference's int16 wrap, A.D8); float64 instantiation: sample-exact."""
+    z = load_npz(f"ref_stream_{case}.npz")
+    data = np.frombuffer(open(golden_path(f"stream_{case}.mp3"), "rb").read(), np.uint8)
+    sc = handle.decode_scan(data, [0, len(data)])
+    ids, bits = handle.decode_reveal()
+    pcm, sp = handle.decode_run(spectra=True, exact=exact)
+    assert int(sc["n_frames"][0]) == int(z["n_frames"])
+    assert int(sc["bitrate"][0]) == int(z["bitrate"]) and int(sc["sample_rate"][0]) == int(z["sampling_rate"])
+    ch = int(sc["channels"][0])
+    assert np.array_equal(sp.astype(np.int32)[:, :, :ch], z["spectra"].astype(np.int32)[:, :, :ch])
+    k = z["tables"].shape[1]
+    assert np.array_equal(ids[:, :k], z["tables"])
+    assert bits[0] == str(z["bits"])
+    got = pcm.reshape(z["pcm16"].shape).astype(np.int32)
+    ref = z["pcm16"].astype(np.int32)
+    if exact:
+        assert np.array_equal(got, ref)
+    else:
+        d = np.abs(got - ref)
+        d = np.minimum(d, 65536 - d)   # a 1-LSB difference across the wrap boundary shows up as 65535
+        assert d.max() <= PCM_TOL_LSB
+
+
 def test_batch_of_all_goldens_vs_oracle(handle, oracle):
     """Every golden MP3 in ONE batch (mixed bitrates / lengths, incl. stream-writer cases) vs the oracle."""
     blobs = [open(golden_path("test.mp3"), "rb").read()]
