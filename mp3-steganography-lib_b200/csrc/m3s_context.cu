@@ -186,6 +186,21 @@ static void build_tables(M3sDevTables *T)
             }
             total += 3 * w;
         }
+        // The 12 short bands cover only `total` (< 576) samples: the reference's reorder drops the rest and leaves the
+        // destinations it never wrote at zero (Frame.py:584,586-602).  Give every dropped source one of those holes and
+        // flag it (0x8000 = "store zero"), so that the scatter is a full permutation and needs no separate clear.
+        {
+            bool covered[576];
+            for (int i = 0; i < 576; i++) covered[i] = false;
+            for (int i = 0; i < total; i++) covered[T->reorder_dst[s][i]] = true;
+            int hole = 0;
+            for (int i = total; i < 576; i++) {
+                while (covered[hole]) hole++;
+                T->reorder_dst[s][i] = (uint16_t)(hole | 0x8000);
+                covered[hole] = true;
+            }
+            for (int i = idx; i < 576; i++) T->short_sfw_of[s][i] = 36;  // past the last band: sfb 12, window 0 (scalefactor 0)
+        }
     }
     for (int i = 0; i < 16; i++) { T->slen[i][0] = M3S_SLEN[2 * i]; T->slen[i][1] = M3S_SLEN[2 * i + 1]; }
     for (int i = 0; i < 22; i++) T->pretab[i] = M3S_PRETAB[i];

@@ -826,8 +826,9 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                     const M3sUnitRec &r = sm.rec[2 * gr + ch];
                     const bool reord = M3S_UA_BT(r.a) == 2 || M3S_UB_MIXED(r.b);
                     if (reord) {
-                        sm.xr[ch][sm.reorder[2 * p]] = val[ch][0];
-                        sm.xr[ch][sm.reorder[2 * p + 1]] = val[ch][1];
+                        const uint32_t d0 = sm.reorder[2 * p], d1 = sm.reorder[2 * p + 1];
+                        sm.xr[ch][d0 & 0x3FFu] = (d0 & 0x8000u) ? (R)0 : val[ch][0];
+                        sm.xr[ch][d1 & 0x3FFu] = (d1 & 0x8000u) ? (R)0 : val[ch][1];
                     } else {
                         sm.xr[ch][2 * p] = val[ch][0];
                         sm.xr[ch][2 * p + 1] = val[ch][1];

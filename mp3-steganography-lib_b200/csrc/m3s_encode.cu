@@ -75,7 +75,7 @@ __device__ __forceinline__ int32_t mulsr32(int32_t a, int32_t b)  // util.mulsr 
 // ================================================================================================
 #define ANA_THREADS 288
 
-__global__ void __launch_bounds__(ANA_THREADS)
+__global__ void __launch_bounds__(ANA_THREADS, 2)
 k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ clips, const M3sEncWork *__restrict__ work,
                const M3sDevTables *__restrict__ T, const EncTables *__restrict__ ET, int sr_idx, int64_t chunk_frame0,
                int32_t *__restrict__ mdct, M3sEncStats *__restrict__ stats)
@@ -247,22 +247,23 @@ struct GranInfo {  // the reference's gr_info fields the probes rewrite (MP3_Enc
     int bv, count1, c1sel, r0, r1, ts0, ts1, ts2;
 };
 
-// quantize() of the single largest coefficient: decides `quantize(...) > 8192` without touching the other 575
-// (ix is monotone in |xr| for a fixed step, and an overflowing probe's ix is never read again).   (:374-415)
-__device__ __forceinline__ int quant_one(const RateSmem &S, int32_t xabs, int step)
+// the reference's double-precision fallback of quantize() for ln >= 10000 (:401-407); rare, kept out of line so that
+// the 18 call sites of the unrolled quantiser stay small
+__device__ __noinline__ int quant_slow(int32_t xabs, double scale)
 {
-    const int32_t scalei = S.steptabi[step + 127];
-    const int32_t ln = mulr32(xabs, scalei);
-    if (ln < 10000) return S.i2i[ln];
-    const double dbl = __dmul_rn(__dmul_rn((double)xabs, S.steptab[step + 127]), 4.656612875e-10);
+    const double dbl = __dmul_rn(__dmul_rn((double)xabs, scale), 4.656612875e-10);
     return (int)__dsqrt_rn(__dmul_rn(__dsqrt_rn(dbl), dbl));
 }
 
+// quantize() of the single largest coefficient: decides `quantize(...) > 8192` without touching the other 575
+// (ix is monotone in |xr| for a fixed step, and an overflowing probe's ix is never read again).   (:374-415)
 __device__ __forceinline__ int quant_max(const RateSmem &S, int32_t xrmax, int step)
 {
     const int32_t scalei = S.steptabi[step + 127];
-    if (mulr32(xrmax, scalei) > 165140) return 16384;
-    return quant_one(S, xrmax, step);
+    const int32_t ln = mulr32(xrmax, scalei);
+    if (ln > 165140) return 16384;
+    if (ln < 10000) return S.i2i[ln];
+    return quant_slow(xrmax, S.steptab[step + 127]);
 }
 
 __device__ __forceinline__ int table_cost(const RateSmem &S, int t, uint32_t lo, uint32_t hi, uint32_t cnt)
@@ -285,10 +286,11 @@ __device__ __forceinline__ int choose_table(const RateSmem &S, int mx, uint32_t 
         choice = 13;  // the count-down search always stops at 13 (A.E4); only its 13-vs-15 arm is live
         if (table_cost(S, 15, lo, hi, cnt) <= table_cost(S, 13, lo, hi, cnt)) choice = 15;
     } else {
-        const int m = mx - 15;
-        int c0 = 0, c1 = 0;
-        for (int i = 15; i < 24; i++) if ((int)S.linmax[i] >= m) { c0 = i; break; }
-        for (int i = 24; i < 32; i++) if ((int)S.linmax[i] >= m) { c1 = i; break; }
+        // first table of 15..23 / 24..31 whose lin_max (0,1,3,7,15,63,255,1023,8191 / 15,31,63,127,255,511,2047,8191) covers mx - 15:
+        // a function of the bit length of mx - 15 (<= 13 bits since mx <= 8192 here)
+        const int nb = 32 - __clz(mx - 15);
+        const int c0 = 15 + (int)((0x88877665543210ULL >> (4 * nb)) & 15);
+        const int c1 = 24 + (int)((0x77665432100000ULL >> (4 * nb)) & 15);
         choice = c0;
         if (table_cost(S, c1, lo, hi, cnt) < table_cost(S, c0, lo, hi, cnt)) choice = c1;
     }
@@ -328,7 +330,8 @@ __device__ __forceinline__ int probe_bits(const RateSmem &S, const uint32_t (&qx
             const uint32_t nx = lane < 31 ? (nb >> (2 * j)) & 3u : (nb >> (2 * j + 2)) & 3u;
             const uint32_t idx = me | (nx << 2);  // v + 2 w + 4 x + 8 y
             const uint32_t nn = __popc(idx);
-            c1s += (S.hlc1[0][idx] + nn) | ((S.hlc1[1][idx] + nn) << 16);
+            // code lengths: table A = {1,4,4,5,4,6,5,6,4,5,5,6,5,6,6,6} (one nibble each), table B = 4 everywhere
+            c1s += ((uint32_t)((0x6665655465645441ULL >> (4 * idx)) & 15) + nn) | ((4u + nn) << 16);
         }
     }
     c1s = __reduce_add_sync(FULL, c1s);
@@ -381,16 +384,26 @@ __device__ __forceinline__ int probe_bits(const RateSmem &S, const uint32_t (&qx
     return bits;
 }
 
-// quantize() of all 576 values (:374-415); returns nothing: callers know from quant_max() that the maximum is <= 8192
+// quantize() of all 576 values (:374-415); callers know from quant_max() that the maximum is <= 8192
 __device__ __forceinline__ void quantize_all(const RateSmem &S, const uint32_t (&ax)[9], const uint32_t (&ay)[9], int step,
                                              uint32_t (&qx)[9], uint32_t (&qy)[9])
 {
     const int32_t scalei = S.steptabi[step + 127];
+    uint32_t big = 0;
 #pragma unroll
     for (int j = 0; j < 9; j++) {
         const int32_t lx = mulr32((int32_t)ax[j], scalei), ly = mulr32((int32_t)ay[j], scalei);
-        qx[j] = lx < 10000 ? (uint32_t)S.i2i[lx] : (uint32_t)quant_one(S, (int32_t)ax[j], step);
-        qy[j] = ly < 10000 ? (uint32_t)S.i2i[ly] : (uint32_t)quant_one(S, (int32_t)ay[j], step);
+        qx[j] = S.i2i[min(lx, 9999)];
+        qy[j] = S.i2i[min(ly, 9999)];
+        big |= (uint32_t)(lx >= 10000) << (2 * j) | (uint32_t)(ly >= 10000) << (2 * j + 1);
+    }
+    if (__any_sync(0xFFFFFFFFu, big != 0)) {
+        const double scale = S.steptab[step + 127];
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            if ((big >> (2 * j)) & 1u) qx[j] = (uint32_t)quant_slow((int32_t)ax[j], scale);
+            if ((big >> (2 * j + 1)) & 1u) qy[j] = (uint32_t)quant_slow((int32_t)ay[j], scale);
+        }
     }
 }
 
@@ -461,28 +474,32 @@ k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ state
                         hb = __ballot_sync(FULL, one);
                     }
                     uint32_t qx[9], qy[9];
-                    // ---- bin_search_step_size (:958-996)
-                    int next = -120, count = 120;
-                    do {
-                        const int half = count / 2;
-                        int bit;
-                        if (quant_max(S, xrmax, next + half) > 8192) bit = 100000;
-                        else {
-                            quantize_all(S, ax, ay, next + half, qx, qy);
-                            bit = probe_bits(S, qx, qy, lane, gi, a1, a2, a3, hiding, hn, hb);
+                    // ---- bin_search_step_size (:958-996) then inner_loop (:1064-1095), as one loop with a single probe site
+                    int next = -120, count = 120, half = 0, bits = 0;
+                    bool in_bin = true;
+                    for (;;) {
+                        int s;
+                        bool ovf = false;
+                        if (in_bin) {
+                            half = count / 2;
+                            s = next + half;
+                            ovf = quant_max(S, xrmax, s) > 8192;
+                        } else {
+                            while (quant_max(S, xrmax, step + 1) > 8192) step++;
+                            step++;
+                            s = step;
                         }
-                        if (bit < max_bits) count = half;
-                        else { next += half; count -= half; }
-                    } while (count > 1);
-                    step = next;
-                    // ---- inner_loop (:1064-1095)
-                    int bits;
-                    do {
-                        while (quant_max(S, xrmax, step + 1) > 8192) step++;
-                        step++;
-                        quantize_all(S, ax, ay, step, qx, qy);
-                        bits = probe_bits(S, qx, qy, lane, gi, a1, a2, a3, hiding, hn, hb);
-                    } while (bits > max_bits);
+                        bits = 100000;
+                        if (!ovf) {
+                            quantize_all(S, ax, ay, s, qx, qy);
+                            bits = probe_bits(S, qx, qy, lane, gi, a1, a2, a3, hiding, hn, hb);
+                        }
+                        if (in_bin) {
+                            if (bits < max_bits) count = half;
+                            else { next += half; count -= half; }
+                            if (count <= 1) { in_bin = false; step = next; }
+                        } else if (bits <= max_bits) break;
+                    }
                     part23 = bits;
                     st.hide_off += (gi.ts0 > 0) + (gi.ts1 > 0) + (gi.ts2 > 0);   // :808-809
                     // ---- signed ix as format_bitstream leaves it (:1272-1276)
