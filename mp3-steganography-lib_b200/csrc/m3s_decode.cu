@@ -687,11 +687,11 @@ struct HybSmem {
     R xr[2][576];
     R prev[2][2][576];
     R tt[2][18][32];
-    R v[2][33][64];
+    R v[2][64][32];            // ring of the last 64 slots of the 32 DISTINCT matrixing outputs per slot (see "matrixing")
+    R uw[HYB_THREADS / 32][32];  // per-warp butterfly scratch: u[0..15] | w[0..15]
     R cos36[36][18];
     R cos12[12][8];
     R sine[4][36];
-    R d[512];
     R pow43[256];
     R cs[8], ca[8];
     R quarter[4];
@@ -726,7 +726,7 @@ __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
 template <typename R, typename TAB, bool FLOAT_OUT>
-__global__ void __launch_bounds__(HYB_THREADS)
+__global__ void __launch_bounds__(HYB_THREADS, sizeof(R) == 4 ? 3 : 1)
 k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
          const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
          const TAB *__restrict__ TF, void *__restrict__ pcm_out)
@@ -741,21 +741,39 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
     for (int i = tid; i < 36 * 18; i += HYB_THREADS) (&sm.cos36[0][0])[i] = (&TF->imdct_cos36[0][0])[i];
     for (int i = tid; i < 12 * 8; i += HYB_THREADS) (&sm.cos12[0][0])[i] = (&TF->imdct_cos12[0][0])[i];
     for (int i = tid; i < 4 * 36; i += HYB_THREADS) (&sm.sine[0][0])[i] = (&TF->sine_block[0][0])[i];
-    for (int i = tid; i < 512; i += HYB_THREADS) sm.d[i] = TF->synth_d[i];
     for (int i = tid; i < 256; i += HYB_THREADS) sm.pow43[i] = TF->pow43[i];
     if (tid < 8) { sm.cs[tid] = TF->alias_cs[tid]; sm.ca[tid] = TF->alias_ca[tid]; }
     if (tid < 4) sm.quarter[tid] = TF->quarter[tid];
     if (tid < 22) sm.pretab[tid] = T->pretab[tid];
     if (tid == 0) sm.sr_loaded = -1;
     for (int i = tid; i < 2 * 2 * 576; i += HYB_THREADS) (&sm.prev[0][0][0])[i] = (R)0;
-    for (int i = tid; i < 2 * 33 * 64; i += HYB_THREADS) (&sm.v[0][0][0])[i] = (R)0;
-    // matrixing row held in registers: output index i = (warp & 1) * 32 + lane
-    R nrow[32];
+    for (int i = tid; i < 2 * 64 * 32; i += HYB_THREADS) (&sm.v[0][0][0])[i] = (R)0;
+    // ---- matrixing (Frame.py:81-87): V[i] = sum_j N[i][j] S[j], N[i][j] = cos((16 + i)(2 j + 1) pi / 64).
+    // Two exact symmetries shrink the 64 x 32 product to 32 x 16:
+    //   (a) N[i][31 - j] = (-1)^i N[i][j]            -> V[i] = sum_{j<16} N[i][j] (S[j] +- S[31 - j])      (u for even i, w for odd i)
+    //   (b) V[32 - i] = -V[i] (so V[16] = 0) and V[96 - i] = V[i]  -> only i = 0..15 and 48..63 are distinct.
+    // Lane l owns the distinct output i(l) = l (l < 16) or 32 + l (l >= 16) and keeps its 16 coefficients in registers.
+    R ncoef[16];
     {
-        const int i = (warp & 1) * 32 + lane;
+        const int i = lane < 16 ? lane : 32 + lane;
 #pragma unroll
-        for (int j = 0; j < 32; j++) nrow[j] = TF->synth_n[i][j];
+        for (int j = 0; j < 16; j++) ncoef[j] = TF->synth_n[i][j];
     }
+    // ---- windowing (Frame.py:89-101): pcm[32 t + i] = sum_m V_{t-2m}[i] D[64 m + i] + V_{t-2m-1}[32 + i] D[64 m + 32 + i].
+    // Lane i reads V through symmetry (b): V[i] = +W[i] | 0 | -W[32 - i], V[32 + i] = -W[0] | +W[32 - i] | +W[i]; the signs are
+    // folded into its 16 window coefficients, which stay in registers.
+    R dA[8], dB[8];
+    int idxA, idxB;
+    {
+        const int i = lane;
+        const R sA = i < 16 ? (R)1 : (i == 16 ? (R)0 : (R)-1);
+        const R sB = i == 0 ? (R)-1 : (R)1;
+        idxA = i < 16 ? i : (i == 16 ? 0 : 32 - i);
+        idxB = i == 0 ? 0 : (i < 16 ? 32 - i : i);
+#pragma unroll
+        for (int m = 0; m < 8; m++) { dA[m] = sA * TF->synth_d[64 * m + i]; dB[m] = sB * TF->synth_d[64 * m + 32 + i]; }
+    }
+    int vcur = 0;   // ring slot of the current granule's first time slot
     __syncthreads();
 
     int pp = 0;  // ping-pong index of the overlap buffer: prev[pp] is read, prev[pp ^ 1] written
@@ -854,78 +872,107 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                 if (ch < nch) {
                     const M3sUnitRec &r = sm.rec[2 * gr + ch];
                     const int bt = M3S_UA_BT(r.a);
-                    R x[18];
-#pragma unroll
-                    for (int k = 0; k < 18; k++) x[k] = sm.xr[ch][18 * sb + k];
                     const R *pv = sm.prev[pp][ch];
                     R *pn = sm.prev[pp ^ 1][ch];
+                    if (bt != 2) {
+                        // 36-point IMDCT (Frame.py:119-133): x_i = sum_k X_k cos(pi/72 (2 i + 19)(2 k + 1)) has x_{17-i} = -x_i and
+                        // x_{53-i} = x_i, so 18 sums give all 36 outputs; warp q takes 5 + 4 + 5 + 4 of them.
+                        R x[18];
 #pragma unroll
-                    for (int ii = 0; ii < 9; ii++) {
-                        const int i = 9 * q + ii;
-                        R acc = (R)0;
-                        if (bt != 2) {
+                        for (int k = 0; k < 18; k++) x[k] = sm.xr[ch][18 * sb + k];
+                        const int i0 = (q & 1) ? 5 : 0, n = (q & 1) ? 4 : 5;
+                        const bool second = q >= 2;
 #pragma unroll
-                            for (int k = 0; k < 18; k++) acc = fma_t(x[k], sm.cos36[i][k], acc);
-                            acc *= sm.sine[bt][i];
-                        } else if (i >= 6 && i < 30) {
-                            // three 12-point windows placed at 6/12/18 with overlap (Frame.py:135-148)
-                            const int w_hi = (i - 6) / 6;            // window whose first half covers i
-                            const int i_hi = i - 6 - 6 * w_hi;       // 0..5
-                            if (w_hi < 3) {
-                                R a2 = (R)0;
+                        for (int ii = 0; ii < 5; ii++) {
+                            if (ii < n) {
+                                const int d = i0 + ii;                 // 0..8
+                                const int i = second ? 18 + d : d;     // cos row
+                                R acc = (R)0;
 #pragma unroll
-                                for (int k = 0; k < 6; k++) a2 = fma_t(sm.xr[ch][18 * sb + 6 * w_hi + k], sm.cos12[i_hi][k], a2);
-                                acc += a2 * sm.sine[2][i_hi];
+                                for (int k = 0; k < 18; k++) acc = fma_t(x[k], sm.cos36[i][k], acc);
+                                if (!second) {
+                                    const int j = 17 - d;
+                                    R o1 = acc * sm.sine[bt][d] + pv[18 * sb + d];
+                                    R o2 = -acc * sm.sine[bt][j] + pv[18 * sb + j];
+                                    if ((sb & 1) && (d & 1)) o1 = -o1;
+                                    if ((sb & 1) && (j & 1)) o2 = -o2;
+                                    sm.tt[ch][d][sb] = o1;
+                                    sm.tt[ch][j][sb] = o2;
+                                } else {
+                                    pn[18 * sb + d] = acc * sm.sine[bt][18 + d];
+                                    pn[18 * sb + 17 - d] = acc * sm.sine[bt][35 - d];
+                                }
                             }
-                            const int w_lo = w_hi - 1;               // window whose second half covers i
-                            if (w_lo >= 0) {
-                                R a2 = (R)0;
-#pragma unroll
-                                for (int k = 0; k < 6; k++) a2 = fma_t(sm.xr[ch][18 * sb + 6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
-                                acc += a2 * sm.sine[2][i_hi + 6];
-                            }
-                        }
-                        if (i < 18) {
-                            R o = acc + pv[18 * sb + i];
-                            if ((sb & 1) && (i & 1)) o = -o;
-                            sm.tt[ch][i][sb] = o;
-                        } else pn[18 * sb + (i - 18)] = acc;
-                    }
-                }
-            }
-            __syncthreads();
-            // ------------------------------------------------ matrixing: V[t][i] = sum_j N[i][j] * S_t[j]
-            {
-                const int i = (warp & 1) * 32 + lane, tg = warp >> 1;
-                for (int cidx = tg; cidx < nch * 18; cidx += 4) {
-                    const int ch = cidx / 18, t = cidx - 18 * ch;
-                    R acc = (R)0;
-                    if constexpr (sizeof(R) == 4) {
-                        const float4 *s4 = (const float4 *)sm.tt[ch][t];
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; j4++) {
-                            const float4 s = s4[j4];
-                            acc = fma_t((R)s.x, nrow[4 * j4 + 0], acc);
-                            acc = fma_t((R)s.y, nrow[4 * j4 + 1], acc);
-                            acc = fma_t((R)s.z, nrow[4 * j4 + 2], acc);
-                            acc = fma_t((R)s.w, nrow[4 * j4 + 3], acc);
                         }
                     } else {
-                        const double2 *s2 = (const double2 *)sm.tt[ch][t];
 #pragma unroll
-                        for (int j2 = 0; j2 < 16; j2++) {
-                            const double2 s = s2[j2];
-                            acc = fma_t((R)s.x, nrow[2 * j2 + 0], acc);
-                            acc = fma_t((R)s.y, nrow[2 * j2 + 1], acc);
+                        for (int ii = 0; ii < 9; ii++) {
+                            const int i = 9 * q + ii;
+                            R acc = (R)0;
+                            if (i >= 6 && i < 30) {
+                                // three 12-point windows placed at 6/12/18 with overlap (Frame.py:135-148)
+                                const int w_hi = (i - 6) / 6;            // window whose first half covers i
+                                const int i_hi = i - 6 - 6 * w_hi;       // 0..5
+                                if (w_hi < 3) {
+                                    R a2 = (R)0;
+#pragma unroll
+                                    for (int k = 0; k < 6; k++) a2 = fma_t(sm.xr[ch][18 * sb + 6 * w_hi + k], sm.cos12[i_hi][k], a2);
+                                    acc += a2 * sm.sine[2][i_hi];
+                                }
+                                const int w_lo = w_hi - 1;               // window whose second half covers i
+                                if (w_lo >= 0) {
+                                    R a2 = (R)0;
+#pragma unroll
+                                    for (int k = 0; k < 6; k++) a2 = fma_t(sm.xr[ch][18 * sb + 6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
+                                    acc += a2 * sm.sine[2][i_hi + 6];
+                                }
+                            }
+                            if (i < 18) {
+                                R o = acc + pv[18 * sb + i];
+                                if ((sb & 1) && (i & 1)) o = -o;
+                                sm.tt[ch][i][sb] = o;
+                            } else pn[18 * sb + (i - 18)] = acc;
                         }
                     }
-                    sm.v[ch][15 + t][i] = acc;
                 }
             }
             __syncthreads();
-            // ------------------------------------------------ windowing + output
+            // ------------------------------------------------ matrixing: the 32 distinct V values of every (channel, slot)
+            for (int cidx = warp; cidx < nch * 18; cidx += HYB_THREADS / 32) {
+                const int ch = cidx / 18, t = cidx - 18 * ch;
+                const R sv = sm.tt[ch][t][lane];
+                const R pr = __shfl_sync(0xFFFFFFFFu, sv, 31 - lane);
+                // lanes 0..15: u[l] = S[l] + S[31 - l]; lanes 16..31: w[31 - l] = S[31 - l] - S[l]
+                sm.uw[warp][lane < 16 ? lane : 47 - lane] = lane < 16 ? sv + pr : pr - sv;
+                __syncwarp();
+                const R *in = sm.uw[warp] + ((lane & 1) ? 16 : 0);   // i(l) has the parity of l
+                R acc = (R)0;
+                if constexpr (sizeof(R) == 4) {
+                    const float4 *s4 = (const float4 *)in;
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; j4++) {
+                        const float4 v4 = s4[j4];
+                        acc = fma_t((R)v4.x, ncoef[4 * j4 + 0], acc);
+                        acc = fma_t((R)v4.y, ncoef[4 * j4 + 1], acc);
+                        acc = fma_t((R)v4.z, ncoef[4 * j4 + 2], acc);
+                        acc = fma_t((R)v4.w, ncoef[4 * j4 + 3], acc);
+                    }
+                } else {
+                    const double2 *s2 = (const double2 *)in;
+#pragma unroll
+                    for (int j2 = 0; j2 < 8; j2++) {
+                        const double2 v2 = s2[j2];
+                        acc = fma_t((R)v2.x, ncoef[2 * j2 + 0], acc);
+                        acc = fma_t((R)v2.y, ncoef[2 * j2 + 1], acc);
+                    }
+                }
+                sm.v[ch][(vcur + t) & 63][lane] = acc;
+                __syncwarp();
+            }
+            __syncthreads();
+            // ------------------------------------------------ windowing + output (lane = sample index within the slot)
             for (int o = tid; o < 576; o += HYB_THREADS) {
-                const int t = o >> 5, i = o & 31;
+                const int t = o >> 5;
                 R s[2] = {(R)0, (R)0};
 #pragma unroll
                 for (int ch = 0; ch < 2; ch++) {
@@ -933,8 +980,8 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                     R acc = (R)0;
 #pragma unroll
                     for (int m = 0; m < 8; m++) {
-                        acc = fma_t(sm.v[ch][15 + t - 2 * m][i], sm.d[64 * m + i], acc);
-                        acc = fma_t(sm.v[ch][15 + t - 2 * m - 1][32 + i], sm.d[64 * m + 32 + i], acc);
+                        acc = fma_t(sm.v[ch][(vcur + t - 2 * m) & 63][idxA], dA[m], acc);
+                        acc = fma_t(sm.v[ch][(vcur + t - 2 * m - 1) & 63][idxB], dB[m], acc);
                     }
                     s[ch] = acc;
                 }
@@ -959,12 +1006,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                     }
                 }
             }
-            __syncthreads();
-            // ------------------------------------------------ slide the V history: slots 18..32 -> 0..14
-            for (int idx = tid; idx < nch * 15 * 64; idx += HYB_THREADS) {
-                const int ch = idx / (15 * 64), r_ = idx - ch * 15 * 64;
-                (&sm.v[ch][0][0])[r_] = (&sm.v[ch][18][0])[r_];
-            }
+            vcur = (vcur + 18) & 63;
             pp ^= 1;
             __syncthreads();
         }
