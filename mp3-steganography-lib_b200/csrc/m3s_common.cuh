@@ -191,6 +191,7 @@ int m3s_fail(m3s_ctx *h, int code, const char *fmt, ...);
 void m3s_time_begin(m3s_ctx *h, int id);
 void m3s_time_end(m3s_ctx *h);
 int m3s_buf_reserve(m3s_ctx *h, M3sBuf &b, size_t bytes);
+int m3s_upload_cos36(const float *f, const double *d);  // m3s_decode.cu: constant-memory IMDCT rows of the current device
 
 #define M3S_CUDA(h, call)                                                                             \
     do {                                                                                              \

@@ -272,6 +272,19 @@ extern "C" int m3s_create(int device, m3s_handle_t *out)
         if (e == cudaSuccess) e = cudaMemcpy(h->d_tab_f64, TD, sizeof(M3sDevTablesD), cudaMemcpyHostToDevice);
         delete TD;
     }
+    if (e == cudaSuccess) {
+        // the 18 distinct IMDCT-36 rows (outputs 0..8 and 18..26) as immediate constant-bank operands
+        const double PI = 3.141592653589793;
+        static float cf[18][18];
+        static double cd[18][18];
+        for (int r = 0; r < 18; r++)
+            for (int k = 0; k < 18; k++) {
+                const int i = r < 9 ? r : 18 + (r - 9);
+                cd[r][k] = cos(PI / 72.0 * (2 * i + 1 + 18) * (2 * k + 1));
+                cf[r][k] = (float)cd[r][k];
+            }
+        if (m3s_upload_cos36(&cf[0][0], &cd[0][0]) != 0) e = cudaErrorUnknown;
+    }
     if (e != cudaSuccess) {
         cudaStreamDestroy(h->own_stream);
         delete h;

@@ -687,9 +687,8 @@ struct HybSmem {
     R xr[2][576];
     R prev[2][2][576];
     R tt[2][18][32];
-    R v[2][64][32];            // ring of the last 64 slots of the 32 DISTINCT matrixing outputs per slot (see "matrixing")
+    R v[2][33][32];            // the 32 DISTINCT matrixing outputs per slot (see "matrixing"): 15 slots of history + 18 new
     R uw[HYB_THREADS / 32][32];  // per-warp butterfly scratch: u[0..15] | w[0..15]
-    R cos36[36][18];
     R cos12[12][8];
     R sine[4][36];
     R pow43[256];
@@ -725,6 +724,50 @@ __device__ __forceinline__ double requant_mag(const HybSmem<double> &sm, int ax,
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
+// The 18 distinct rows of the 36-point IMDCT matrix (rows 0..8: outputs 0..8; rows 9..17: outputs 18..26) in constant memory:
+// with the row and column known at compile time every coefficient is an immediate constant-bank operand of its FMA.
+__constant__ float c_cos36_f[18][18];
+__constant__ double c_cos36_d[18][18];
+template <typename R> __device__ __forceinline__ R cos36c(int row, int k);
+template <> __device__ __forceinline__ float cos36c<float>(int row, int k) { return c_cos36_f[row][k]; }
+template <> __device__ __forceinline__ double cos36c<double>(int row, int k) { return c_cos36_d[row][k]; }
+
+int m3s_upload_cos36(const float *f, const double *d)
+{
+    if (cudaMemcpyToSymbol(c_cos36_f, f, sizeof(float) * 18 * 18) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(c_cos36_d, d, sizeof(double) * 18 * 18) != cudaSuccess) return -1;
+    return 0;
+}
+
+// Long-block IMDCT of one subband for warp role Q (Frame.py:119-133, 150-153): x_i = sum_k X_k cos(pi/72 (2 i + 19)(2 k + 1)) has
+// x_{17-i} = -x_i and x_{53-i} = x_i, so 18 sums give all 36 outputs; roles 0/1 take sums 0..4 / 5..8 of the first half (windowed,
+// overlap-added, frequency-inverted into tt), roles 2/3 the same of the second half (windowed into the next overlap buffer).
+template <typename R, int Q>
+__device__ __forceinline__ void imdct_long(const R (&x)[18], const R *sine_bt, const R *pv, R *pn, R *tt_col, int sb)
+{
+    constexpr int D0 = (Q & 1) ? 5 : 0, N = (Q & 1) ? 4 : 5;
+    constexpr bool SECOND = Q >= 2;
+#pragma unroll
+    for (int ii = 0; ii < N; ii++) {
+        const int d = D0 + ii;
+        R acc = (R)0;
+#pragma unroll
+        for (int k = 0; k < 18; k++) acc = fma_t(x[k], cos36c<R>((SECOND ? 9 : 0) + d, k), acc);
+        if (!SECOND) {
+            const int j = 17 - d;
+            R o1 = acc * sine_bt[d] + pv[18 * sb + d];
+            R o2 = -acc * sine_bt[j] + pv[18 * sb + j];
+            if ((sb & 1) && (d & 1)) o1 = -o1;
+            if ((sb & 1) && (j & 1)) o2 = -o2;
+            tt_col[32 * d] = o1;      // tt[ch][d][sb]
+            tt_col[32 * j] = o2;
+        } else {
+            pn[18 * sb + d] = acc * sine_bt[18 + d];
+            pn[18 * sb + 17 - d] = acc * sine_bt[35 - d];
+        }
+    }
+}
+
 template <typename R, typename TAB, bool FLOAT_OUT>
 __global__ void __launch_bounds__(HYB_THREADS, sizeof(R) == 4 ? 3 : 1)
 k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
@@ -738,7 +781,6 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
     const int nch = wk.channels;
 
     // ---- one-time table staging
-    for (int i = tid; i < 36 * 18; i += HYB_THREADS) (&sm.cos36[0][0])[i] = (&TF->imdct_cos36[0][0])[i];
     for (int i = tid; i < 12 * 8; i += HYB_THREADS) (&sm.cos12[0][0])[i] = (&TF->imdct_cos12[0][0])[i];
     for (int i = tid; i < 4 * 36; i += HYB_THREADS) (&sm.sine[0][0])[i] = (&TF->sine_block[0][0])[i];
     for (int i = tid; i < 256; i += HYB_THREADS) sm.pow43[i] = TF->pow43[i];
@@ -747,7 +789,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
     if (tid < 22) sm.pretab[tid] = T->pretab[tid];
     if (tid == 0) sm.sr_loaded = -1;
     for (int i = tid; i < 2 * 2 * 576; i += HYB_THREADS) (&sm.prev[0][0][0])[i] = (R)0;
-    for (int i = tid; i < 2 * 64 * 32; i += HYB_THREADS) (&sm.v[0][0][0])[i] = (R)0;
+    for (int i = tid; i < 2 * 33 * 32; i += HYB_THREADS) (&sm.v[0][0][0])[i] = (R)0;
     // ---- matrixing (Frame.py:81-87): V[i] = sum_j N[i][j] S[j], N[i][j] = cos((16 + i)(2 j + 1) pi / 64).
     // Two exact symmetries shrink the 64 x 32 product to 32 x 16:
     //   (a) N[i][31 - j] = (-1)^i N[i][j]            -> V[i] = sum_{j<16} N[i][j] (S[j] +- S[31 - j])      (u for even i, w for odd i)
@@ -773,7 +815,6 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
 #pragma unroll
         for (int m = 0; m < 8; m++) { dA[m] = sA * TF->synth_d[64 * m + i]; dB[m] = sB * TF->synth_d[64 * m + 32 + i]; }
     }
-    int vcur = 0;   // ring slot of the current granule's first time slot
     __syncthreads();
 
     int pp = 0;  // ping-pong index of the overlap buffer: prev[pp] is read, prev[pp ^ 1] written
@@ -875,34 +916,15 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                     const R *pv = sm.prev[pp][ch];
                     R *pn = sm.prev[pp ^ 1][ch];
                     if (bt != 2) {
-                        // 36-point IMDCT (Frame.py:119-133): x_i = sum_k X_k cos(pi/72 (2 i + 19)(2 k + 1)) has x_{17-i} = -x_i and
-                        // x_{53-i} = x_i, so 18 sums give all 36 outputs; warp q takes 5 + 4 + 5 + 4 of them.
                         R x[18];
 #pragma unroll
                         for (int k = 0; k < 18; k++) x[k] = sm.xr[ch][18 * sb + k];
-                        const int i0 = (q & 1) ? 5 : 0, n = (q & 1) ? 4 : 5;
-                        const bool second = q >= 2;
-#pragma unroll
-                        for (int ii = 0; ii < 5; ii++) {
-                            if (ii < n) {
-                                const int d = i0 + ii;                 // 0..8
-                                const int i = second ? 18 + d : d;     // cos row
-                                R acc = (R)0;
-#pragma unroll
-                                for (int k = 0; k < 18; k++) acc = fma_t(x[k], sm.cos36[i][k], acc);
-                                if (!second) {
-                                    const int j = 17 - d;
-                                    R o1 = acc * sm.sine[bt][d] + pv[18 * sb + d];
-                                    R o2 = -acc * sm.sine[bt][j] + pv[18 * sb + j];
-                                    if ((sb & 1) && (d & 1)) o1 = -o1;
-                                    if ((sb & 1) && (j & 1)) o2 = -o2;
-                                    sm.tt[ch][d][sb] = o1;
-                                    sm.tt[ch][j][sb] = o2;
-                                } else {
-                                    pn[18 * sb + d] = acc * sm.sine[bt][18 + d];
-                                    pn[18 * sb + 17 - d] = acc * sm.sine[bt][35 - d];
-                                }
-                            }
+                        R *ttc = &sm.tt[ch][0][sb];
+                        switch (q) {   // warp-uniform
+                        case 0: imdct_long<R, 0>(x, sm.sine[bt], pv, pn, ttc, sb); break;
+                        case 1: imdct_long<R, 1>(x, sm.sine[bt], pv, pn, ttc, sb); break;
+                        case 2: imdct_long<R, 2>(x, sm.sine[bt], pv, pn, ttc, sb); break;
+                        default: imdct_long<R, 3>(x, sm.sine[bt], pv, pn, ttc, sb); break;
                         }
                     } else {
 #pragma unroll
@@ -966,7 +988,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                         acc = fma_t((R)v2.y, ncoef[2 * j2 + 1], acc);
                     }
                 }
-                sm.v[ch][(vcur + t) & 63][lane] = acc;
+                sm.v[ch][15 + t][lane] = acc;
                 __syncwarp();
             }
             __syncthreads();
@@ -977,13 +999,14 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
 #pragma unroll
                 for (int ch = 0; ch < 2; ch++) {
                     if (ch >= nch) continue;
-                    R acc = (R)0;
+                    const R *va = &sm.v[ch][15 + t][idxA], *vb = &sm.v[ch][14 + t][idxB];   // fixed offsets from two bases
+                    R acc0 = (R)0, acc1 = (R)0;
 #pragma unroll
                     for (int m = 0; m < 8; m++) {
-                        acc = fma_t(sm.v[ch][(vcur + t - 2 * m) & 63][idxA], dA[m], acc);
-                        acc = fma_t(sm.v[ch][(vcur + t - 2 * m - 1) & 63][idxB], dB[m], acc);
+                        acc0 = fma_t(va[-64 * m], dA[m], acc0);
+                        acc1 = fma_t(vb[-64 * m], dB[m], acc1);
                     }
-                    s[ch] = acc;
+                    s[ch] = acc0 + acc1;
                 }
                 if (emit) {
                     const int reps = (meta & M3S_META_DUP) ? 2 : 1;
@@ -1006,9 +1029,13 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                     }
                 }
             }
-            vcur = (vcur + 18) & 63;
-            pp ^= 1;
             __syncthreads();
+            // ------------------------------------------------ slide the V history: slots 18..32 -> 0..14
+            for (int idx = tid; idx < nch * 15 * 32; idx += HYB_THREADS) {
+                const int ch = idx / (15 * 32), r_ = idx - ch * 15 * 32;
+                (&sm.v[ch][0][0])[r_] = (&sm.v[ch][18][0])[r_];
+            }
+            pp ^= 1;   // no barrier needed here: the next writers of v[15..32] sit behind the barriers of the next granule's phases
         }
     }
 }

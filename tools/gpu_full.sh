@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/tests_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/tests_gpu.log
 tail -25 gpurun_out/tests_gpu.log
 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
-timeout 1500 python bench.py --files ${FILES:-1000} --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+timeout 1500 python bench.py --files ${FILES:-1000} --steps 3 --warmup 3 ${BENCH_ARGS} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
 cat gpurun_out/bench.json; tail -8 gpurun_out/bench.err
 if [ -z "$NO_NCU" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
