@@ -189,8 +189,8 @@ def corpus_config(args):
     return {"workload": f"configs[1]: batch decode+reveal of {args.files} synthetic 320 kbps 44.1 kHz stereo "
                         f"{args.frames * 1152 / 44100.0:.0f}-s MP3s per GPU ({args.files * args.frames} frames); "
                         f"encode_hide = configs[2]: the same WAVs -> 128 kbps hiding random ASCII beyond capacity",
-            "files_per_gpu": args.files, "frames_per_file": args.frames, "wave_files": args.wave,
-            "l2": "inputs larger than L2 (every wave streams >= 0.9 GB of MP3 / >= 4 GB of PCM)",
+            "files_per_gpu": args.files, "frames_per_file": args.frames, "wave_files": args.wave, "e2e_wave_files": args.e2e_wave, "e2e_workers": args.e2e_workers,
+            "l2": "inputs larger than L2 (every wave streams >= 0.36 GB of MP3 and >= 1.6 GB of PCM; L2 is 126 MB)",
             "corpus": "tone+noise WAVs (SURVEY 8d) generated on device; MP3s produced from them by the product encoder "
                       "(byte-identical to the reference encoder's output)"}
 
@@ -284,26 +284,32 @@ def run_product_arm(args):
     mp3_all = res["mp3"]
     mp3_host_all = mp3_all.cpu().pin_memory()
     del res
-    waves = []
-    for w in range(nw):
-        lo, hi = w * args.wave, min(args.files, (w + 1) * args.wave)
-        b0, b1 = int(off_all[lo]), int(off_all[hi])
-        waves.append(dict(n=hi - lo, frames=(hi - lo) * args.frames, off=off_all[lo:hi + 1] - b0,
-                          mp3_dev=mp3_all[b0:b1], mp3_host=mp3_host_all[b0:b1]))
+    def make_waves(wave_files):
+        ws = []
+        for lo in range(0, args.files, wave_files):
+            hi = min(args.files, lo + wave_files)
+            b0, b1 = int(off_all[lo]), int(off_all[hi])
+            ws.append(dict(n=hi - lo, frames=(hi - lo) * args.frames, off=off_all[lo:hi + 1] - b0,
+                           mp3_dev=mp3_all[b0:b1], mp3_host=mp3_host_all[b0:b1]))
+        return ws
+
+    waves = make_waves(args.wave)             # device-resident leg: large waves (fewer latency-bound scan launches)
+    e2e_waves = make_waves(args.e2e_wave)     # host leg: smaller waves keep both PCIe directions busy with short fill / drain
     pay_all, pay_off_all = random_payload_bits(args.files, pay_bits, 31 * rank + 5)
     pcm_host_all = None
     total_frames = args.files * args.frames
     max_wave_frames = max(w["frames"] for w in waves)
+    max_e2e_frames = max(w["frames"] for w in e2e_waves)
     mp3_bytes = int(off_all[-1])
     log(f"[rank {rank}] corpus: {args.files} files x {args.frames} frames = {total_frames} frames, "
         f"{mp3_bytes / 1e9:.2f} GB MP3 @320k, {total_frames * 4608 / 1e9:.2f} GB PCM, {nw} decode waves ({time.perf_counter() - t0:.1f}s)")
 
     pcm_out_dev = torch.empty(max_wave_frames * 1152 * 2 + 64, dtype=torch.int16, device=dev)
-    pcm_out_host = torch.empty(max_wave_frames * 1152 * 2 + 64, dtype=torch.int16, pin_memory=True)
+    pcm_out_host = torch.empty(max_e2e_frames * 1152 * 2 + 64, dtype=torch.int16, pin_memory=True)
     ids_dev = torch.empty(max_wave_frames * 12, dtype=torch.uint8, device=dev)
     bits_dev = torch.empty(max_wave_frames * 12, dtype=torch.uint8, device=dev)
-    ids_host = np.zeros(max_wave_frames * 12, np.uint8)
-    bits_host = np.zeros(max_wave_frames * 12, np.uint8)
+    ids_host = torch.empty(max_e2e_frames * 12, dtype=torch.uint8, pin_memory=True)
+    bits_host = torch.empty(max_e2e_frames * 12, dtype=torch.uint8, pin_memory=True)
     enc_cap = int(_lib.load().m3s_encode_bound(n_samp, 44100, 128)) * args.files + 64
     enc_out_dev = torch.empty(enc_cap, dtype=torch.uint8, device=dev)
     enc_out_host = None
@@ -319,14 +325,42 @@ def run_product_arm(args):
             check["reveal_bits"] = int(ln.sum())
         return n
 
+    # e2e: host buffers through the C ABI.  A host application keeps PCIe busy in both directions by running one worker
+    # thread per handle (handles are independent: own stream, own workspaces, own pinned PCM buffer); the waves are dealt
+    # round-robin, so wave k's PCM goes home while wave k+1 is in the kernels and wave k+2's MP3 bytes come up.
+    import threading
+    n_workers = max(1, min(args.e2e_workers, len(e2e_waves)))
+    workers = [dict(h=h, pcm=pcm_out_host, ids=ids_host, bits=bits_host)]
+    for _ in range(1, n_workers):
+        workers.append(dict(h=_lib.Handle(local), pcm=torch.empty(max_e2e_frames * 1152 * 2 + 64, dtype=torch.int16, pin_memory=True),
+                            ids=torch.empty(max_e2e_frames * 12, dtype=torch.uint8, pin_memory=True),
+                            bits=torch.empty(max_e2e_frames * 12, dtype=torch.uint8, pin_memory=True)))
+
     def dec_host():
-        n = 0
-        for w in waves:
-            sc = h.decode_scan(w["mp3_host"], w["off"])
-            h.decode_reveal_into(ids_host, bits_host)
-            h.decode_run(pcm=pcm_out_host)
-            n += int(sc["n_frames"].sum())
-        return n
+        counts = [0] * n_workers
+        errs = []
+
+        def run(k):
+            try:
+                torch.cuda.set_device(local)
+                wk = workers[k]
+                for w in e2e_waves[k::n_workers]:
+                    sc = wk["h"].decode_scan(w["mp3_host"], w["off"])
+                    wk["h"].decode_reveal_into(wk["ids"], wk["bits"])
+                    wk["h"].decode_run(pcm=wk["pcm"])
+                    counts[k] += int(sc["n_frames"].sum())
+            except Exception as e:   # surfaced below: a failed worker must fail the bench
+                errs.append(e)
+
+        ts = [threading.Thread(target=run, args=(k,)) for k in range(1, n_workers)]
+        for t in ts:
+            t.start()
+        run(0)
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+        return sum(counts)
 
     # encode+hide: ONE call over all clips -- the rate loop runs one warp per clip, so the whole corpus goes in together
     # (the library walks it in frame windows to bound its intermediates)
@@ -448,8 +482,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--files", type=int, default=1000, help="files per GPU")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_FILE, help="frames per file")
-    ap.add_argument("--wave", type=int, default=125, help="files per wave (bounds the device workspaces)")
+    ap.add_argument("--wave", type=int, default=250, help="files per wave of the device-resident decode leg (bounds the workspaces)")
+    ap.add_argument("--e2e-wave", type=int, default=50, help="files per wave of the host-buffer (e2e) decode leg")
     ap.add_argument("--no-encode", action="store_true", help="skip the encode+hide half")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="host worker threads (one handle each) of the decode e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

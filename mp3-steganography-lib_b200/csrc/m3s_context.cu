@@ -296,6 +296,65 @@ extern "C" int m3s_create(int device, m3s_handle_t *out)
 
 static void timing_resolve(m3s_ctx *h);
 
+int m3s_pipeline_init(m3s_ctx *h)
+{
+    if (h->copy_in) return M3S_OK;
+    M3S_CUDA(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    M3S_CUDA(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
+    M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    return M3S_OK;
+}
+
+// Bulk PCIe transfers are issued in pieces of at most M3S_COPY_PIECE bytes: a copy engine serves one command at a time,
+// so a multi-GB command would hold back every small descriptor copy (and the host thread waiting on it) of this and of
+// other handles for tens of milliseconds; with bounded pieces those slot in within about a millisecond.
+#define M3S_COPY_PIECE ((size_t)32 << 20)
+
+cudaError_t m3s_copy_bulk(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s)
+{
+    for (size_t o = 0; o < bytes; o += M3S_COPY_PIECE) {
+        const size_t n = bytes - o < M3S_COPY_PIECE ? bytes - o : M3S_COPY_PIECE;
+        const cudaError_t e = cudaMemcpyAsync((char *)dst + o, (const char *)src + o, n, kind, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t m3s_copy_rows(const std::vector<M3sRow> &rows, cudaMemcpyKind kind, cudaStream_t s)
+{
+    const size_t n = rows.size();
+    if (n == 0) return cudaSuccess;
+    bool regular = n > 1 && rows[0].bytes > 0;
+    ptrdiff_t dp = 0, sp = 0;
+    if (regular) {
+        dp = rows[1].dst - rows[0].dst;
+        sp = rows[1].src - rows[0].src;
+        regular = dp >= (ptrdiff_t)rows[0].bytes && sp >= (ptrdiff_t)rows[0].bytes && dp <= 0x7FFFFFFF && sp <= 0x7FFFFFFF;
+        for (size_t i = 1; regular && i < n; i++)
+            regular = rows[i].bytes == rows[0].bytes && rows[i].dst - rows[i - 1].dst == dp && rows[i].src - rows[i - 1].src == sp;
+    }
+    if (regular) {
+        size_t per = M3S_COPY_PIECE / rows[0].bytes;   // rows per 2-D command
+        if (per < 1) per = 1;
+        for (size_t i = 0; i < n; i += per) {
+            const size_t h = n - i < per ? n - i : per;
+            const cudaError_t e = cudaMemcpy2DAsync(rows[i].dst, (size_t)dp, rows[i].src, (size_t)sp, rows[0].bytes, h, kind, s);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    for (const M3sRow &r : rows)
+        if (r.bytes) {
+            const cudaError_t e = m3s_copy_bulk(r.dst, r.src, r.bytes, kind, s);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
+}
+
 static void free_buf(M3sBuf &b)
 {
     if (b.p) cudaFree(b.p);
@@ -318,6 +377,13 @@ extern "C" int m3s_destroy(m3s_handle_t h)
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->d_tab) cudaFree(h->d_tab);
     if (h->d_tab_f64) cudaFree(h->d_tab_f64);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
+    }
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return M3S_OK;

@@ -1061,7 +1061,7 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     if (mem == M3S_MEM_HOST) {
         int rc = m3s_buf_reserve(h, h->b_stage_in, (size_t)total_bytes + 16);
         if (rc) return rc;
-        M3S_CUDA(h, cudaMemcpyAsync(h->b_stage_in.p, bytes, (size_t)total_bytes, cudaMemcpyHostToDevice, h->stream));
+        M3S_CUDA(h, m3s_copy_bulk(h->b_stage_in.p, bytes, (size_t)total_bytes, cudaMemcpyHostToDevice, h->stream));
         h->d_bytes = (const uint8_t *)h->b_stage_in.p;
     } else
         h->d_bytes = bytes;
@@ -1236,7 +1236,7 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
         k_spec_export<<<(unsigned)((nf * 288 * 4 + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)h->b_spec.p, nf, d_sp);
         M3S_LAUNCH_CHECK(h);
         if (mem == M3S_MEM_HOST)
-            M3S_CUDA(h, cudaMemcpyAsync(spectra, d_sp, (size_t)nf * 4 * 576 * 2, cudaMemcpyDeviceToHost, h->stream));
+            M3S_CUDA(h, m3s_copy_bulk(spectra, d_sp, (size_t)nf * 4 * 576 * 2, cudaMemcpyDeviceToHost, h->stream));
     }
     const bool exact = (flags & M3S_DEC_EXACT) != 0;
 #define M3S_LAUNCH_HYBRID(R, TAB, FL, tabptr)                                                                              \
@@ -1257,7 +1257,7 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
     }
     M3S_LAUNCH_CHECK(h);
     if (mem == M3S_MEM_HOST)
-        M3S_CUDA(h, cudaMemcpyAsync(pcm, d_pcm, (size_t)total_elems * esz, cudaMemcpyDeviceToHost, h->stream));
+        M3S_CUDA(h, m3s_copy_bulk(pcm, d_pcm, (size_t)total_elems * esz, cudaMemcpyDeviceToHost, h->stream));
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     return M3S_OK;
 }

@@ -878,15 +878,13 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         if ((rc = m3s_buf_reserve(h, h->e_tabs, sizeof(EncTables)))) return rc;
         M3S_CUDA(h, cudaMemcpy(h->e_tabs.p, &E, sizeof E, cudaMemcpyHostToDevice));
     }
-    // ---- inputs
+    // ---- inputs.  Host buffers are streamed: the PCM of chunk k+1 crosses PCIe on `copy_in` while chunk k is in the
+    //      kernels, and the MP3 bytes of chunk k-1 go back on `copy_out` (see the chunk loop below)
+    const bool host = mem == M3S_MEM_HOST;
     const int16_t *d_pcm = pcm;
-    if (mem == M3S_MEM_HOST) {
-        if ((rc = m3s_buf_reserve(h, h->e_pcm, (size_t)pcm_elems * 2 + 16))) return rc;
-        M3S_CUDA(h, cudaMemcpyAsync(h->e_pcm.p, pcm, (size_t)pcm_elems * 2, cudaMemcpyHostToDevice, h->stream));
-        d_pcm = (const int16_t *)h->e_pcm.p;
-    }
     uint8_t *d_out = mp3_out;
-    if (mem == M3S_MEM_HOST) {
+    if (host) {
+        if ((rc = m3s_pipeline_init(h))) return rc;
         if ((rc = m3s_buf_reserve(h, h->e_out, (size_t)out_total + 16))) return rc;
         d_out = (uint8_t *)h->e_out.p;
     }
@@ -920,8 +918,36 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     std::vector<M3sEncWork> work;
     std::vector<int32_t> frame_clip;
     std::vector<M3sEncClip> cclips(n_clips);
-    for (int64_t c0 = 0; c0 < max_frames; c0 += cf) {
+    // host staging: per chunk every clip owns a region of cf * 1152 + 1056 stereo samples (1056 = the analysis history the
+    // first granule of the chunk reaches back to: 480 window taps + one warm-up granule), two regions sets for double buffering
+    const int64_t region = cf * 1152 + 1056;
+    const size_t stage_bytes = host ? (size_t)n_clips * (size_t)region * 4 : 0;
+    if (host && (rc = m3s_buf_reserve(h, h->e_pcm, 2 * stage_bytes + 16))) return rc;
+    std::vector<M3sRow> rows;
+    bool free_recorded[2] = {false, false};
+    auto stage_chunk = [&](int64_t c0, int buf) -> cudaError_t {   // H2D of the PCM that chunk [c0, c0 + cf) reads
+        rows.clear();
+        for (int i = 0; i < n_clips; i++) {
+            const int64_t nfc = std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0));
+            if (nfc == 0) continue;
+            const int64_t first = c0 * 1152 - 1056, s0 = std::max<int64_t>(first, 0), s1 = (c0 + nfc) * 1152;
+            M3sRow r;
+            r.dst = (char *)h->e_pcm.p + (size_t)buf * stage_bytes + ((size_t)i * region + (size_t)(s0 - first)) * 4;
+            r.src = (const char *)pcm + clips[i].pcm_base * 2 + s0 * 4;
+            r.bytes = (size_t)(s1 - s0) * 4;
+            rows.push_back(r);
+        }
+        cudaError_t e = cudaSuccess;
+        if (free_recorded[buf]) e = cudaStreamWaitEvent(h->copy_in, h->ev_free[buf], 0);
+        if (e == cudaSuccess) e = m3s_copy_rows(rows, cudaMemcpyHostToDevice, h->copy_in);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[buf], h->copy_in);
+        return e;
+    };
+    if (host) M3S_CUDA(h, stage_chunk(0, 0));
+    int chunk_idx = 0;
+    for (int64_t c0 = 0; c0 < max_frames; c0 += cf, chunk_idx++) {
         // frames [c0, c0 + cf) of every clip; within the chunk buffers clip i's frames start at chunk-local base
+        const int buf = chunk_idx & 1;
         work.clear();
         frame_clip.clear();
         int64_t base = 0;
@@ -930,6 +956,8 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
             const int64_t nfc = std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0));
             // chunk-local frame slot of clip frame f is  base + (f - c0)  ==  (frame_base' + f) - chunk_frame0 with frame_base' = base - c0, chunk_frame0 = 0
             cclips[i].frame_base = base - c0;
+            // staged PCM: sample t of the clip sits at  region * i + t - (c0 * 1152 - 1056)  of this chunk's staging buffer
+            if (host) cclips[i].pcm_base = 2 * ((int64_t)i * region - (c0 * 1152 - 1056));
             for (int64_t g = 2 * c0; g < 2 * (c0 + nfc); g += ENC_RUN) {
                 M3sEncWork w;
                 w.clip = i; w.g_first = (int32_t)g; w.count = (int32_t)std::min<int64_t>(ENC_RUN, 2 * (c0 + nfc) - g); w.pad = 0;
@@ -944,11 +972,23 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         M3S_CUDA(h, cudaMemcpyAsync(h->e_work.p, work.data(), sizeof(M3sEncWork) * work.size(), cudaMemcpyHostToDevice, h->stream));
         M3S_CUDA(h, cudaMemcpyAsync(h->e_misc.p, frame_clip.data(), sizeof(int32_t) * frame_clip.size(), cudaMemcpyHostToDevice, h->stream));
         M3S_CUDA(h, cudaMemcpyAsync(h->e_clips.p, cclips.data(), sizeof(M3sEncClip) * n_clips, cudaMemcpyHostToDevice, h->stream));
+        // next chunk's PCM rides under this chunk's kernels; queued AFTER the descriptor copies above so that they (and the
+        // kernels behind them) do not wait for it in the copy engine
+        if (host && c0 + cf < max_frames) M3S_CUDA(h, stage_chunk(c0 + cf, buf ^ 1));
+        const int16_t *k_pcm = d_pcm;
+        if (host) {
+            k_pcm = (const int16_t *)((const char *)h->e_pcm.p + (size_t)buf * stage_bytes);
+            M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[buf], 0));
+        }
         M3S_KBEGIN(h, M3S_K_ENC_ANALYSIS);
         k_enc_analysis<<<(unsigned)work.size(), ANA_THREADS, 0, h->stream>>>(
-            d_pcm, (const M3sEncClip *)h->e_clips.p, (const M3sEncWork *)h->e_work.p, h->d_tab, (const EncTables *)h->e_tabs.p, sri, 0,
+            k_pcm, (const M3sEncClip *)h->e_clips.p, (const M3sEncWork *)h->e_work.p, h->d_tab, (const EncTables *)h->e_tabs.p, sri, 0,
             (int32_t *)h->e_mdct.p, (M3sEncStats *)h->e_gran.p);
         M3S_LAUNCH_CHECK(h);
+        if (host) {
+            M3S_CUDA(h, cudaEventRecord(h->ev_free[buf], h->stream));   // the staging buffer may be refilled once the analysis has read it
+            free_recorded[buf] = true;
+        }
         M3S_KBEGIN(h, M3S_K_ENC_RATE);
         k_enc_rate<<<(unsigned)n_clips, 32, sizeof(RateSmem), h->stream>>>(
             (const M3sEncClip *)h->e_clips.p, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p,
@@ -961,14 +1001,32 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
             (const M3sEncClip *)h->e_clips.p, (const int32_t *)h->e_misc.p, h->d_tab, (const uint32_t *)h->e_pad.p, sri, bri, whole, 0,
             chunk_total, (const uint32_t *)h->e_ix.p, (const int32_t *)h->e_info.p, (const uint8_t *)h->e_scfsi.p, d_out);
         M3S_LAUNCH_CHECK(h);
+        if (host) {
+            // this chunk's bytes of every clip go home behind the pack kernel, under the next chunk's kernels
+            M3S_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
+            M3S_CUDA(h, cudaStreamWaitEvent(h->copy_out, h->ev_done, 0));
+            rows.clear();
+            for (int i = 0; i < n_clips; i++) {
+                const int64_t nfc = std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0));
+                if (nfc == 0) continue;
+                const int64_t b0 = byteoff[c0], b1 = std::min<int64_t>(byteoff[c0 + nfc], clips[i].out_len);
+                if (b1 <= b0) continue;
+                M3sRow r;
+                r.dst = (char *)mp3_out + clips[i].out_base + b0;
+                r.src = (const char *)d_out + clips[i].out_base + b0;
+                r.bytes = (size_t)(b1 - b0);
+                rows.push_back(r);
+            }
+            M3S_CUDA(h, m3s_copy_rows(rows, cudaMemcpyDeviceToHost, h->copy_out));
+        }
         // the host vectors above are reused by the next chunk: their copies must have been consumed
         M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     }
     // ---- results
     std::vector<M3sEncState> states(n_clips);
     M3S_CUDA(h, cudaMemcpyAsync(states.data(), h->e_state.p, sizeof(M3sEncState) * n_clips, cudaMemcpyDeviceToHost, h->stream));
-    if (mem == M3S_MEM_HOST) M3S_CUDA(h, cudaMemcpyAsync(mp3_out, d_out, (size_t)out_total, cudaMemcpyDeviceToHost, h->stream));
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (host) M3S_CUDA(h, cudaStreamSynchronize(h->copy_out));
     if (hide_str_offset_out)
         for (int i = 0; i < n_clips; i++) hide_str_offset_out[i] = states[i].hide_off;
     h->enc_taps_ok = single_chunk;

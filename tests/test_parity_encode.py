@@ -143,6 +143,30 @@ def test_chunked_equals_single(built, oracle):
     h.close()
 
 
+def test_chunked_regular_batch_host_and_device(built, oracle):
+    """Equal-length clips take the strided (2-D) PCIe staging path of the host pipeline; host and device buffers and the
+    oracle must agree byte for byte across chunk boundaries."""
+    import torch
+    from mp3stego_b200 import _lib
+    os.environ["M3S_ENC_CHUNK_FRAMES"] = "28"     # 4 clips x 7 frames per chunk -> 4 chunks, the last one ragged
+    try:
+        h = _lib.Handle(0)
+    finally:
+        del os.environ["M3S_ENC_CHUNK_FRAMES"]
+    clips = [synth_wav(40 + k, 23) for k in range(4)]
+    bits = ["0110" * 300, "", "1" * 50, "10" * 400]
+    got = _encode(h, clips, 128, payloads=bits, taps=False)
+    pcm = np.concatenate([c.reshape(-1) for c in clips]).astype(np.int16)
+    res = h.encode(torch.from_numpy(pcm).cuda(), [c.shape[0] for c in clips], 44100, 128, payloads=bits)
+    dev_mp3 = res["mp3"].cpu().numpy()
+    for i, (c, p, g) in enumerate(zip(clips, bits, got)):
+        ref = oracle.encode(c, 44100, 128, p, taps=False)
+        assert g["mp3"] == ref["mp3"] and g["hide_str_offset"] == ref["hide_str_offset"]
+        o = int(res["mp3_off"][i])
+        assert bytes(dev_mp3[o:o + int(res["out_len"][i])]) == ref["mp3"]
+    h.close()
+
+
 def test_hide_reveal_roundtrip_at_scale(handle, oracle):
     """Size-independent property at BASELINE configs[2] scale (3-minute clips): what encode hides, decode reveals."""
     rng = np.random.default_rng(1)

@@ -1,0 +1,90 @@
+"""CPU: the N>1 host logic (file partition, off-path gather, max-over-ranks step time) on a world_size-2 gloo group.
+The codec work of each rank is done by the oracle here (no GPU in this suite); on the GPU box the same functions run
+under nccl around the C-ABI calls (bench.py, shard.decode_reveal_sharded)."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "mp3-steganography-lib_b200")
+
+
+def test_partition_is_exact_cover_and_balanced():
+    sys.path.insert(0, PKG)
+    from mp3stego_b200 import shard
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(1_000, 9_000_000, size=1000)
+    for world in (1, 2, 3, 8):
+        parts = shard.partition_files(sizes, world)
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(len(sizes)))
+        loads = [int(sizes[p].sum()) for p in parts]
+        assert max(loads) - min(loads) <= int(sizes.max())        # greedy longest-first bound
+    assert shard.partition_files([], 2) == [[], []]
+    assert shard.partition_files([5, 5, 5], 2) == [[0, 2], [1]]   # ties go to the lowest rank: every rank agrees
+
+
+def test_frame_ranges_cover_and_warm_up():
+    sys.path.insert(0, PKG)
+    from mp3stego_b200 import shard
+    for n, parts in ((6890, 8), (5, 8), (1, 1), (0, 4), (1148, 3)):
+        r = shard.frame_ranges(n, parts)
+        assert sum(x["count"] for x in r) == n
+        pos = 0
+        for x in r:
+            assert x["first"] == pos and x["warm"] == (1 if pos > 0 else 0)
+            pos += x["count"]
+
+
+def _worker(rank, world, port, blobs, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, PKG)
+    import torch.distributed as dist
+    from mp3stego_b200 import shard
+    from oracle import oracle as O
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = shard.partition_files([len(b) for b in blobs], world)[rank]
+        local = {}
+        for k in mine:
+            r = O.decode(blobs[k], 0, taps=False)
+            local[k] = (int(r["n_frames"]), r["bits"], int(np.asarray(r["pcm16"], np.int64).sum()))
+        merged = shard.gather_results(local)
+        t = shard.max_over_ranks(1.0 + rank)
+        q.put((rank, mine, merged, t))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_decode_reveal_world2_gloo():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    O.build()
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.mp3")))
+    assert len(files) >= 4
+    blobs = [open(f, "rb").read() for f in files]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, blobs, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shards = {r: mine for r, mine, _, _ in got}
+    assert sorted(shards[0] + shards[1]) == list(range(len(blobs))) and shards[0] and shards[1]
+    single = {}
+    for k, b in enumerate(blobs):
+        r = O.decode(b, 0, taps=False)
+        single[k] = (int(r["n_frames"]), r["bits"], int(np.asarray(r["pcm16"], np.int64).sum()))
+    for _, _, merged, t in got:
+        assert merged == single               # every rank sees the whole job's results, identical to one process
+        assert t == pytest.approx(2.0)        # max over ranks of (1.0, 2.0)
