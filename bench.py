@@ -329,14 +329,25 @@ def run_product_arm(args):
     # thread per handle (handles are independent: own stream, own workspaces, own pinned PCM buffer); the waves are dealt
     # round-robin, so wave k's PCM goes home while wave k+1 is in the kernels and wave k+2's MP3 bytes come up.
     import threading
-    n_workers = max(1, min(args.e2e_workers, len(e2e_waves)))
-    workers = [dict(h=h, pcm=pcm_out_host, ids=ids_host, bits=bits_host)]
-    for _ in range(1, n_workers):
-        workers.append(dict(h=_lib.Handle(local), pcm=torch.empty(max_e2e_frames * 1152 * 2 + 64, dtype=torch.int16, pin_memory=True),
-                            ids=torch.empty(max_e2e_frames * 12, dtype=torch.uint8, pin_memory=True),
-                            bits=torch.empty(max_e2e_frames * 12, dtype=torch.uint8, pin_memory=True)))
+    state = dict(waves=e2e_waves, n=max(1, min(args.e2e_workers, len(e2e_waves))), trace=None)
+    workers = []
+
+    def ensure_workers(n, frames):
+        for wk in workers:
+            if wk["pcm"].numel() < frames * 1152 * 2 + 64:
+                wk["pcm"] = torch.empty(frames * 1152 * 2 + 64, dtype=torch.int16, pin_memory=True)
+                wk["ids"] = torch.empty(frames * 12, dtype=torch.uint8, pin_memory=True)
+                wk["bits"] = torch.empty(frames * 12, dtype=torch.uint8, pin_memory=True)
+        while len(workers) < n:
+            workers.append(dict(h=h if not workers else _lib.Handle(local),
+                                pcm=torch.empty(frames * 1152 * 2 + 64, dtype=torch.int16, pin_memory=True),
+                                ids=torch.empty(frames * 12, dtype=torch.uint8, pin_memory=True),
+                                bits=torch.empty(frames * 12, dtype=torch.uint8, pin_memory=True)))
+
+    ensure_workers(state["n"], max_e2e_frames)
 
     def dec_host():
+        n_workers, wv = state["n"], state["waves"]
         counts = [0] * n_workers
         errs = []
 
@@ -344,10 +355,16 @@ def run_product_arm(args):
             try:
                 torch.cuda.set_device(local)
                 wk = workers[k]
-                for w in e2e_waves[k::n_workers]:
+                for w in wv[k::n_workers]:
+                    t0 = time.perf_counter()
                     sc = wk["h"].decode_scan(w["mp3_host"], w["off"])
+                    t1 = time.perf_counter()
                     wk["h"].decode_reveal_into(wk["ids"], wk["bits"])
+                    t2 = time.perf_counter()
                     wk["h"].decode_run(pcm=wk["pcm"])
+                    t3 = time.perf_counter()
+                    if state["trace"] is not None:
+                        state["trace"].append((k, t0, t1, t2, t3))
                     counts[k] += int(sc["n_frames"].sum())
             except Exception as e:   # surfaced below: a failed worker must fail the bench
                 errs.append(e)
@@ -361,6 +378,27 @@ def run_product_arm(args):
         if errs:
             raise errs[0]
         return sum(counts)
+
+    if args.e2e_sweep:    # diagnostic: e2e decode throughput over worker counts and wave sizes, with a per-call trace
+        for wf in (25, 50, 125):
+            state["waves"] = make_waves(wf)
+            for nwk in (1, 2, 3, 4, 6):
+                state["n"] = nwk
+                ensure_workers(nwk, max(w["frames"] for w in state["waves"]))
+                dec_host()
+                state["trace"] = []
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n = dec_host()
+                dt = time.perf_counter() - t0
+                tr = state["trace"]
+                state["trace"] = None
+                sc = np.mean([b - a for _, a, b, _, _ in tr]) * 1e3
+                rv = np.mean([c - b for _, _, b, c, _ in tr]) * 1e3
+                rn = np.mean([d - c for _, _, _, c, d in tr]) * 1e3
+                log(f"[sweep] wave {wf:4d} files, {nwk} workers: {dt * 1e3:7.1f} ms/step = {n / dt / 1e6:6.2f} M frames/s; "
+                    f"mean call ms: scan {sc:6.1f} reveal {rv:6.1f} run {rn:6.1f}")
+        return
 
     # encode+hide: ONE call over all clips -- the rate loop runs one warp per clip, so the whole corpus goes in together
     # (the library walks it in frame windows to bound its intermediates)
@@ -485,6 +523,7 @@ def main():
     ap.add_argument("--wave", type=int, default=250, help="files per wave of the device-resident decode leg (bounds the workspaces)")
     ap.add_argument("--e2e-wave", type=int, default=50, help="files per wave of the host-buffer (e2e) decode leg")
     ap.add_argument("--no-encode", action="store_true", help="skip the encode+hide half")
+    ap.add_argument("--e2e-sweep", action="store_true", help="diagnostic sweep of the decode e2e leg (no JSON line)")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host worker threads (one handle each) of the decode e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -158,6 +158,7 @@ struct m3s_ctx {
     // copy streams + events of the host-buffer pipelines (created on first use): PCIe transfers of chunk k+1 / k-1 overlap the kernels of chunk k
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done = nullptr;
+    cudaEvent_t ev_pace[3] = {nullptr, nullptr, nullptr};   // m3s_copy_paced
     std::string err;
     int64_t launches = 0;
     // ---- optional per-kernel device timing (m3s_timing_enable): cudaEvent pairs on the launching stream
@@ -197,6 +198,9 @@ int m3s_buf_reserve(m3s_ctx *h, M3sBuf &b, size_t bytes);
 int m3s_pipeline_init(m3s_ctx *h);   // creates copy_in / copy_out and their events
 // a batch of (dst, src, bytes) row copies on one stream: one cudaMemcpy2DAsync when the rows are equally long and equally spaced
 struct M3sRow { char *dst; const char *src; size_t bytes; };
+// blocking-call flavour: at most two pieces are queued at a time, so copies of OTHER handles (whose host threads wait on them)
+// interleave within a millisecond instead of queueing behind the whole transfer -- copy engines serve commands in submission order
+int m3s_copy_paced(m3s_ctx *h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind);
 cudaError_t m3s_copy_bulk(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s);   // in bounded pieces
 cudaError_t m3s_copy_rows(const std::vector<M3sRow> &rows, cudaMemcpyKind kind, cudaStream_t s);
 int m3s_upload_cos36(const float *f, const double *d);  // m3s_decode.cu: constant-memory IMDCT rows of the current device

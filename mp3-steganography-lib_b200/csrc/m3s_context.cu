@@ -312,7 +312,7 @@ int m3s_pipeline_init(m3s_ctx *h)
 // Bulk PCIe transfers are issued in pieces of at most M3S_COPY_PIECE bytes: a copy engine serves one command at a time,
 // so a multi-GB command would hold back every small descriptor copy (and the host thread waiting on it) of this and of
 // other handles for tens of milliseconds; with bounded pieces those slot in within about a millisecond.
-#define M3S_COPY_PIECE ((size_t)32 << 20)
+#define M3S_COPY_PIECE ((size_t)16 << 20)
 
 cudaError_t m3s_copy_bulk(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s)
 {
@@ -322,6 +322,20 @@ cudaError_t m3s_copy_bulk(void *dst, const void *src, size_t bytes, cudaMemcpyKi
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+int m3s_copy_paced(m3s_ctx *h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind)
+{
+    for (int i = 0; i < 3; i++)
+        if (!h->ev_pace[i]) M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_pace[i], cudaEventDisableTiming));
+    int i = 0;
+    for (size_t o = 0; o < bytes; o += M3S_COPY_PIECE, i++) {
+        const size_t n = bytes - o < M3S_COPY_PIECE ? bytes - o : M3S_COPY_PIECE;
+        if (i >= 2) M3S_CUDA(h, cudaEventSynchronize(h->ev_pace[(i - 2) % 3]));
+        M3S_CUDA(h, cudaMemcpyAsync((char *)dst + o, (const char *)src + o, n, kind, h->stream));
+        M3S_CUDA(h, cudaEventRecord(h->ev_pace[i % 3], h->stream));
+    }
+    return M3S_OK;
 }
 
 cudaError_t m3s_copy_rows(const std::vector<M3sRow> &rows, cudaMemcpyKind kind, cudaStream_t s)
@@ -384,6 +398,8 @@ extern "C" int m3s_destroy(m3s_handle_t h)
         if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
     }
     if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (int i = 0; i < 3; i++)
+        if (h->ev_pace[i]) cudaEventDestroy(h->ev_pace[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return M3S_OK;

@@ -1061,7 +1061,7 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     if (mem == M3S_MEM_HOST) {
         int rc = m3s_buf_reserve(h, h->b_stage_in, (size_t)total_bytes + 16);
         if (rc) return rc;
-        M3S_CUDA(h, m3s_copy_bulk(h->b_stage_in.p, bytes, (size_t)total_bytes, cudaMemcpyHostToDevice, h->stream));
+        if ((rc = m3s_copy_paced(h, h->b_stage_in.p, bytes, (size_t)total_bytes, cudaMemcpyHostToDevice))) return rc;
         h->d_bytes = (const uint8_t *)h->b_stage_in.p;
     } else
         h->d_bytes = bytes;
@@ -1257,7 +1257,7 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
     }
     M3S_LAUNCH_CHECK(h);
     if (mem == M3S_MEM_HOST)
-        M3S_CUDA(h, m3s_copy_bulk(pcm, d_pcm, (size_t)total_elems * esz, cudaMemcpyDeviceToHost, h->stream));
+        if ((rc = m3s_copy_paced(h, pcm, d_pcm, (size_t)total_elems * esz, cudaMemcpyDeviceToHost))) return rc;
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     return M3S_OK;
 }

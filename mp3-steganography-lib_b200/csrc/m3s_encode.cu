@@ -71,168 +71,207 @@ __device__ __forceinline__ int32_t mulsr32(int32_t a, int32_t b)  // util.mulsr 
 }
 
 // ================================================================================================
-// E1: analysis filterbank + MDCT
+// E1: analysis filterbank + MDCT.  Every product is the reference's mul(a, b) = (a * b) >> 32 truncated on its own
+// (util.py:121-127), so no algebraic folding is exact and the work is 66,816 IMAD.HI per granule-channel; IMAD.HI issues
+// at a quarter of the FP32 rate (tools/ubench_pipes.cu: 29 lanes/clk/SM), which is this kernel's roof.  The design keeps
+// everything else off that pipe's critical path by register tiling: both channels advance together (half the barriers),
+//   windowing   thread (ch, slot parity, i): 16 samples in registers feed 9 slots x 8 taps               (0.22 LDS / mul)
+//   matrixing   thread (ch, slot half, band, row half): 32 matrix coefficients live in registers for the
+//               whole kernel, the windowed vector arrives as broadcast 128-bit loads                      (0.25 LDS / mul)
+//   MDCT        thread (ch, band, k range): cos_l is an immediate constant-bank operand of the IMAD.HI   (0.22 LDS / mul)
 // ================================================================================================
-#define ANA_THREADS 288
+#define ANA_THREADS 256
+
+__constant__ int32_t c_enc_cos[18][36];   // MP3Encoder.__cos_l (:557-566), window folded in
+
+struct AnaSmem {
+    int32_t x[2][2][1056];      // [buffer][ch]: 480 samples of history + 576 new, as int16 << 16 (double buffered: no shift barrier)
+    __align__(16) int32_t y[2][18][64];   // [ch][slot][i] windowed vectors
+    int32_t sb[2][2][18][32];   // [ch][ping-pong][slot][band] subband samples
+    int32_t mf[2][576];         // [ch][band * 18 + k] MDCT lines
+    uint32_t bins[2][24];       // per channel: 0..20 band energies, 21 total, 22 xrmax
+    uint8_t sfb[576];
+    int32_t ca[8], cs[8];
+};
+
+// MDCT of band `lane` for outputs K0 .. K0 + NK - 1: X[k] = sum_j mul(in[j], cos_l[k][j]), in = 18 previous + 18 current
+// subband samples (:683-701)
+template <int K0, int NK>
+__device__ __forceinline__ void mdct_band(const int32_t *__restrict__ prev, const int32_t *__restrict__ cur, int lane,
+                                          int32_t *__restrict__ mf)
+{
+    uint32_t acc[NK];
+#pragma unroll
+    for (int q = 0; q < NK; q++) acc[q] = 0u;
+#pragma unroll
+    for (int j = 0; j < 18; j++) {
+        const int32_t v = prev[j * 32 + lane];
+#pragma unroll
+        for (int q = 0; q < NK; q++) acc[q] += (uint32_t)__mulhi(v, c_enc_cos[K0 + q][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 18; j++) {
+        const int32_t v = cur[j * 32 + lane];
+#pragma unroll
+        for (int q = 0; q < NK; q++) acc[q] += (uint32_t)__mulhi(v, c_enc_cos[K0 + q][18 + j]);
+    }
+#pragma unroll
+    for (int q = 0; q < NK; q++) mf[lane * 18 + K0 + q] = (int32_t)acc[q];
+}
 
 __global__ void __launch_bounds__(ANA_THREADS, 2)
 k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ clips, const M3sEncWork *__restrict__ work,
                const M3sDevTables *__restrict__ T, const EncTables *__restrict__ ET, int sr_idx, int64_t chunk_frame0,
                int32_t *__restrict__ mdct, M3sEncStats *__restrict__ stats)
 {
-    __shared__ int32_t s_x[2][1056];        // per channel: 480 samples of history + 576 new, as int16 << 16
-    __shared__ int32_t s_win[512];
-    __shared__ __align__(16) int32_t s_tmp[18][64];
-    __shared__ int32_t s_sb[2][2][18][32];  // [ch][ping-pong][slot][band]
-    __shared__ int32_t s_cos[18][36];
-    __shared__ int32_t s_mf[576];
-    __shared__ uint32_t s_bins[24];         // 0..20 band energies, 21 total, 22 xrmax
-    __shared__ uint8_t s_sfb[576];
-    __shared__ int32_t s_ca[8], s_cs[8];
-
+    __shared__ AnaSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const M3sEncWork wk = work[blockIdx.x];
     const M3sEncClip cl = clips[wk.clip];
-    for (int i = tid; i < 512; i += ANA_THREADS) s_win[i] = T->enwindow[i];
-    for (int i = tid; i < 18 * 36; i += ANA_THREADS) (&s_cos[0][0])[i] = (&T->enc_cosl[0][0])[i];
-    for (int i = tid; i < 576; i += ANA_THREADS) s_sfb[i] = T->long_sfb_of[sr_idx][i];
-    if (tid < 8) { s_ca[tid] = T->enc_ca[tid]; s_cs[tid] = T->enc_cs[tid]; }
-    for (int i = tid; i < 2 * 2 * 18 * 32; i += ANA_THREADS) (&s_sb[0][0][0][0])[i] = 0;
-    int32_t fl[64];  // row `lane` of the polyphase matrix
+    for (int i = tid; i < 576; i += ANA_THREADS) S.sfb[i] = T->long_sfb_of[sr_idx][i];
+    if (tid < 8) { S.ca[tid] = T->enc_ca[tid]; S.cs[tid] = T->enc_cs[tid]; }
+    for (int i = tid; i < 2 * 2 * 18 * 32; i += ANA_THREADS) (&S.sb[0][0][0][0])[i] = 0;
+    // ---- per-thread roles and their register-resident coefficients
+    const int wch = tid >> 7, wpar = (tid >> 6) & 1, wi = tid & 63;                  // windowing: channel, slot parity, output i
+    int32_t wcoef[8];
 #pragma unroll
-    for (int j = 0; j < 64; j++) fl[j] = T->enc_fl[lane][j];
+    for (int k = 0; k < 8; k++) wcoef[k] = T->enwindow[wi + 64 * k];
+    const int mch = tid >> 7, mhalf = (tid >> 6) & 1, mb = (tid & 63) >> 1, mh = tid & 1;   // matrixing: channel, slots 9*mhalf.., band, row half
+    int32_t fl[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) fl[j] = T->enc_fl[mb][32 * mh + j];
+    const int dch = warp >> 2, dkq = warp & 3;                                       // MDCT: channel, k range; band = lane
     __syncthreads();
 
     const uint32_t *pcm32 = (const uint32_t *)(pcm + cl.pcm_base);  // one stereo sample per word (pcm_base is even)
     const int g_begin = wk.g_first > 0 ? wk.g_first - 1 : 0;
     const int g_end = wk.g_first + wk.count;
-    int pp = 0;
-    for (int G = g_begin; G < g_end; G++) {
-        // ---- PCM window: samples [576 G - 480, 576 G + 576) of both channels
+    int pp = 0, xb = 0;
+    for (int G = g_begin; G < g_end; G++, pp ^= 1, xb ^= 1) {
+        // ---- PCM window: samples [576 G - 480, 576 G + 576) of both channels; the history comes from the other buffer
         const int64_t t0 = (int64_t)G * 576 - 480;
         if (G == g_begin) {
             for (int i = tid; i < 1056; i += ANA_THREADS) {
                 const int64_t t = t0 + i;
                 const uint32_t w = t >= 0 ? __ldg(pcm32 + t) : 0u;
-                s_x[0][i] = (int32_t)(w << 16);
-                s_x[1][i] = (int32_t)(w & 0xFFFF0000u);
+                S.x[xb][0][i] = (int32_t)(w << 16);
+                S.x[xb][1][i] = (int32_t)(w & 0xFFFF0000u);
             }
         } else {
-            int32_t keep0[2], keep1[2];
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int i = tid + q * ANA_THREADS;
-                if (i < 480) { keep0[q] = s_x[0][576 + i]; keep1[q] = s_x[1][576 + i]; }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int i = tid + q * ANA_THREADS;
-                if (i < 480) { s_x[0][i] = keep0[q]; s_x[1][i] = keep1[q]; }
+            for (int i = tid; i < 480; i += ANA_THREADS) {
+                S.x[xb][0][i] = S.x[xb ^ 1][0][576 + i];
+                S.x[xb][1][i] = S.x[xb ^ 1][1][576 + i];
             }
             for (int i = tid; i < 576; i += ANA_THREADS) {
                 const uint32_t w = __ldg(pcm32 + t0 + 480 + i);
-                s_x[0][480 + i] = (int32_t)(w << 16);
-                s_x[1][480 + i] = (int32_t)(w & 0xFFFF0000u);
+                S.x[xb][0][480 + i] = (int32_t)(w << 16);
+                S.x[xb][1][480 + i] = (int32_t)(w & 0xFFFF0000u);
             }
         }
         __syncthreads();
-        const bool emit = G >= wk.g_first;
-        for (int ch = 1; ch >= 0; ch--) {  // the reference walks ch = nch-1 .. 0 (:661); the channels are independent
-            // ---- windowing: y_i = sum_k mul(x[t = 32 s + 31 - i - 64 k], enwindow[i + 64 k])   (:337-356)
-            for (int o = tid; o < 18 * 64; o += ANA_THREADS) {
-                const int s = o >> 6, i = o & 63;
-                const int32_t *xp = &s_x[ch][480 + 32 * s + 31 - i];
+        // ---- windowing: y_s[i] = sum_k mul(x[32 s + 31 - i - 64 k], enwindow[i + 64 k])   (:337-356).  Slots s = p + 2 q of one
+        //      parity share their samples: x index = base + 64 (q - k), 16 distinct values for 9 slots x 8 taps
+        {
+            const int32_t *xp = &S.x[xb][wch][480 + 32 * wpar + 31 - wi];
+            int32_t xv[16];
+#pragma unroll
+            for (int d = 0; d < 16; d++) xv[d] = xp[64 * (d - 7)];
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
                 uint32_t acc = 0;
 #pragma unroll
-                for (int k = 0; k < 8; k++) acc += (uint32_t)__mulhi(xp[-64 * k], s_win[i + 64 * k]);
-                s_tmp[s][i] = (int32_t)acc;
+                for (int k = 0; k < 8; k += 2)
+                    acc += (uint32_t)__mulhi(xv[q - k + 7], wcoef[k]) + (uint32_t)__mulhi(xv[q - k + 6], wcoef[k + 1]);
+                S.y[wch][wpar + 2 * q][wi] = (int32_t)acc;
             }
-            __syncthreads();
-            // ---- matrixing: s_b = sum_j mul(fl[b][j], y_j); odd bands of odd slots negated   (:358-368, :678-679)
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int s = 2 * warp + q;
-                const int4 *y4 = (const int4 *)s_tmp[s];
-                uint32_t acc = 0;
-#pragma unroll
-                for (int j4 = 0; j4 < 16; j4++) {
-                    const int4 y = y4[j4];
-                    acc += (uint32_t)__mulhi(fl[4 * j4 + 0], y.x);
-                    acc += (uint32_t)__mulhi(fl[4 * j4 + 1], y.y);
-                    acc += (uint32_t)__mulhi(fl[4 * j4 + 2], y.z);
-                    acc += (uint32_t)__mulhi(fl[4 * j4 + 3], y.w);
-                }
-                if ((s & 1) && (lane & 1)) acc = 0u - acc;
-                s_sb[ch][pp][s][lane] = (int32_t)acc;
-            }
-            __syncthreads();
-            if (emit) {
-                // ---- MDCT: X[b][k] = sum_j mul(in[j], cos_l[k][j]), in = 18 previous + 18 current subband samples   (:683-701)
-                if (tid < 24) s_bins[tid] = 0u;
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int k = 2 * warp + q;
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int j = 0; j < 18; j++) acc += (uint32_t)__mulhi(s_sb[ch][pp ^ 1][j][lane], s_cos[k][j]);
-#pragma unroll
-                    for (int j = 0; j < 18; j++) acc += (uint32_t)__mulhi(s_sb[ch][pp][j][lane], s_cos[k][18 + j]);
-                    s_mf[lane * 18 + k] = (int32_t)acc;
-                }
-                __syncthreads();
-                // ---- alias butterflies between neighbouring bands, cmuls with >> 31   (:704-744, util.py:145-155)
-                if (tid < 248) {
-                    const int band = 1 + (tid >> 3), k = tid & 7;
-                    const int64_t are = s_mf[band * 18 + k], aim = s_mf[(band - 1) * 18 + 17 - k];
-                    const int64_t bre = s_cs[k], bim = s_ca[k];
-                    s_mf[band * 18 + k] = (int32_t)((are * bre - aim * bim) >> 31);
-                    s_mf[(band - 1) * 18 + 17 - k] = (int32_t)((are * bim + aim * bre) >> 31);
-                }
-                __syncthreads();
-                // ---- store + statistics: xrmax, en_tot, en[sfb]   (:772-776, :836-857)
-                const int frame = G >> 1, gr = G & 1;
-                const int64_t gslot = (((int64_t)(cl.frame_base + frame) - chunk_frame0) * 2 + ch) * 2 + gr;
-                int32_t *dst = mdct + gslot * 576;
-                uint32_t tot = 0, mx = 0;
-                for (int i = tid; i < 576; i += ANA_THREADS) {
-                    const int32_t v = s_mf[i];
-                    dst[i] = v;
-                    const uint32_t e = (uint32_t)(mulsr32(v, v) >> 10);
-                    const int sfb = s_sfb[i];
-                    if (sfb < 21) atomicAdd(&s_bins[sfb], e);
-                    tot += e;
-                    const uint32_t a = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
-                    mx = a > mx ? a : mx;
-                }
-                tot = __reduce_add_sync(0xFFFFFFFFu, tot);
-                mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-                if (lane == 0) { atomicAdd(&s_bins[21], tot); atomicMax(&s_bins[22], mx); }
-                __syncthreads();
-                if (tid < 22) {
-                    const uint32_t temp = s_bins[tid];
-                    int en = 0;
-                    if (temp) {
-                        en = -21;
-                        for (int j = 0; j < 31; j++) en += ET->en_thresh[j] <= temp;
-                    }
-                    M3sEncStats *st = stats + gslot;
-                    if (tid == 21) { st->en_tot = (int8_t)en; st->xrmax = (int32_t)s_bins[22]; }
-                    else st->en[tid] = (int8_t)en;
-                }
-            }
-            __syncthreads();
         }
-        pp ^= 1;
+        __syncthreads();
+        // ---- matrixing: s_b = sum_j mul(fl[b][j], y_j); odd bands of odd slots negated   (:358-368, :678-679)
+#pragma unroll 1
+        for (int q = 0; q < 9; q++) {
+            const int s = 9 * mhalf + q;
+            const int4 *y4 = (const int4 *)&S.y[mch][s][32 * mh];
+            uint32_t acc = 0;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int4 yv = y4[m];
+                acc += (uint32_t)__mulhi(fl[4 * m + 0], yv.x) + (uint32_t)__mulhi(fl[4 * m + 1], yv.y);
+                acc += (uint32_t)__mulhi(fl[4 * m + 2], yv.z) + (uint32_t)__mulhi(fl[4 * m + 3], yv.w);
+            }
+            acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+            if (mh == 0) {
+                if ((s & 1) && (mb & 1)) acc = 0u - acc;
+                S.sb[mch][pp][s][mb] = (int32_t)acc;
+            }
+        }
+        __syncthreads();
+        if (G < wk.g_first) continue;   // warm-up granule: only its subband samples are needed (block-uniform)
+        // ---- MDCT   (:683-701)
+        {
+            const int32_t *prev = &S.sb[dch][pp ^ 1][0][0], *cur = &S.sb[dch][pp][0][0];
+            int32_t *mf = S.mf[dch];
+            switch (dkq) {   // warp-uniform
+            case 0: mdct_band<0, 5>(prev, cur, lane, mf); break;
+            case 1: mdct_band<5, 5>(prev, cur, lane, mf); break;
+            case 2: mdct_band<10, 4>(prev, cur, lane, mf); break;
+            default: mdct_band<14, 4>(prev, cur, lane, mf); break;
+            }
+            if (tid < 48) (&S.bins[0][0])[tid] = 0u;
+        }
+        __syncthreads();
+        // ---- alias butterflies between neighbouring bands, cmuls with >> 31   (:704-744, util.py:145-155)
+        for (int a = tid; a < 2 * 248; a += ANA_THREADS) {
+            const int ch = a >= 248, r = a - 248 * ch;
+            const int band = 1 + (r >> 3), k = r & 7;
+            int32_t *mf = S.mf[ch];
+            const int64_t are = mf[band * 18 + k], aim = mf[(band - 1) * 18 + 17 - k];
+            const int64_t bre = S.cs[k], bim = S.ca[k];
+            mf[band * 18 + k] = (int32_t)((are * bre - aim * bim) >> 31);
+            mf[(band - 1) * 18 + 17 - k] = (int32_t)((are * bim + aim * bre) >> 31);
+        }
+        __syncthreads();
+        // ---- store + statistics: xrmax, en_tot, en[sfb]   (:772-776, :836-857)
+        const int frame = G >> 1, gr = G & 1;
+        const int64_t gslot0 = (((int64_t)(cl.frame_base + frame) - chunk_frame0) * 2) * 2 + gr;   // channel 0; channel 1 is + 2
+        for (int idx = tid; idx < 2 * 576; idx += ANA_THREADS) {   // a warp never straddles the channels (576 = 18 * 32)
+            const int ch = idx >= 576, i = idx - 576 * ch;
+            const int32_t v = S.mf[ch][i];
+            mdct[(gslot0 + 2 * ch) * 576 + i] = v;
+            const uint32_t e = (uint32_t)(mulsr32(v, v) >> 10);
+            const int sfb = S.sfb[i];
+            if (sfb < 21 && e) atomicAdd(&S.bins[ch][sfb], e);
+            const uint32_t a = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, e), mx = __reduce_max_sync(0xFFFFFFFFu, a);
+            if (lane == 0) { atomicAdd(&S.bins[ch][21], tot); atomicMax(&S.bins[ch][22], mx); }
+        }
+        __syncthreads();
+        if (tid < 44) {
+            const int ch = tid >= 22, b = tid - 22 * ch;
+            const uint32_t temp = S.bins[ch][b];
+            int en = 0;
+            if (temp) {
+                en = -21;
+                for (int j = 0; j < 31; j++) en += ET->en_thresh[j] <= temp;
+            }
+            M3sEncStats *st = stats + gslot0 + 2 * ch;
+            if (b == 21) { st->en_tot = (int8_t)en; st->xrmax = (int32_t)S.bins[ch][22]; }
+            else st->en[b] = (int8_t)en;
+        }
+        // no barrier: the next writers of bins (MDCT phase of the next granule) sit behind three barriers
     }
 }
 
 // ================================================================================================
 // E2: rate loop, one warp per clip
 // ================================================================================================
+#define RATE_WARPS 2       // warps per clip: warp w owns granule index gr = w of every frame (see k_enc_rate)
+
 struct RateSmem {
     uint16_t i2i[10000];
-    uint32_t hl4[256];
+    uint2 hlc[256];        // .x = hl4 (code lengths of books 13 | 15 << 8 | 16 << 16 | 24 << 24), .y = signs | escapes << 16 of the pair
+    int32_t slot[4][4];    // per (gr, ch) slot: address1..3 (stale when big_values == 0, A.E6), quantizerStepSize
+    int32_t cnt[2][2];     // [round parity][gr] payload bits the granule consumed
+    int32_t p23[2][4];     // [frame parity][slot] part2_3_length before resv_frame_end
     int32_t steptabi[128];
     double steptab[128];
     uint16_t sfb[24];
@@ -361,9 +400,9 @@ __device__ __forceinline__ int probe_bits(const RateSmem &S, const uint32_t (&qx
     for (int j = 0; j < 9; j++) {
         const int e = 2 * (32 * j + lane);
         const uint32_t x = qx[j], y = qy[j];
-        const uint32_t w = S.hl4[min(x, 15u) * 16 + min(y, 15u)];
-        const uint32_t wl = w & 0x00FF00FFu, wh = (w >> 8) & 0x00FF00FFu;
-        const uint32_t cn = (uint32_t)(x != 0) + (uint32_t)(y != 0) + (((uint32_t)(x > 14) + (uint32_t)(y > 14)) << 16);
+        const uint2 w2 = S.hlc[min(x, 15u) * 16 + min(y, 15u)];
+        const uint32_t wl = w2.x & 0x00FF00FFu, wh = (w2.x >> 8) & 0x00FF00FFu;
+        const uint32_t cn = w2.y;   // (x != 0) + (y != 0) + (((x > 14) + (y > 14)) << 16)
         const uint32_t mx = max(x, y);
         if (e < a1) { lo0 += wl; hi0 += wh; cn0 += cn; m0 = max(m0, mx); }
         else if (e < a2) { lo1 += wl; hi1 += wh; cn1 += cn; m1 = max(m1, mx); }
@@ -407,7 +446,24 @@ __device__ __forceinline__ void quantize_all(const RateSmem &S, const uint32_t (
     }
 }
 
-__global__ void __launch_bounds__(32)
+// payload bits a granule starting at payload offset `off` can consume: bits[off .. off + 2]   (:1154-1168)
+__device__ __forceinline__ void payload_bits_at(const uint8_t *__restrict__ payload, const M3sEncClip &cl, int64_t off, int lane,
+                                                int &hn, uint32_t &hb)
+{
+    const int64_t left = cl.payload_len - off;
+    hn = left > 3 ? 3 : (left < 0 ? 0 : (int)left);
+    const bool one = lane < hn && __ldg(payload + cl.payload_base + off + lane) == '1';
+    hb = __ballot_sync(0xFFFFFFFFu, one);
+}
+
+// One CTA of two warps per clip.  The reference visits a frame's granules as (ch0,gr0) (ch0,gr1) (ch1,gr0) (ch1,gr1) and
+// chains them through hide_str_offset (which payload bits a granule may consume) and through the per-slot stale
+// address1..3 / step.  Warp w owns granule index gr = w, so the slot state never leaves its warp; within a channel the
+// two granules run CONCURRENTLY: warp 0 with the exact offset, warp 1 speculating that granule 0 consumes three bits (one
+// per non-empty region; none if granule 0 is silent).  A granule depends on its offset only through the <= 3 bits it
+// reads, so after warp 0 publishes its count warp 1 keeps its result when the bits at the true offset equal the ones it
+// used and re-runs otherwise (the tone+noise corpus mispredicts 1-2 % of the granules, low tones up to 27 %).
+__global__ void __launch_bounds__(32 * RATE_WARPS, 7)
 k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ states, const M3sDevTables *__restrict__ T,
            const EncTables *__restrict__ ET, const uint32_t *__restrict__ byteoff, const uint8_t *__restrict__ payload,
            int sr_idx, int whole_slots, int32_t chunk_first, int32_t chunk_frames, int64_t chunk_frame0,
@@ -416,163 +472,196 @@ k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ state
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RateSmem &S = *reinterpret_cast<RateSmem *>(smem_raw);
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, gr = tid >> 5;
     const uint32_t FULL = 0xFFFFFFFFu;
-    for (int i = lane; i < 10000; i += 32) S.i2i[i] = (uint16_t)T->int2idx[i];
-    for (int i = lane; i < 256; i += 32) S.hl4[i] = ET->hl4[i];
-    for (int i = lane; i < 128; i += 32) { S.steptabi[i] = T->steptabi[i]; S.steptab[i] = T->steptab[i]; }
-    if (lane < 24) S.sfb[lane] = lane < 23 ? T->sfb_long[sr_idx][lane] : 576;
-    S.linmax[lane] = T->enc_linmax[lane];
-    S.linbits[lane] = T->enc_linbits[lane];
-    if (lane < 23) { S.subdv[lane][0] = T->subdv[lane][0]; S.subdv[lane][1] = T->subdv[lane][1]; }
-    S.pair[lane][0] = T->pair[lane][0];
-    S.pair[lane][1] = T->pair[lane][1];
-    if (lane < 16) { S.hlc1[0][lane] = ET->hlc1[0][lane]; S.hlc1[1][lane] = ET->hlc1[1][lane]; }
-    __syncwarp();
-
     const int c = blockIdx.x;
     const M3sEncClip cl = clips[c];
-    M3sEncState st = states[c];
+    for (int i = tid; i < 10000; i += 32 * RATE_WARPS) S.i2i[i] = (uint16_t)T->int2idx[i];
+    for (int i = tid; i < 256; i += 32 * RATE_WARPS) {
+        const uint32_t x = i >> 4, y = i & 15;
+        S.hlc[i] = make_uint2(ET->hl4[i], (uint32_t)(x != 0) + (uint32_t)(y != 0) + (((uint32_t)(x > 14) + (uint32_t)(y > 14)) << 16));
+    }
+    for (int i = tid; i < 128; i += 32 * RATE_WARPS) { S.steptabi[i] = T->steptabi[i]; S.steptab[i] = T->steptab[i]; }
+    if (tid < 24) S.sfb[tid] = tid < 23 ? T->sfb_long[sr_idx][tid] : 576;
+    if (tid < 32) {
+        S.linmax[tid] = T->enc_linmax[tid];
+        S.linbits[tid] = T->enc_linbits[tid];
+        S.pair[tid][0] = T->pair[tid][0];
+        S.pair[tid][1] = T->pair[tid][1];
+    }
+    if (tid < 23) { S.subdv[tid][0] = T->subdv[tid][0]; S.subdv[tid][1] = T->subdv[tid][1]; }
+    if (tid < 16) { S.hlc1[0][tid] = ET->hlc1[0][tid]; S.hlc1[1][tid] = ET->hlc1[1][tid]; }
+    if (tid < 4) {
+        const M3sEncState *sp = states + c;
+        S.slot[tid][0] = sp->a1[tid]; S.slot[tid][1] = sp->a2[tid]; S.slot[tid][2] = sp->a3[tid]; S.slot[tid][3] = sp->step[tid];
+    }
+    int64_t off = states[c].hide_off;   // MP3Encoder.hide_str_offset, tracked identically by both warps
+    __syncthreads();
+
     const bool hiding = cl.payload_len > 0;
     const int f_end = min(cl.n_frames, chunk_first + chunk_frames);
+    int round = 0;
     for (int f = chunk_first; f < f_end; f++) {
         const int padding = (int)(byteoff[f + 1] - byteoff[f]) - whole_slots;
         const int bits_per_frame = 8 * (whole_slots + padding);
         const int mean_bits = (bits_per_frame - 288) / 2;          // :634-636 (side info 8 * (4 + 32) bits)
         const int max_bits = min(mean_bits / 2, 4095);             // :894-912 with the reservoir never enabled (A.E7)
         const int64_t fl_ = cl.frame_base + f - chunk_frame0;      // frame slot in the chunk buffers
-        int p23[4];                                                // by slot = 2 * gr + ch
-        int32_t rec[4][ENC_INFO_FIELDS];
-        int resv = 0;
-        for (int ch = 0; ch < 2; ch++) {
-            for (int gr = 0; gr < 2; gr++) {
-                const int slot = 2 * gr + ch;
-                const int64_t gslot = (fl_ * 2 + ch) * 2 + gr;
-                const int2 *xr = (const int2 *)(mdct + gslot * 576);
-                uint32_t ax[9], ay[9], sg = 0;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ch++, round ^= 1) {
+            const int slot = 2 * gr + ch;
+            const int64_t gslot = (fl_ * 2 + ch) * 2 + gr;
+            const int2 *xr = (const int2 *)(mdct + gslot * 576);
+            uint32_t ax[9], ay[9], sg = 0;
+#pragma unroll
+            for (int j = 0; j < 9; j++) {
+                const int2 v = __ldg(xr + 32 * j + lane);
+                ax[j] = v.x < 0 ? (uint32_t)(-(int64_t)v.x) : (uint32_t)v.x;
+                ay[j] = v.y < 0 ? (uint32_t)(-(int64_t)v.y) : (uint32_t)v.y;
+                sg |= (uint32_t)(v.x < 0) << (2 * j) | (uint32_t)(v.y < 0) << (2 * j + 1);
+            }
+            const int32_t xrmax = stats[gslot].xrmax;
+            // granule 1 starts where granule 0 of the same channel ends: predicted as three bits past `off` (none when it is silent)
+            int64_t use_off = off;
+            if (gr == 1 && stats[gslot - 1].xrmax) use_off += 3;
+            GranInfo gi;
+            int a1 = 0, a2 = 0, a3 = 0, step = 0, part23 = 0, cnt = 0, hn = 0;
+            uint32_t hb = 0, qx[9], qy[9];
+            bool need = true;
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2; attempt++) {
+                if (need) {
+                    gi.bv = 0; gi.count1 = 0; gi.c1sel = 0; gi.r0 = 0; gi.r1 = 0; gi.ts0 = 0; gi.ts1 = 0; gi.ts2 = 0;
+                    a1 = S.slot[slot][0]; a2 = S.slot[slot][1]; a3 = S.slot[slot][2]; step = S.slot[slot][3];
+                    part23 = 0; cnt = 0;
+                    if (xrmax) {
+                        if (hiding) payload_bits_at(payload, cl, use_off, lane, hn, hb);
+                        // ---- bin_search_step_size (:958-996) then inner_loop (:1064-1095), as one loop with a single probe site
+                        int next = -120, count = 120, half = 0, bits = 0;
+                        bool in_bin = true;
+                        for (;;) {
+                            int s;
+                            bool ovf = false;
+                            if (in_bin) {
+                                half = count / 2;
+                                s = next + half;
+                                ovf = quant_max(S, xrmax, s) > 8192;
+                            } else {
+                                while (quant_max(S, xrmax, step + 1) > 8192) step++;
+                                step++;
+                                s = step;
+                            }
+                            bits = 100000;
+                            if (!ovf) {
+                                quantize_all(S, ax, ay, s, qx, qy);
+                                bits = probe_bits(S, qx, qy, lane, gi, a1, a2, a3, hiding, hn, hb);
+                            }
+                            if (in_bin) {
+                                if (bits < max_bits) count = half;
+                                else { next += half; count -= half; }
+                                if (count <= 1) { in_bin = false; step = next; }
+                            } else if (bits <= max_bits) break;
+                        }
+                        part23 = bits;
+                        cnt = (gi.ts0 > 0) + (gi.ts1 > 0) + (gi.ts2 > 0);   // :808-809
+                    }
+                }
+                if (attempt == 0) {
+                    if (gr == 0 && lane == 0) S.cnt[round][0] = cnt;
+                    __syncthreads();
+                    need = false;
+                    if (gr == 1 && hiding && xrmax) {
+                        const int64_t actual = off + S.cnt[round][0];
+                        if (actual != use_off) {
+                            int hn2;
+                            uint32_t hb2;
+                            payload_bits_at(payload, cl, actual, lane, hn2, hb2);
+                            need = hn2 != hn || hb2 != hb;
+                            use_off = actual;
+                        }
+                    }
+                }
+            }
+            // ---- results of this granule
+            uint32_t *ixd = ixout + gslot * 288;
+            if (xrmax) {
+                // signed ix as format_bitstream leaves it (:1272-1276)
 #pragma unroll
                 for (int j = 0; j < 9; j++) {
-                    const int2 v = __ldg(xr + 32 * j + lane);
-                    ax[j] = v.x < 0 ? (uint32_t)(-(int64_t)v.x) : (uint32_t)v.x;
-                    ay[j] = v.y < 0 ? (uint32_t)(-(int64_t)v.y) : (uint32_t)v.y;
-                    sg |= (uint32_t)(v.x < 0) << (2 * j) | (uint32_t)(v.y < 0) << (2 * j + 1);
+                    const int vx = ((sg >> (2 * j)) & 1u) ? -(int)qx[j] : (int)qx[j];
+                    const int vy = ((sg >> (2 * j + 1)) & 1u) ? -(int)qy[j] : (int)qy[j];
+                    ixd[32 * j + lane] = ((uint32_t)vx & 0xFFFFu) | ((uint32_t)vy << 16);
                 }
-                const int32_t xrmax = stats[gslot].xrmax;
-                GranInfo gi;
-                gi.bv = 0; gi.count1 = 0; gi.c1sel = 0; gi.r0 = 0; gi.r1 = 0; gi.ts0 = 0; gi.ts1 = 0; gi.ts2 = 0;
-                int a1 = st.a1[slot], a2 = st.a2[slot], a3 = st.a3[slot], step = st.step[slot];
-                int part23 = 0;
-                uint32_t *ixd = ixout + gslot * 288;
-                if (xrmax) {
-                    // payload bits this granule can consume: bits[hide_off .. hide_off + 2]   (:1154-1168)
-                    int hn = 0;
-                    uint32_t hb = 0;
-                    if (hiding) {
-                        const int64_t left = cl.payload_len - st.hide_off;
-                        hn = left > 3 ? 3 : (left < 0 ? 0 : (int)left);
-                        const bool one = lane < hn && __ldg(payload + cl.payload_base + st.hide_off + lane) == '1';
-                        hb = __ballot_sync(FULL, one);
-                    }
-                    uint32_t qx[9], qy[9];
-                    // ---- bin_search_step_size (:958-996) then inner_loop (:1064-1095), as one loop with a single probe site
-                    int next = -120, count = 120, half = 0, bits = 0;
-                    bool in_bin = true;
-                    for (;;) {
-                        int s;
-                        bool ovf = false;
-                        if (in_bin) {
-                            half = count / 2;
-                            s = next + half;
-                            ovf = quant_max(S, xrmax, s) > 8192;
-                        } else {
-                            while (quant_max(S, xrmax, step + 1) > 8192) step++;
-                            step++;
-                            s = step;
-                        }
-                        bits = 100000;
-                        if (!ovf) {
-                            quantize_all(S, ax, ay, s, qx, qy);
-                            bits = probe_bits(S, qx, qy, lane, gi, a1, a2, a3, hiding, hn, hb);
-                        }
-                        if (in_bin) {
-                            if (bits < max_bits) count = half;
-                            else { next += half; count -= half; }
-                            if (count <= 1) { in_bin = false; step = next; }
-                        } else if (bits <= max_bits) break;
-                    }
-                    part23 = bits;
-                    st.hide_off += (gi.ts0 > 0) + (gi.ts1 > 0) + (gi.ts2 > 0);   // :808-809
-                    // ---- signed ix as format_bitstream leaves it (:1272-1276)
+            } else {
+                // silent granule: l3_enc keeps the previous frame's values of this slot (never coded: big_values = count1 = 0)
+                const uint32_t *src = f > chunk_first ? ixout + (gslot - 4) * 288
+                                                      : (f > 0 ? last_ix + ((int64_t)c * 4 + (2 * ch + gr)) * 288 : nullptr);
 #pragma unroll
-                    for (int j = 0; j < 9; j++) {
-                        const int vx = ((sg >> (2 * j)) & 1u) ? -(int)qx[j] : (int)qx[j];
-                        const int vy = ((sg >> (2 * j + 1)) & 1u) ? -(int)qy[j] : (int)qy[j];
-                        ixd[32 * j + lane] = ((uint32_t)vx & 0xFFFFu) | ((uint32_t)vy << 16);
-                    }
-                } else {
-                    // silent granule: l3_enc keeps the previous frame's values of this slot (never coded: big_values = count1 = 0)
-                    const uint32_t *src = f > chunk_first ? ixout + (gslot - 4) * 288
-                                                          : (f > 0 ? last_ix + ((int64_t)c * 4 + (2 * ch + gr)) * 288 : nullptr);
-#pragma unroll
-                    for (int j = 0; j < 9; j++) ixd[32 * j + lane] = src ? src[32 * j + lane] : 0u;
-                }
-                st.a1[slot] = a1; st.a2[slot] = a2; st.a3[slot] = a3; st.step[slot] = step;
-                p23[slot] = part23;
-                resv += mean_bits / 2 - part23;   // :812 (mean_bits is even: bits_per_frame and 288 are multiples of 8)
-                int32_t *r = rec[slot];
-                r[0] = part23; r[1] = gi.bv; r[2] = gi.count1; r[3] = step + 210; r[4] = gi.ts0; r[5] = gi.ts1; r[6] = gi.ts2;
-                r[7] = gi.r0; r[8] = gi.r1; r[9] = gi.c1sel; r[10] = a1; r[11] = a2; r[12] = a3; r[13] = step; r[14] = padding;
-                r[15] = 0;
+                for (int j = 0; j < 9; j++) ixd[32 * j + lane] = src ? src[32 * j + lane] : 0u;
             }
-            // ---- calc_scfsi for this channel (:862-892): needs the statistics of both granules
             if (lane == 0) {
-                const M3sEncStats s0 = stats[(fl_ * 2 + ch) * 2 + 0], s1 = stats[(fl_ * 2 + ch) * 2 + 1];
-                int condition = 2 + (s0.xrmax != 0) + (s1.xrmax != 0);
-                if (abs((int)s0.en_tot - (int)s1.en_tot) < 10) condition++;
-                int tp = 0;
-                for (int sfb = 0; sfb < 21; sfb++) tp += abs((int)s0.en[sfb] - (int)s1.en[sfb]);
-                if (tp < 100) condition++;
-                const int band[5] = {0, 6, 11, 16, 21};
-                for (int b = 0; b < 4; b++) {
-                    int sum0 = 0;
-                    for (int sfb = band[b]; sfb < band[b + 1]; sfb++) sum0 += abs((int)s0.en[sfb] - (int)s1.en[sfb]);
-                    scfsi_out[(fl_ * 2 + ch) * 4 + b] = (condition == 6 && sum0 < 10) ? 1 : 0;   // xm[] is all zero: sum1 = 0
-                }
+                S.slot[slot][0] = a1; S.slot[slot][1] = a2; S.slot[slot][2] = a3; S.slot[slot][3] = step;
+                S.p23[f & 1][slot] = part23;
+                if (gr == 1) S.cnt[round][1] = cnt;
+                int32_t *r = info + (fl_ * 4 + slot) * ENC_INFO_FIELDS;   // info layout [frame][gr][ch] == slot order
+                r[1] = gi.bv; r[2] = gi.count1; r[3] = step + 210; r[4] = gi.ts0; r[5] = gi.ts1; r[6] = gi.ts2;
+                r[7] = gi.r0; r[8] = gi.r1; r[9] = gi.c1sel; r[10] = a1; r[11] = a2; r[12] = a3; r[13] = step; r[14] = padding;
+            }
+            __syncthreads();
+            off += S.cnt[round][0] + S.cnt[round][1];
+        }
+        // ---- calc_scfsi (:862-892), warp w takes channel w: needs the statistics of both granules
+        {
+            const M3sEncStats *s0 = stats + (fl_ * 2 + gr) * 2, *s1 = s0 + 1;
+            const int d = lane < 21 ? abs((int)s0->en[lane] - (int)s1->en[lane]) : 0;
+            const int tp = __reduce_add_sync(FULL, d);
+            int condition = 2 + (s0->xrmax != 0) + (s1->xrmax != 0);
+            if (abs((int)s0->en_tot - (int)s1->en_tot) < 10) condition++;
+            if (tp < 100) condition++;
+            const int b0 = __reduce_add_sync(FULL, lane < 6 ? d : 0), b1 = __reduce_add_sync(FULL, lane >= 6 && lane < 11 ? d : 0);
+            const int b2 = __reduce_add_sync(FULL, lane >= 11 && lane < 16 ? d : 0), b3 = __reduce_add_sync(FULL, lane >= 16 ? d : 0);
+            if (lane < 4) {
+                const int sum0 = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+                scfsi_out[(fl_ * 2 + gr) * 4 + lane] = (condition == 6 && sum0 < 10) ? 1 : 0;   // xm[] is all zero: sum1 = 0
             }
         }
         // ---- resv_frame_end (:1097-1145): every unused bit of the frame becomes stuffing
-        int stuffing = resv;
-        if (stuffing > 0) {
-            if (p23[0] + stuffing < 4095) p23[0] += stuffing;
-            else {
-                const int order[4] = {0, 1, 2, 3};  // gr0ch0, gr0ch1, gr1ch0, gr1ch1 == slot order
-                for (int q = 0; q < 4 && stuffing > 0; q++) {
-                    const int s = order[q];
-                    const int t = min(4095 - p23[s], stuffing);
-                    p23[s] += t;
-                    stuffing -= t;
+        if (tid == 0) {
+            int p23[4];
+            int stuffing = 0;
+            for (int q = 0; q < 4; q++) { p23[q] = S.p23[f & 1][q]; stuffing += mean_bits / 2 - p23[q]; }   // :812 (mean_bits is even)
+            if (stuffing > 0) {
+                if (p23[0] + stuffing < 4095) p23[0] += stuffing;
+                else {
+                    for (int q = 0; q < 4 && stuffing > 0; q++) {   // gr0ch0, gr0ch1, gr1ch0, gr1ch1 == slot order
+                        const int t = min(4095 - p23[q], stuffing);
+                        p23[q] += t;
+                        stuffing -= t;
+                    }
                 }
             }
+            for (int q = 0; q < 4; q++) {
+                int32_t *r = info + (fl_ * 4 + q) * ENC_INFO_FIELDS;
+                r[0] = p23[q];
+                r[15] = (int32_t)off;
+            }
         }
-        if (lane < 4) {                         // info layout [frame][gr][ch] == slot order
-            int32_t *d = info + (fl_ * 4 + lane) * ENC_INFO_FIELDS;
-            for (int q = 1; q < ENC_INFO_FIELDS - 1; q++) d[q] = rec[lane][q];
-            d[0] = p23[lane];
-            d[15] = (int32_t)st.hide_off;
-        }
-        __syncwarp();
     }
     // ---- hand the state to the next chunk
     if (f_end > chunk_first && f_end < cl.n_frames) {
         const int64_t fl_ = cl.frame_base + (f_end - 1) - chunk_frame0;
-        for (int ch = 0; ch < 2; ch++)
-            for (int gr = 0; gr < 2; gr++) {
-                const uint32_t *src = ixout + ((fl_ * 2 + ch) * 2 + gr) * 288;
-                uint32_t *dst = last_ix + ((int64_t)c * 4 + (2 * ch + gr)) * 288;
-                for (int j = 0; j < 9; j++) dst[32 * j + lane] = src[32 * j + lane];
-            }
+        for (int ch = 0; ch < 2; ch++) {
+            const uint32_t *src = ixout + ((fl_ * 2 + ch) * 2 + gr) * 288;
+            uint32_t *dst = last_ix + ((int64_t)c * 4 + (2 * ch + gr)) * 288;
+            for (int j = 0; j < 9; j++) dst[32 * j + lane] = src[32 * j + lane];
+        }
     }
-    if (lane == 0) states[c] = st;
+    __syncthreads();
+    if (tid < 4) {
+        M3sEncState *sp = states + c;
+        sp->a1[tid] = S.slot[tid][0]; sp->a2[tid] = S.slot[tid][1]; sp->a3[tid] = S.slot[tid][2]; sp->step[tid] = S.slot[tid][3];
+        if (tid == 0) sp->hide_off = off;
+    }
 }
 
 // ================================================================================================
@@ -877,6 +966,7 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         build_enc_tables((const M3sDevTables *)hostT.data(), &E);
         if ((rc = m3s_buf_reserve(h, h->e_tabs, sizeof(EncTables)))) return rc;
         M3S_CUDA(h, cudaMemcpy(h->e_tabs.p, &E, sizeof E, cudaMemcpyHostToDevice));
+        M3S_CUDA(h, cudaMemcpyToSymbol(c_enc_cos, ((const M3sDevTables *)hostT.data())->enc_cosl, sizeof(int32_t) * 18 * 36));
     }
     // ---- inputs.  Host buffers are streamed: the PCM of chunk k+1 crosses PCIe on `copy_in` while chunk k is in the
     //      kernels, and the MP3 bytes of chunk k-1 go back on `copy_out` (see the chunk loop below)
@@ -914,6 +1004,7 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     if ((rc = m3s_buf_reserve(h, h->e_misc, (size_t)chunk_cap * 4))) return rc;
 
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 7 CTAs x 24 KB per SM
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
     std::vector<M3sEncWork> work;
     std::vector<int32_t> frame_clip;
@@ -990,7 +1081,7 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
             free_recorded[buf] = true;
         }
         M3S_KBEGIN(h, M3S_K_ENC_RATE);
-        k_enc_rate<<<(unsigned)n_clips, 32, sizeof(RateSmem), h->stream>>>(
+        k_enc_rate<<<(unsigned)n_clips, 32 * RATE_WARPS, sizeof(RateSmem), h->stream>>>(
             (const M3sEncClip *)h->e_clips.p, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p,
             (const uint32_t *)h->e_pad.p, (const uint8_t *)h->e_payload.p, sri, whole, (int32_t)c0, (int32_t)cf, 0,
             (const int32_t *)h->e_mdct.p, (const M3sEncStats *)h->e_gran.p, (uint32_t *)h->e_ix.p, (int32_t *)h->e_info.p,
