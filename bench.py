@@ -380,9 +380,9 @@ def run_product_arm(args):
         return sum(counts)
 
     if args.e2e_sweep:    # diagnostic: e2e decode throughput over worker counts and wave sizes, with a per-call trace
-        for wf in (25, 50, 125):
+        for wf in ((50,) if os.environ.get("M3S_TRACE") else (25, 50, 125)):
             state["waves"] = make_waves(wf)
-            for nwk in (1, 2, 3, 4, 6):
+            for nwk in ((2,) if os.environ.get("M3S_TRACE") else (1, 2, 3, 4, 6)):
                 state["n"] = nwk
                 ensure_workers(nwk, max(w["frames"] for w in state["waves"]))
                 dec_host()

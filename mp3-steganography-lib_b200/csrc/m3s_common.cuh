@@ -180,7 +180,13 @@ struct m3s_ctx {
     const uint8_t *d_bytes = nullptr;  // device pointer to the batch bytes (caller's or staged)
     std::vector<M3sFileRec> files;
     std::vector<M3sFileOut> fouts;
-    M3sBuf b_stage_in, b_files, b_fouts, b_tmp_pos, b_fr_pos, b_fr_P, b_fr_meta, b_fr_carry, b_fr_reveal, b_fr_file;
+    // per-file results of the scan kernels land in MAPPED pinned host memory (zero-copy stores): reading them back needs no
+    // copy-engine command, so a scan is never queued behind another handle's bulk PCM transfer
+    M3sFileOut *fouts_mapped = nullptr, *fouts_dev = nullptr;
+    size_t fouts_cap = 0;
+    uint8_t *rev_mapped = nullptr, *rev_dev = nullptr;   // same idea for the reveal outputs (24 bytes per frame), filled by a copy KERNEL
+    size_t rev_cap = 0;
+    M3sBuf b_stage_in, b_files, b_tmp_pos, b_fr_pos, b_fr_P, b_fr_meta, b_fr_carry, b_fr_reveal, b_fr_file;
     M3sBuf b_units, b_sf, b_S, b_spec, b_tabids, b_reveal, b_work, b_pcm_stage, b_spec_export;
     // ---- encode state
     M3sBuf e_pcm, e_clips, e_mdct, e_ix, e_info, e_gran, e_out, e_payload, e_misc, e_pad, e_tabs, e_state, e_lastix, e_scfsi, e_work;

@@ -381,12 +381,14 @@ extern "C" int m3s_destroy(m3s_handle_t h)
     if (!h) return M3S_ERR_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    M3sBuf *bufs[] = {&h->b_stage_in, &h->b_files, &h->b_fouts, &h->b_tmp_pos, &h->b_fr_pos, &h->b_fr_P, &h->b_fr_meta, &h->b_fr_carry,
+    M3sBuf *bufs[] = {&h->b_stage_in, &h->b_files, &h->b_tmp_pos, &h->b_fr_pos, &h->b_fr_P, &h->b_fr_meta, &h->b_fr_carry,
                       &h->b_fr_reveal, &h->b_fr_file, &h->b_units, &h->b_sf, &h->b_S, &h->b_spec, &h->b_tabids,
                       &h->b_reveal, &h->b_work, &h->b_pcm_stage, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
                       &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad, &h->e_tabs, &h->e_state,
                       &h->e_lastix, &h->e_scfsi, &h->e_work};
     for (M3sBuf *b : bufs) free_buf(*b);
+    if (h->fouts_mapped) cudaFreeHost(h->fouts_mapped);
+    if (h->rev_mapped) cudaFreeHost(h->rev_mapped);
     timing_resolve(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->d_tab) cudaFree(h->d_tab);

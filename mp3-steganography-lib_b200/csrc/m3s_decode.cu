@@ -1043,6 +1043,11 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
 // ================================================================================================
 // host orchestration
 // ================================================================================================
+#include <chrono>
+static const bool g_trace = getenv("M3S_TRACE") != nullptr;   // host-clock stage timing of the decode calls (diagnostic)
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define M3S_TRACE_MARK(tag) do { if (g_trace) { const double t__ = now_ms(); fprintf(stderr, "[m3s %p] %-18s +%.2f ms\n", (void *)h, tag, t__ - tr_t); tr_t = t__; } } while (0)
+
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, const int64_t *file_off,
@@ -1053,6 +1058,7 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     h->scanned = false;
     if (!bytes || !file_off || n_files <= 0) return m3s_fail(h, M3S_ERR_ARG, "decode_scan: bytes/file_off/n_files");
     M3S_CUDA(h, cudaSetDevice(h->device));
+    double tr_t = g_trace ? now_ms() : 0.0;
     const int64_t total_bytes = file_off[n_files];
     for (int i = 0; i < n_files; i++)
         if (file_off[i + 1] < file_off[i] || (audio_start && (audio_start[i] < 0)))
@@ -1065,6 +1071,7 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
         h->d_bytes = (const uint8_t *)h->b_stage_in.p;
     } else
         h->d_bytes = bytes;
+    M3S_TRACE_MARK("scan.h2d_submitted");
     h->n_files = n_files;
     h->files.assign(n_files, M3sFileRec());
     h->fouts.assign(n_files, M3sFileOut());
@@ -1078,7 +1085,16 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     }
     int rc;
     if ((rc = m3s_buf_reserve(h, h->b_files, sizeof(M3sFileRec) * n_files))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_fouts, sizeof(M3sFileOut) * n_files))) return rc;
+    if ((size_t)n_files > h->fouts_cap) {
+        M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->fouts_mapped) M3S_CUDA(h, cudaFreeHost(h->fouts_mapped));
+        h->fouts_mapped = nullptr;
+        h->fouts_cap = 0;
+        const size_t cap = (size_t)n_files + 64;
+        M3S_CUDA(h, cudaHostAlloc((void **)&h->fouts_mapped, sizeof(M3sFileOut) * cap, cudaHostAllocMapped));
+        M3S_CUDA(h, cudaHostGetDevicePointer((void **)&h->fouts_dev, h->fouts_mapped, 0));
+        h->fouts_cap = cap;
+    }
     M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
     // ---- walk: positions of every frame (file-relative) into a temporary array sized by the smallest legal frame (96 bytes)
     {
@@ -1094,11 +1110,13 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
     const int wg = (n_files + WALK_WARPS - 1) / WALK_WARPS;
     M3S_KBEGIN(h, M3S_K_WALK);
-    k_walk<<<wg, 32 * WALK_WARPS, 0, h->stream>>>(h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p,
+    k_walk<<<wg, 32 * WALK_WARPS, 0, h->stream>>>(h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, h->fouts_dev,
                                                    n_files, (uint32_t *)h->b_tmp_pos.p);
     M3S_LAUNCH_CHECK(h);
-    M3S_CUDA(h, cudaMemcpyAsync(h->fouts.data(), h->b_fouts.p, sizeof(M3sFileOut) * n_files, cudaMemcpyDeviceToHost, h->stream));
+    M3S_TRACE_MARK("scan.walk_launched");
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(h->fouts.data(), h->fouts_mapped, sizeof(M3sFileOut) * n_files);
+    M3S_TRACE_MARK("scan.walk_synced");
     int64_t fb = 0, sb = 0;
     for (int i = 0; i < n_files; i++) {
         M3sFileRec &f = h->files[i];
@@ -1124,7 +1142,7 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     if ((rc = m3s_buf_reserve(h, h->b_reveal, 12 * nf))) return rc;
     M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
     M3S_KBEGIN(h, M3S_K_FSCAN);
-    k_fscan<<<wg, 32 * WALK_WARPS, 0, h->stream>>>(h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, (M3sFileOut *)h->b_fouts.p,
+    k_fscan<<<wg, 32 * WALK_WARPS, 0, h->stream>>>(h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, h->fouts_dev,
                                                     n_files, (const uint32_t *)h->b_tmp_pos.p, (int64_t *)h->b_fr_pos.p,
                                                     (uint32_t *)h->b_fr_P.p, (uint32_t *)h->b_fr_meta.p, (uint32_t *)h->b_fr_carry.p,
                                                     (uint32_t *)h->b_fr_reveal.p, (int32_t *)h->b_fr_file.p);
@@ -1137,8 +1155,10 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
             (const int32_t *)h->b_fr_file.p, (M3sUnitRec *)h->b_units.p, (uint8_t *)h->b_tabids.p, (uint8_t *)h->b_reveal.p);
         M3S_LAUNCH_CHECK(h);
     }
-    M3S_CUDA(h, cudaMemcpyAsync(h->fouts.data(), h->b_fouts.p, sizeof(M3sFileOut) * n_files, cudaMemcpyDeviceToHost, h->stream));
+    M3S_TRACE_MARK("scan.fscan_launched");
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(h->fouts.data(), h->fouts_mapped, sizeof(M3sFileOut) * n_files);
+    M3S_TRACE_MARK("scan.fscan_synced");
     for (int i = 0; i < n_files; i++) {
         const M3sFileOut &o = h->fouts[i];
         h->files[i].flags = o.status;
@@ -1154,19 +1174,51 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     return M3S_OK;
 }
 
+// device -> mapped host memory by SM stores (one 32-bit word per thread, coalesced): the reveal outputs are small and the host
+// thread waits for them, so they must not queue behind another handle's bulk PCM transfer in the copy engine
+__global__ void k_words_out(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, int64_t n_words, uint32_t *__restrict__ out_a,
+                            uint32_t *__restrict__ out_b)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    if (out_a) out_a[i] = a[i];
+    if (out_b) out_b[i] = b[i];
+}
+
 extern "C" int m3s_decode_reveal(m3s_handle_t h, uint8_t *table_ids, uint8_t *reveal_bits, int mem, int64_t *reveal_len)
 {
     if (!h) return M3S_ERR_ARG;
     if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_reveal: call m3s_decode_scan first");
     M3S_CUDA(h, cudaSetDevice(h->device));
-    const cudaMemcpyKind kind = mem == M3S_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    if (h->total_frames > 0) {
-        if (table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids, h->b_tabids.p, 12 * h->total_frames, kind, h->stream));
-        if (reveal_bits) M3S_CUDA(h, cudaMemcpyAsync(reveal_bits, h->b_reveal.p, 12 * h->total_frames, kind, h->stream));
-    }
     if (reveal_len)
         for (int i = 0; i < h->n_files; i++) reveal_len[i] = h->fouts[i].reveal_len;
+    const size_t nb = (size_t)12 * (size_t)h->total_frames;   // bytes of each output (a multiple of 4)
+    if (nb == 0 || (!table_ids && !reveal_bits)) return M3S_OK;
+    if (mem != M3S_MEM_HOST) {
+        if (table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids, h->b_tabids.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+        if (reveal_bits) M3S_CUDA(h, cudaMemcpyAsync(reveal_bits, h->b_reveal.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+        M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+        return M3S_OK;
+    }
+    if (2 * nb > h->rev_cap) {
+        M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->rev_mapped) M3S_CUDA(h, cudaFreeHost(h->rev_mapped));
+        h->rev_mapped = nullptr;
+        h->rev_cap = 0;
+        const size_t cap = 2 * nb + (1 << 16);
+        M3S_CUDA(h, cudaHostAlloc((void **)&h->rev_mapped, cap, cudaHostAllocMapped));
+        M3S_CUDA(h, cudaHostGetDevicePointer((void **)&h->rev_dev, h->rev_mapped, 0));
+        h->rev_cap = cap;
+    }
+    const int64_t nw = (int64_t)(nb / 4);
+    M3S_KBEGIN(h, M3S_K_SIDEINFO);
+    k_words_out<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)h->b_tabids.p, (const uint32_t *)h->b_reveal.p, nw,
+                                                                       table_ids ? (uint32_t *)h->rev_dev : nullptr,
+                                                                       reveal_bits ? (uint32_t *)(h->rev_dev + nb) : nullptr);
+    M3S_LAUNCH_CHECK(h);
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (table_ids) memcpy(table_ids, h->rev_mapped, nb);
+    if (reveal_bits) memcpy(reveal_bits, h->rev_mapped + nb, nb);
     return M3S_OK;
 }
 
@@ -1180,6 +1232,7 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
     M3S_CUDA(h, cudaSetDevice(h->device));
     const int64_t nf = h->total_frames;
     if (nf == 0) return M3S_OK;
+    double tr_t = g_trace ? now_ms() : 0.0;
     const bool fl = (flags & M3S_DEC_PCM_FLOAT) != 0;
     const size_t esz = fl ? 4 : 2;
     int rc;
@@ -1256,8 +1309,11 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
         else M3S_LAUNCH_HYBRID(float, M3sDevTables, false, h->d_tab);
     }
     M3S_LAUNCH_CHECK(h);
+    M3S_TRACE_MARK("run.launched");
+    if (g_trace) { cudaStreamSynchronize(h->stream); M3S_TRACE_MARK("run.kernels_done"); }
     if (mem == M3S_MEM_HOST)
         if ((rc = m3s_copy_paced(h, pcm, d_pcm, (size_t)total_elems * esz, cudaMemcpyDeviceToHost))) return rc;
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    M3S_TRACE_MARK("run.d2h_done");
     return M3S_OK;
 }
