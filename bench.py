@@ -524,7 +524,7 @@ def main():
     ap.add_argument("--e2e-wave", type=int, default=50, help="files per wave of the host-buffer (e2e) decode leg")
     ap.add_argument("--no-encode", action="store_true", help="skip the encode+hide half")
     ap.add_argument("--e2e-sweep", action="store_true", help="diagnostic sweep of the decode e2e leg (no JSON line)")
-    ap.add_argument("--e2e-workers", type=int, default=4, help="host worker threads (one handle each) of the decode e2e leg")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="host worker threads (one handle each) of the decode e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

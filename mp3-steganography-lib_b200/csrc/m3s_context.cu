@@ -301,6 +301,8 @@ int m3s_pipeline_init(m3s_ctx *h)
     if (h->copy_in) return M3S_OK;
     M3S_CUDA(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
     M3S_CUDA(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    M3S_CUDA(h, cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_ana[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
@@ -385,7 +387,7 @@ extern "C" int m3s_destroy(m3s_handle_t h)
                       &h->b_fr_reveal, &h->b_fr_file, &h->b_units, &h->b_sf, &h->b_S, &h->b_spec, &h->b_tabids,
                       &h->b_reveal, &h->b_work, &h->b_pcm_stage, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
                       &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad, &h->e_tabs, &h->e_state,
-                      &h->e_lastix, &h->e_scfsi, &h->e_work};
+                      &h->e_lastix, &h->e_scfsi, &h->e_work, &h->e_clips2, &h->e_mdct2, &h->e_gran2};
     for (M3sBuf *b : bufs) free_buf(*b);
     if (h->fouts_mapped) cudaFreeHost(h->fouts_mapped);
     if (h->rev_mapped) cudaFreeHost(h->rev_mapped);
@@ -395,6 +397,9 @@ extern "C" int m3s_destroy(m3s_handle_t h)
     if (h->d_tab_f64) cudaFree(h->d_tab_f64);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    if (h->aux) cudaStreamDestroy(h->aux);
+    for (int i = 0; i < 2; i++)
+        if (h->ev_ana[i]) cudaEventDestroy(h->ev_ana[i]);
     for (int i = 0; i < 2; i++) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
@@ -448,18 +453,19 @@ void m3s_time_begin(m3s_ctx *h, int id)
     t.id = id;
     t.e0 = take_event(h);
     t.e1 = take_event(h);
-    cudaEventRecord(t.e0, h->stream);
+    cudaEventRecord(t.e0, h->launch_stream ? h->launch_stream : h->stream);
     h->timed.push_back(t);
 }
 
 void m3s_time_end(m3s_ctx *h)
 {
-    if (!h->timed.empty()) cudaEventRecord(h->timed.back().e1, h->stream);
+    if (!h->timed.empty()) cudaEventRecord(h->timed.back().e1, h->launch_stream ? h->launch_stream : h->stream);
 }
 
 static void timing_resolve(m3s_ctx *h)
 {
     cudaStreamSynchronize(h->stream);
+    if (h->aux) cudaStreamSynchronize(h->aux);
     for (auto &t : h->timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) h->k_ms[t.id] += ms;

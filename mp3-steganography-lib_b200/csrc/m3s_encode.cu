@@ -49,7 +49,7 @@ struct M3sEncWork {        // E1 work item: a run of granules of one clip
     int32_t clip;
     int32_t g_first;       // first granule (2 * frame + gr) whose MDCT this CTA emits
     int32_t count;
-    int32_t pad;
+    int32_t ch;            // channel this CTA transforms
 };
 
 #define ENC_INFO_FIELDS 16
@@ -80,16 +80,16 @@ __device__ __forceinline__ int32_t mulsr32(int32_t a, int32_t b)  // util.mulsr 
 //               whole kernel, the windowed vector arrives as broadcast 128-bit loads                      (0.25 LDS / mul)
 //   MDCT        thread (ch, band, k range): cos_l is an immediate constant-bank operand of the IMAD.HI   (0.22 LDS / mul)
 // ================================================================================================
-#define ANA_THREADS 256
+#define ANA_THREADS 128
 
 __constant__ int32_t c_enc_cos[18][36];   // MP3Encoder.__cos_l (:557-566), window folded in
 
 struct AnaSmem {
-    int32_t x[2][2][1056];      // [buffer][ch]: 480 samples of history + 576 new, as int16 << 16 (double buffered: no shift barrier)
-    __align__(16) int32_t y[2][18][64];   // [ch][slot][i] windowed vectors
-    int32_t sb[2][2][18][32];   // [ch][ping-pong][slot][band] subband samples
-    int32_t mf[2][576];         // [ch][band * 18 + k] MDCT lines
-    uint32_t bins[2][24];       // per channel: 0..20 band energies, 21 total, 22 xrmax
+    int32_t x[2][1056];         // [buffer]: 480 samples of history + 576 new of this channel, as int16 << 16 (double buffered: no shift barrier)
+    __align__(16) int32_t y[18][64];   // [slot][i] windowed vectors
+    int32_t sb[2][18][32];      // [ping-pong][slot][band] subband samples
+    int32_t mf[576];            // [band * 18 + k] MDCT lines
+    uint32_t bins[24];          // 0..20 band energies, 21 total, 22 xrmax
     uint8_t sfb[576];
     int32_t ca[8], cs[8];
 };
@@ -119,7 +119,10 @@ __device__ __forceinline__ void mdct_band(const int32_t *__restrict__ prev, cons
     for (int q = 0; q < NK; q++) mf[lane * 18 + K0 + q] = (int32_t)acc[q];
 }
 
-__global__ void __launch_bounds__(ANA_THREADS, 2)
+// One CTA of four warps walks a run of granules of ONE channel of one clip (work item = clip, first granule, count, channel).
+// The small CTA (128 threads, ~21 KB of shared memory) is what lets it share an SM with the rate loop's CTAs of the
+// previous chunk, whose latency-bound chains leave the IMAD.HI pipe idle (see m3s_encode: the two kernels overlap).
+__global__ void __launch_bounds__(ANA_THREADS, 4)
 k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ clips, const M3sEncWork *__restrict__ work,
                const M3sDevTables *__restrict__ T, const EncTables *__restrict__ ET, int sr_idx, int64_t chunk_frame0,
                int32_t *__restrict__ mdct, M3sEncStats *__restrict__ stats)
@@ -128,51 +131,47 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const M3sEncWork wk = work[blockIdx.x];
     const M3sEncClip cl = clips[wk.clip];
+    const int ch = wk.ch;
     for (int i = tid; i < 576; i += ANA_THREADS) S.sfb[i] = T->long_sfb_of[sr_idx][i];
     if (tid < 8) { S.ca[tid] = T->enc_ca[tid]; S.cs[tid] = T->enc_cs[tid]; }
-    for (int i = tid; i < 2 * 2 * 18 * 32; i += ANA_THREADS) (&S.sb[0][0][0][0])[i] = 0;
+    for (int i = tid; i < 2 * 18 * 32; i += ANA_THREADS) (&S.sb[0][0][0])[i] = 0;
     // ---- per-thread roles and their register-resident coefficients
-    const int wch = tid >> 7, wpar = (tid >> 6) & 1, wi = tid & 63;                  // windowing: channel, slot parity, output i
+    const int wpar = tid >> 6, wi = tid & 63;                                  // windowing: slot parity, output i
     int32_t wcoef[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) wcoef[k] = T->enwindow[wi + 64 * k];
-    const int mch = tid >> 7, mhalf = (tid >> 6) & 1, mb = (tid & 63) >> 1, mh = tid & 1;   // matrixing: channel, slots 9*mhalf.., band, row half
+    const int mhalf = tid >> 6, mb = (tid & 63) >> 1, mh = tid & 1;            // matrixing: slots 9*mhalf.., band, row half
     int32_t fl[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) fl[j] = T->enc_fl[mb][32 * mh + j];
-    const int dch = warp >> 2, dkq = warp & 3;                                       // MDCT: channel, k range; band = lane
     __syncthreads();
 
     const uint32_t *pcm32 = (const uint32_t *)(pcm + cl.pcm_base);  // one stereo sample per word (pcm_base is even)
+    const int sh = ch ? 0 : 16;                                     // channel 0 = low half of the word
     const int g_begin = wk.g_first > 0 ? wk.g_first - 1 : 0;
     const int g_end = wk.g_first + wk.count;
     int pp = 0, xb = 0;
     for (int G = g_begin; G < g_end; G++, pp ^= 1, xb ^= 1) {
-        // ---- PCM window: samples [576 G - 480, 576 G + 576) of both channels; the history comes from the other buffer
+        // ---- PCM window: samples [576 G - 480, 576 G + 576); the history comes from the other buffer
         const int64_t t0 = (int64_t)G * 576 - 480;
         if (G == g_begin) {
             for (int i = tid; i < 1056; i += ANA_THREADS) {
                 const int64_t t = t0 + i;
                 const uint32_t w = t >= 0 ? __ldg(pcm32 + t) : 0u;
-                S.x[xb][0][i] = (int32_t)(w << 16);
-                S.x[xb][1][i] = (int32_t)(w & 0xFFFF0000u);
+                S.x[xb][i] = (int32_t)((w << sh) & 0xFFFF0000u);
             }
         } else {
-            for (int i = tid; i < 480; i += ANA_THREADS) {
-                S.x[xb][0][i] = S.x[xb ^ 1][0][576 + i];
-                S.x[xb][1][i] = S.x[xb ^ 1][1][576 + i];
-            }
+            for (int i = tid; i < 480; i += ANA_THREADS) S.x[xb][i] = S.x[xb ^ 1][576 + i];
             for (int i = tid; i < 576; i += ANA_THREADS) {
                 const uint32_t w = __ldg(pcm32 + t0 + 480 + i);
-                S.x[xb][0][480 + i] = (int32_t)(w << 16);
-                S.x[xb][1][480 + i] = (int32_t)(w & 0xFFFF0000u);
+                S.x[xb][480 + i] = (int32_t)((w << sh) & 0xFFFF0000u);
             }
         }
         __syncthreads();
         // ---- windowing: y_s[i] = sum_k mul(x[32 s + 31 - i - 64 k], enwindow[i + 64 k])   (:337-356).  Slots s = p + 2 q of one
         //      parity share their samples: x index = base + 64 (q - k), 16 distinct values for 9 slots x 8 taps
         {
-            const int32_t *xp = &S.x[xb][wch][480 + 32 * wpar + 31 - wi];
+            const int32_t *xp = &S.x[xb][480 + 32 * wpar + 31 - wi];
             int32_t xv[16];
 #pragma unroll
             for (int d = 0; d < 16; d++) xv[d] = xp[64 * (d - 7)];
@@ -182,7 +181,7 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
 #pragma unroll
                 for (int k = 0; k < 8; k += 2)
                     acc += (uint32_t)__mulhi(xv[q - k + 7], wcoef[k]) + (uint32_t)__mulhi(xv[q - k + 6], wcoef[k + 1]);
-                S.y[wch][wpar + 2 * q][wi] = (int32_t)acc;
+                S.y[wpar + 2 * q][wi] = (int32_t)acc;
             }
         }
         __syncthreads();
@@ -190,7 +189,7 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
 #pragma unroll 1
         for (int q = 0; q < 9; q++) {
             const int s = 9 * mhalf + q;
-            const int4 *y4 = (const int4 *)&S.y[mch][s][32 * mh];
+            const int4 *y4 = (const int4 *)&S.y[s][32 * mh];
             uint32_t acc = 0;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
@@ -201,61 +200,56 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
             acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
             if (mh == 0) {
                 if ((s & 1) && (mb & 1)) acc = 0u - acc;
-                S.sb[mch][pp][s][mb] = (int32_t)acc;
+                S.sb[pp][s][mb] = (int32_t)acc;
             }
         }
         __syncthreads();
         if (G < wk.g_first) continue;   // warm-up granule: only its subband samples are needed (block-uniform)
-        // ---- MDCT   (:683-701)
+        // ---- MDCT   (:683-701): warp = k range, lane = band
         {
-            const int32_t *prev = &S.sb[dch][pp ^ 1][0][0], *cur = &S.sb[dch][pp][0][0];
-            int32_t *mf = S.mf[dch];
-            switch (dkq) {   // warp-uniform
-            case 0: mdct_band<0, 5>(prev, cur, lane, mf); break;
-            case 1: mdct_band<5, 5>(prev, cur, lane, mf); break;
-            case 2: mdct_band<10, 4>(prev, cur, lane, mf); break;
-            default: mdct_band<14, 4>(prev, cur, lane, mf); break;
+            const int32_t *prev = &S.sb[pp ^ 1][0][0], *cur = &S.sb[pp][0][0];
+            switch (warp) {   // warp-uniform
+            case 0: mdct_band<0, 5>(prev, cur, lane, S.mf); break;
+            case 1: mdct_band<5, 5>(prev, cur, lane, S.mf); break;
+            case 2: mdct_band<10, 4>(prev, cur, lane, S.mf); break;
+            default: mdct_band<14, 4>(prev, cur, lane, S.mf); break;
             }
-            if (tid < 48) (&S.bins[0][0])[tid] = 0u;
+            if (tid < 24) S.bins[tid] = 0u;
         }
         __syncthreads();
         // ---- alias butterflies between neighbouring bands, cmuls with >> 31   (:704-744, util.py:145-155)
-        for (int a = tid; a < 2 * 248; a += ANA_THREADS) {
-            const int ch = a >= 248, r = a - 248 * ch;
+        for (int r = tid; r < 248; r += ANA_THREADS) {
             const int band = 1 + (r >> 3), k = r & 7;
-            int32_t *mf = S.mf[ch];
-            const int64_t are = mf[band * 18 + k], aim = mf[(band - 1) * 18 + 17 - k];
+            const int64_t are = S.mf[band * 18 + k], aim = S.mf[(band - 1) * 18 + 17 - k];
             const int64_t bre = S.cs[k], bim = S.ca[k];
-            mf[band * 18 + k] = (int32_t)((are * bre - aim * bim) >> 31);
-            mf[(band - 1) * 18 + 17 - k] = (int32_t)((are * bim + aim * bre) >> 31);
+            S.mf[band * 18 + k] = (int32_t)((are * bre - aim * bim) >> 31);
+            S.mf[(band - 1) * 18 + 17 - k] = (int32_t)((are * bim + aim * bre) >> 31);
         }
         __syncthreads();
         // ---- store + statistics: xrmax, en_tot, en[sfb]   (:772-776, :836-857)
         const int frame = G >> 1, gr = G & 1;
-        const int64_t gslot0 = (((int64_t)(cl.frame_base + frame) - chunk_frame0) * 2) * 2 + gr;   // channel 0; channel 1 is + 2
-        for (int idx = tid; idx < 2 * 576; idx += ANA_THREADS) {   // a warp never straddles the channels (576 = 18 * 32)
-            const int ch = idx >= 576, i = idx - 576 * ch;
-            const int32_t v = S.mf[ch][i];
-            mdct[(gslot0 + 2 * ch) * 576 + i] = v;
+        const int64_t gslot = (((int64_t)(cl.frame_base + frame) - chunk_frame0) * 2 + ch) * 2 + gr;
+        for (int i = tid; i < 576; i += ANA_THREADS) {   // 576 = 18 * 32: whole warps
+            const int32_t v = S.mf[i];
+            mdct[gslot * 576 + i] = v;
             const uint32_t e = (uint32_t)(mulsr32(v, v) >> 10);
             const int sfb = S.sfb[i];
-            if (sfb < 21 && e) atomicAdd(&S.bins[ch][sfb], e);
+            if (sfb < 21 && e) atomicAdd(&S.bins[sfb], e);
             const uint32_t a = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
             const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, e), mx = __reduce_max_sync(0xFFFFFFFFu, a);
-            if (lane == 0) { atomicAdd(&S.bins[ch][21], tot); atomicMax(&S.bins[ch][22], mx); }
+            if (lane == 0) { atomicAdd(&S.bins[21], tot); atomicMax(&S.bins[22], mx); }
         }
         __syncthreads();
-        if (tid < 44) {
-            const int ch = tid >= 22, b = tid - 22 * ch;
-            const uint32_t temp = S.bins[ch][b];
+        if (tid < 22) {
+            const uint32_t temp = S.bins[tid];
             int en = 0;
             if (temp) {
                 en = -21;
                 for (int j = 0; j < 31; j++) en += ET->en_thresh[j] <= temp;
             }
-            M3sEncStats *st = stats + gslot0 + 2 * ch;
-            if (b == 21) { st->en_tot = (int8_t)en; st->xrmax = (int32_t)S.bins[ch][22]; }
-            else st->en[b] = (int8_t)en;
+            M3sEncStats *st = stats + gslot;
+            if (tid == 21) { st->en_tot = (int8_t)en; st->xrmax = (int32_t)S.bins[22]; }
+            else st->en[tid] = (int8_t)en;
         }
         // no barrier: the next writers of bins (MDCT phase of the next granule) sit behind three barriers
     }
@@ -463,7 +457,7 @@ __device__ __forceinline__ void payload_bits_at(const uint8_t *__restrict__ payl
 // per non-empty region; none if granule 0 is silent).  A granule depends on its offset only through the <= 3 bits it
 // reads, so after warp 0 publishes its count warp 1 keeps its result when the bits at the true offset equal the ones it
 // used and re-runs otherwise (the tone+noise corpus mispredicts 1-2 % of the granules, low tones up to 27 %).
-__global__ void __launch_bounds__(32 * RATE_WARPS, 7)
+__global__ void __launch_bounds__(32 * RATE_WARPS, 10)
 k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ states, const M3sDevTables *__restrict__ T,
            const EncTables *__restrict__ ET, const uint32_t *__restrict__ byteoff, const uint8_t *__restrict__ payload,
            int sr_idx, int whole_slots, int32_t chunk_first, int32_t chunk_frames, int64_t chunk_frame0,
@@ -973,15 +967,15 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     const bool host = mem == M3S_MEM_HOST;
     const int16_t *d_pcm = pcm;
     uint8_t *d_out = mp3_out;
+    if ((rc = m3s_pipeline_init(h))) return rc;
     if (host) {
-        if ((rc = m3s_pipeline_init(h))) return rc;
         if ((rc = m3s_buf_reserve(h, h->e_out, (size_t)out_total + 16))) return rc;
         d_out = (uint8_t *)h->e_out.p;
     }
     if ((rc = m3s_buf_reserve(h, h->e_payload, (size_t)pay_total + 16))) return rc;
     if (pay_total > 0) M3S_CUDA(h, cudaMemcpyAsync(h->e_payload.p, payload_bits, (size_t)pay_total, cudaMemcpyHostToDevice, h->stream));
     if ((rc = m3s_buf_reserve(h, h->e_clips, sizeof(M3sEncClip) * n_clips))) return rc;
-    M3S_CUDA(h, cudaMemcpyAsync(h->e_clips.p, clips.data(), sizeof(M3sEncClip) * n_clips, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = m3s_buf_reserve(h, h->e_clips2, sizeof(M3sEncClip) * n_clips))) return rc;
     if ((rc = m3s_buf_reserve(h, h->e_pad, sizeof(uint32_t) * byteoff.size()))) return rc;
     M3S_CUDA(h, cudaMemcpyAsync(h->e_pad.p, byteoff.data(), sizeof(uint32_t) * byteoff.size(), cudaMemcpyHostToDevice, h->stream));
     if ((rc = m3s_buf_reserve(h, h->e_state, sizeof(M3sEncState) * n_clips))) return rc;
@@ -996,100 +990,140 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     const bool single_chunk = cf >= max_frames;
     int64_t chunk_cap = 0;
     for (int i = 0; i < n_clips; i++) chunk_cap += std::min<int64_t>(cf, clips[i].n_frames);
+    const int64_t n_chunks = (max_frames + cf - 1) / cf;
     if ((rc = m3s_buf_reserve(h, h->e_mdct, (size_t)chunk_cap * 4 * 576 * 4))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->e_gran, (size_t)chunk_cap * 4 * sizeof(M3sEncStats)))) return rc;
+    if (n_chunks > 1) {   // the analysis of chunk k+1 writes the second set while the rate loop of chunk k reads the first
+        if ((rc = m3s_buf_reserve(h, h->e_mdct2, (size_t)chunk_cap * 4 * 576 * 4))) return rc;
+        if ((rc = m3s_buf_reserve(h, h->e_gran2, (size_t)chunk_cap * 4 * sizeof(M3sEncStats)))) return rc;
+    }
     if ((rc = m3s_buf_reserve(h, h->e_ix, (size_t)chunk_cap * 4 * 288 * 4))) return rc;
     if ((rc = m3s_buf_reserve(h, h->e_info, (size_t)chunk_cap * 4 * ENC_INFO_FIELDS * 4))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->e_gran, (size_t)chunk_cap * 4 * sizeof(M3sEncStats)))) return rc;
     if ((rc = m3s_buf_reserve(h, h->e_scfsi, (size_t)chunk_cap * 8))) return rc;
     if ((rc = m3s_buf_reserve(h, h->e_misc, (size_t)chunk_cap * 4))) return rc;
+    {
+        size_t max_work = 0;
+        for (int i = 0; i < n_clips; i++) max_work += 2 * (size_t)((2 * std::min<int64_t>(cf, clips[i].n_frames) + ENC_RUN - 1) / ENC_RUN + 1);
+        if ((rc = m3s_buf_reserve(h, h->e_work, sizeof(M3sEncWork) * max_work))) return rc;
+    }
 
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 7 CTAs x 24 KB per SM
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
     std::vector<M3sEncWork> work;
     std::vector<int32_t> frame_clip;
     std::vector<M3sEncClip> cclips(n_clips);
     // host staging: per chunk every clip owns a region of cf * 1152 + 1056 stereo samples (1056 = the analysis history the
-    // first granule of the chunk reaches back to: 480 window taps + one warm-up granule), two regions sets for double buffering
+    // first granule of the chunk reaches back to: 480 window taps + one warm-up granule), two region sets for double buffering
     const int64_t region = cf * 1152 + 1056;
     const size_t stage_bytes = host ? (size_t)n_clips * (size_t)region * 4 : 0;
     if (host && (rc = m3s_buf_reserve(h, h->e_pcm, 2 * stage_bytes + 16))) return rc;
     std::vector<M3sRow> rows;
     bool free_recorded[2] = {false, false};
-    auto stage_chunk = [&](int64_t c0, int buf) -> cudaError_t {   // H2D of the PCM that chunk [c0, c0 + cf) reads
+    auto frames_in_chunk = [&](int i, int64_t c0) { return std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0)); };
+    auto stage_chunk = [&](int64_t k) -> cudaError_t {   // H2D of the PCM that chunk k reads, into staging set k & 1
+        const int64_t c0 = k * cf;
+        const int pb = (int)(k & 1);
         rows.clear();
         for (int i = 0; i < n_clips; i++) {
-            const int64_t nfc = std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0));
+            const int64_t nfc = frames_in_chunk(i, c0);
             if (nfc == 0) continue;
             const int64_t first = c0 * 1152 - 1056, s0 = std::max<int64_t>(first, 0), s1 = (c0 + nfc) * 1152;
             M3sRow r;
-            r.dst = (char *)h->e_pcm.p + (size_t)buf * stage_bytes + ((size_t)i * region + (size_t)(s0 - first)) * 4;
+            r.dst = (char *)h->e_pcm.p + (size_t)pb * stage_bytes + ((size_t)i * region + (size_t)(s0 - first)) * 4;
             r.src = (const char *)pcm + clips[i].pcm_base * 2 + s0 * 4;
             r.bytes = (size_t)(s1 - s0) * 4;
             rows.push_back(r);
         }
         cudaError_t e = cudaSuccess;
-        if (free_recorded[buf]) e = cudaStreamWaitEvent(h->copy_in, h->ev_free[buf], 0);
+        if (free_recorded[pb]) e = cudaStreamWaitEvent(h->copy_in, h->ev_free[pb], 0);
         if (e == cudaSuccess) e = m3s_copy_rows(rows, cudaMemcpyHostToDevice, h->copy_in);
-        if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[buf], h->copy_in);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[pb], h->copy_in);
         return e;
     };
-    if (host) M3S_CUDA(h, stage_chunk(0, 0));
-    int chunk_idx = 0;
-    for (int64_t c0 = 0; c0 < max_frames; c0 += cf, chunk_idx++) {
-        // frames [c0, c0 + cf) of every clip; within the chunk buffers clip i's frames start at chunk-local base
-        const int buf = chunk_idx & 1;
+    // E1 of chunk k on the aux stream: descriptors, (staged) PCM, kernel; ev_ana[k & 1] = spectra + statistics of the chunk are ready
+    auto launch_analysis = [&](int64_t k) -> int {
+        const int64_t c0 = k * cf;
+        const int pb = (int)(k & 1);
         work.clear();
-        frame_clip.clear();
-        int64_t base = 0;
         cclips = clips;
+        int64_t base = 0;
         for (int i = 0; i < n_clips; i++) {
-            const int64_t nfc = std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0));
+            const int64_t nfc = frames_in_chunk(i, c0);
             // chunk-local frame slot of clip frame f is  base + (f - c0)  ==  (frame_base' + f) - chunk_frame0 with frame_base' = base - c0, chunk_frame0 = 0
             cclips[i].frame_base = base - c0;
-            // staged PCM: sample t of the clip sits at  region * i + t - (c0 * 1152 - 1056)  of this chunk's staging buffer
+            // staged PCM: sample t of the clip sits at  region * i + t - (c0 * 1152 - 1056)  of this chunk's staging set
             if (host) cclips[i].pcm_base = 2 * ((int64_t)i * region - (c0 * 1152 - 1056));
             for (int64_t g = 2 * c0; g < 2 * (c0 + nfc); g += ENC_RUN) {
                 M3sEncWork w;
-                w.clip = i; w.g_first = (int32_t)g; w.count = (int32_t)std::min<int64_t>(ENC_RUN, 2 * (c0 + nfc) - g); w.pad = 0;
-                work.push_back(w);
+                w.clip = i; w.g_first = (int32_t)g; w.count = (int32_t)std::min<int64_t>(ENC_RUN, 2 * (c0 + nfc) - g);
+                w.ch = 0; work.push_back(w);
+                w.ch = 1; work.push_back(w);
             }
-            for (int64_t k = 0; k < nfc; k++) frame_clip.push_back(i);
             base += nfc;
         }
-        const int64_t chunk_total = base;
-        if (chunk_total == 0) break;
-        if ((rc = m3s_buf_reserve(h, h->e_work, sizeof(M3sEncWork) * work.size()))) return rc;
-        M3S_CUDA(h, cudaMemcpyAsync(h->e_work.p, work.data(), sizeof(M3sEncWork) * work.size(), cudaMemcpyHostToDevice, h->stream));
-        M3S_CUDA(h, cudaMemcpyAsync(h->e_misc.p, frame_clip.data(), sizeof(int32_t) * frame_clip.size(), cudaMemcpyHostToDevice, h->stream));
-        M3S_CUDA(h, cudaMemcpyAsync(h->e_clips.p, cclips.data(), sizeof(M3sEncClip) * n_clips, cudaMemcpyHostToDevice, h->stream));
-        // next chunk's PCM rides under this chunk's kernels; queued AFTER the descriptor copies above so that they (and the
-        // kernels behind them) do not wait for it in the copy engine
-        if (host && c0 + cf < max_frames) M3S_CUDA(h, stage_chunk(c0 + cf, buf ^ 1));
+        if (work.empty()) return M3S_OK;
+        M3sBuf &bc = pb ? h->e_clips2 : h->e_clips;
+        M3S_CUDA(h, cudaMemcpyAsync(bc.p, cclips.data(), sizeof(M3sEncClip) * n_clips, cudaMemcpyHostToDevice, h->aux));
+        M3S_CUDA(h, cudaMemcpyAsync(h->e_work.p, work.data(), sizeof(M3sEncWork) * work.size(), cudaMemcpyHostToDevice, h->aux));
         const int16_t *k_pcm = d_pcm;
         if (host) {
-            k_pcm = (const int16_t *)((const char *)h->e_pcm.p + (size_t)buf * stage_bytes);
-            M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[buf], 0));
+            k_pcm = (const int16_t *)((const char *)h->e_pcm.p + (size_t)pb * stage_bytes);
+            M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_in[pb], 0));
         }
+        h->launch_stream = h->aux;
         M3S_KBEGIN(h, M3S_K_ENC_ANALYSIS);
-        k_enc_analysis<<<(unsigned)work.size(), ANA_THREADS, 0, h->stream>>>(
-            k_pcm, (const M3sEncClip *)h->e_clips.p, (const M3sEncWork *)h->e_work.p, h->d_tab, (const EncTables *)h->e_tabs.p, sri, 0,
-            (int32_t *)h->e_mdct.p, (M3sEncStats *)h->e_gran.p);
+        k_enc_analysis<<<(unsigned)work.size(), ANA_THREADS, 0, h->aux>>>(
+            k_pcm, (const M3sEncClip *)bc.p, (const M3sEncWork *)h->e_work.p, h->d_tab, (const EncTables *)h->e_tabs.p, sri, 0,
+            (int32_t *)(pb ? h->e_mdct2.p : h->e_mdct.p), (M3sEncStats *)(pb ? h->e_gran2.p : h->e_gran.p));
         M3S_LAUNCH_CHECK(h);
+        h->launch_stream = nullptr;
+        M3S_CUDA(h, cudaEventRecord(h->ev_ana[pb], h->aux));
         if (host) {
-            M3S_CUDA(h, cudaEventRecord(h->ev_free[buf], h->stream));   // the staging buffer may be refilled once the analysis has read it
-            free_recorded[buf] = true;
+            M3S_CUDA(h, cudaEventRecord(h->ev_free[pb], h->aux));   // the staging set may be refilled once the analysis has read it
+            free_recorded[pb] = true;
         }
+        return M3S_OK;
+    };
+    // ---- software pipeline over the chunks (frames [k cf, (k+1) cf) of every clip):
+    //        copy_in   PCM of chunk k+2          (host buffers only)
+    //        aux       analysis of chunk k+1     fills the issue slots the latency-bound rate loop leaves idle
+    //        stream    rate loop + packing of chunk k
+    //        copy_out  MP3 bytes of chunk k      (host buffers only)
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));   // inputs uploaded above (payload, padding table, state) are visible to aux
+    if (host) {
+        M3S_CUDA(h, stage_chunk(0));
+        if (n_chunks > 1) M3S_CUDA(h, stage_chunk(1));
+    }
+    if ((rc = launch_analysis(0))) return rc;
+    for (int64_t k = 0; k < n_chunks; k++) {
+        const int64_t c0 = k * cf;
+        const int pb = (int)(k & 1);
+        frame_clip.clear();
+        for (int i = 0; i < n_clips; i++) {
+            const int64_t nfc = frames_in_chunk(i, c0);
+            for (int64_t q = 0; q < nfc; q++) frame_clip.push_back(i);
+        }
+        const int64_t chunk_total = (int64_t)frame_clip.size();
+        if (chunk_total == 0) break;
+        const M3sEncClip *d_clips = (const M3sEncClip *)(pb ? h->e_clips2.p : h->e_clips.p);
+        const int32_t *d_mdct = (const int32_t *)(pb ? h->e_mdct2.p : h->e_mdct.p);
+        const M3sEncStats *d_gran = (const M3sEncStats *)(pb ? h->e_gran2.p : h->e_gran.p);
+        M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ana[pb], 0));
         M3S_KBEGIN(h, M3S_K_ENC_RATE);
         k_enc_rate<<<(unsigned)n_clips, 32 * RATE_WARPS, sizeof(RateSmem), h->stream>>>(
-            (const M3sEncClip *)h->e_clips.p, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p,
+            d_clips, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p,
             (const uint32_t *)h->e_pad.p, (const uint8_t *)h->e_payload.p, sri, whole, (int32_t)c0, (int32_t)cf, 0,
-            (const int32_t *)h->e_mdct.p, (const M3sEncStats *)h->e_gran.p, (uint32_t *)h->e_ix.p, (int32_t *)h->e_info.p,
-            (uint8_t *)h->e_scfsi.p, (uint32_t *)h->e_lastix.p);
+            d_mdct, d_gran, (uint32_t *)h->e_ix.p, (int32_t *)h->e_info.p, (uint8_t *)h->e_scfsi.p, (uint32_t *)h->e_lastix.p);
         M3S_LAUNCH_CHECK(h);
+        // queued behind the rate loop's CTAs on purpose: the next chunk's analysis takes what they leave free
+        if (k + 1 < n_chunks && (rc = launch_analysis(k + 1))) return rc;
+        if (host && k + 2 < n_chunks) M3S_CUDA(h, stage_chunk(k + 2));
+        M3S_CUDA(h, cudaMemcpyAsync(h->e_misc.p, frame_clip.data(), sizeof(int32_t) * frame_clip.size(), cudaMemcpyHostToDevice, h->stream));
         M3S_KBEGIN(h, M3S_K_ENC_PACK);
         k_enc_pack<<<(unsigned)((chunk_total + PACK_WARPS - 1) / PACK_WARPS), 32 * PACK_WARPS, sizeof(PackSmem), h->stream>>>(
-            (const M3sEncClip *)h->e_clips.p, (const int32_t *)h->e_misc.p, h->d_tab, (const uint32_t *)h->e_pad.p, sri, bri, whole, 0,
+            d_clips, (const int32_t *)h->e_misc.p, h->d_tab, (const uint32_t *)h->e_pad.p, sri, bri, whole, 0,
             chunk_total, (const uint32_t *)h->e_ix.p, (const int32_t *)h->e_info.p, (const uint8_t *)h->e_scfsi.p, d_out);
         M3S_LAUNCH_CHECK(h);
         if (host) {
@@ -1098,7 +1132,7 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
             M3S_CUDA(h, cudaStreamWaitEvent(h->copy_out, h->ev_done, 0));
             rows.clear();
             for (int i = 0; i < n_clips; i++) {
-                const int64_t nfc = std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0));
+                const int64_t nfc = frames_in_chunk(i, c0);
                 if (nfc == 0) continue;
                 const int64_t b0 = byteoff[c0], b1 = std::min<int64_t>(byteoff[c0 + nfc], clips[i].out_len);
                 if (b1 <= b0) continue;
@@ -1110,9 +1144,10 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
             }
             M3S_CUDA(h, m3s_copy_rows(rows, cudaMemcpyDeviceToHost, h->copy_out));
         }
-        // the host vectors above are reused by the next chunk: their copies must have been consumed
+        // the next iteration rewrites buffers this chunk's kernels read (ix, info, the other spectra set)
         M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     }
+    M3S_CUDA(h, cudaStreamSynchronize(h->aux));
     // ---- results
     std::vector<M3sEncState> states(n_clips);
     M3S_CUDA(h, cudaMemcpyAsync(states.data(), h->e_state.p, sizeof(M3sEncState) * n_clips, cudaMemcpyDeviceToHost, h->stream));
