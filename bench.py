@@ -265,7 +265,7 @@ def run_product_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     h = _lib.Handle(local)
-    stream = torch.cuda.Stream(device=dev)   # the library launches on this stream, and so do the timing events
+    stream = torch.cuda.Stream(device=dev, priority=-1)   # the library launches on this stream, and so do the timing events
     h.set_stream(stream.cuda_stream)
 
     # ---- corpus: per-rank shard of files (weak scaling: every rank holds `files` files)

@@ -161,7 +161,7 @@ struct m3s_ctx {
     cudaEvent_t ev_pace[3] = {nullptr, nullptr, nullptr};   // m3s_copy_paced
     // encoder: the analysis of chunk k+1 runs on `aux` next to the rate loop of chunk k (ev_ana[buf] = its spectra are ready)
     cudaStream_t aux = nullptr, launch_stream = nullptr;   // launch_stream: where the kernel being timed is launched (NULL = stream)
-    cudaEvent_t ev_ana[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ana[2] = {nullptr, nullptr}, ev_rate[2] = {nullptr, nullptr}, ev_pack[2] = {nullptr, nullptr};
     std::string err;
     int64_t launches = 0;
     // ---- optional per-kernel device timing (m3s_timing_enable): cudaEvent pairs on the launching stream
@@ -192,7 +192,7 @@ struct m3s_ctx {
     M3sBuf b_stage_in, b_files, b_tmp_pos, b_fr_pos, b_fr_P, b_fr_meta, b_fr_carry, b_fr_reveal, b_fr_file;
     M3sBuf b_units, b_sf, b_S, b_spec, b_tabids, b_reveal, b_work, b_pcm_stage, b_spec_export;
     // ---- encode state
-    M3sBuf e_clips2, e_mdct2, e_gran2;   // second set of the buffers the analysis writes ahead
+    M3sBuf e_clips2, e_mdct2, e_gran2, e_ix2, e_info2, e_scfsi2;   // second set of the buffers the analysis writes ahead
     M3sBuf e_pcm, e_clips, e_mdct, e_ix, e_info, e_gran, e_out, e_payload, e_misc, e_pad, e_tabs, e_state, e_lastix, e_scfsi, e_work;
     bool enc_taps_ok = false;
     int64_t enc_chunk_budget = 0;   // frames of intermediates kept per chunk (0 = default; M3S_ENC_CHUNK_FRAMES overrides)

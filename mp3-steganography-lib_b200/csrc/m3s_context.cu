@@ -248,7 +248,9 @@ extern "C" int m3s_create(int device, m3s_handle_t *out)
         return M3S_ERR_NO_DEVICE;
     }
     h->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // the main stream outranks the helper streams (aux analysis, copies)
+    if (cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         delete h;
         return M3S_ERR_CUDA;
     }
@@ -302,7 +304,11 @@ int m3s_pipeline_init(m3s_ctx *h)
     M3S_CUDA(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
     M3S_CUDA(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
     M3S_CUDA(h, cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_ana[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_ana[i], cudaEventDisableTiming));
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_rate[i], cudaEventDisableTiming));
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_pack[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; i++) {
         M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
@@ -387,7 +393,7 @@ extern "C" int m3s_destroy(m3s_handle_t h)
                       &h->b_fr_reveal, &h->b_fr_file, &h->b_units, &h->b_sf, &h->b_S, &h->b_spec, &h->b_tabids,
                       &h->b_reveal, &h->b_work, &h->b_pcm_stage, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
                       &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad, &h->e_tabs, &h->e_state,
-                      &h->e_lastix, &h->e_scfsi, &h->e_work, &h->e_clips2, &h->e_mdct2, &h->e_gran2};
+                      &h->e_lastix, &h->e_scfsi, &h->e_work, &h->e_clips2, &h->e_mdct2, &h->e_gran2, &h->e_ix2, &h->e_info2, &h->e_scfsi2};
     for (M3sBuf *b : bufs) free_buf(*b);
     if (h->fouts_mapped) cudaFreeHost(h->fouts_mapped);
     if (h->rev_mapped) cudaFreeHost(h->rev_mapped);
@@ -399,7 +405,7 @@ extern "C" int m3s_destroy(m3s_handle_t h)
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->aux) cudaStreamDestroy(h->aux);
     for (int i = 0; i < 2; i++)
-        if (h->ev_ana[i]) cudaEventDestroy(h->ev_ana[i]);
+        if (h->ev_ana[i]) { cudaEventDestroy(h->ev_ana[i]); cudaEventDestroy(h->ev_rate[i]); cudaEventDestroy(h->ev_pack[i]); }
     for (int i = 0; i < 2; i++) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
         if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
@@ -465,7 +471,7 @@ void m3s_time_end(m3s_ctx *h)
 static void timing_resolve(m3s_ctx *h)
 {
     cudaStreamSynchronize(h->stream);
-    if (h->aux) cudaStreamSynchronize(h->aux);
+    if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamSynchronize(h->copy_out); }
     for (auto &t : h->timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) h->k_ms[t.id] += ms;

@@ -661,7 +661,7 @@ k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ state
 // ================================================================================================
 // E3: bit packing, one warp per frame
 // ================================================================================================
-#define PACK_WARPS 8
+#define PACK_WARPS 2
 #define PACK_WORDS 364   // >= 1441 bytes (320 kbps at 32 kHz, padded)
 
 struct PackSmem {
@@ -974,8 +974,6 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     }
     if ((rc = m3s_buf_reserve(h, h->e_payload, (size_t)pay_total + 16))) return rc;
     if (pay_total > 0) M3S_CUDA(h, cudaMemcpyAsync(h->e_payload.p, payload_bits, (size_t)pay_total, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = m3s_buf_reserve(h, h->e_clips, sizeof(M3sEncClip) * n_clips))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->e_clips2, sizeof(M3sEncClip) * n_clips))) return rc;
     if ((rc = m3s_buf_reserve(h, h->e_pad, sizeof(uint32_t) * byteoff.size()))) return rc;
     M3S_CUDA(h, cudaMemcpyAsync(h->e_pad.p, byteoff.data(), sizeof(uint32_t) * byteoff.size(), cudaMemcpyHostToDevice, h->stream));
     if ((rc = m3s_buf_reserve(h, h->e_state, sizeof(M3sEncState) * n_clips))) return rc;
@@ -991,37 +989,66 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     int64_t chunk_cap = 0;
     for (int i = 0; i < n_clips; i++) chunk_cap += std::min<int64_t>(cf, clips[i].n_frames);
     const int64_t n_chunks = (max_frames + cf - 1) / cf;
-    if ((rc = m3s_buf_reserve(h, h->e_mdct, (size_t)chunk_cap * 4 * 576 * 4))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->e_gran, (size_t)chunk_cap * 4 * sizeof(M3sEncStats)))) return rc;
-    if (n_chunks > 1) {   // the analysis of chunk k+1 writes the second set while the rate loop of chunk k reads the first
-        if ((rc = m3s_buf_reserve(h, h->e_mdct2, (size_t)chunk_cap * 4 * 576 * 4))) return rc;
-        if ((rc = m3s_buf_reserve(h, h->e_gran2, (size_t)chunk_cap * 4 * sizeof(M3sEncStats)))) return rc;
-    }
-    if ((rc = m3s_buf_reserve(h, h->e_ix, (size_t)chunk_cap * 4 * 288 * 4))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->e_info, (size_t)chunk_cap * 4 * ENC_INFO_FIELDS * 4))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->e_scfsi, (size_t)chunk_cap * 8))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->e_misc, (size_t)chunk_cap * 4))) return rc;
-    {
-        size_t max_work = 0;
-        for (int i = 0; i < n_clips; i++) max_work += 2 * (size_t)((2 * std::min<int64_t>(cf, clips[i].n_frames) + ENC_RUN - 1) / ENC_RUN + 1);
-        if ((rc = m3s_buf_reserve(h, h->e_work, sizeof(M3sEncWork) * max_work))) return rc;
+    const int nset = n_chunks > 1 ? 2 : 1;   // every per-chunk intermediate exists twice: chunk k uses set k & 1
+    M3sBuf *b_mdct[2] = {&h->e_mdct, &h->e_mdct2}, *b_gran[2] = {&h->e_gran, &h->e_gran2}, *b_ix[2] = {&h->e_ix, &h->e_ix2};
+    M3sBuf *b_info[2] = {&h->e_info, &h->e_info2}, *b_scfsi[2] = {&h->e_scfsi, &h->e_scfsi2};
+    for (int q = 0; q < nset; q++) {
+        if ((rc = m3s_buf_reserve(h, *b_mdct[q], (size_t)chunk_cap * 4 * 576 * 4))) return rc;
+        if ((rc = m3s_buf_reserve(h, *b_gran[q], (size_t)chunk_cap * 4 * sizeof(M3sEncStats)))) return rc;
+        if ((rc = m3s_buf_reserve(h, *b_ix[q], (size_t)chunk_cap * 4 * 288 * 4))) return rc;
+        if ((rc = m3s_buf_reserve(h, *b_info[q], (size_t)chunk_cap * 4 * ENC_INFO_FIELDS * 4))) return rc;
+        if ((rc = m3s_buf_reserve(h, *b_scfsi[q], (size_t)chunk_cap * 8))) return rc;
     }
 
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 7 CTAs x 24 KB per SM
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
-    std::vector<M3sEncWork> work;
-    std::vector<int32_t> frame_clip;
-    std::vector<M3sEncClip> cclips(n_clips);
+    auto frames_in_chunk = [&](int i, int64_t c0) { return std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0)); };
     // host staging: per chunk every clip owns a region of cf * 1152 + 1056 stereo samples (1056 = the analysis history the
     // first granule of the chunk reaches back to: 480 window taps + one warm-up granule), two region sets for double buffering
     const int64_t region = cf * 1152 + 1056;
     const size_t stage_bytes = host ? (size_t)n_clips * (size_t)region * 4 : 0;
     if (host && (rc = m3s_buf_reserve(h, h->e_pcm, 2 * stage_bytes + 16))) return rc;
+    // ---- descriptors of ALL chunks go up once, so that the chunk loop below issues no small copy (a pageable copy blocks the host
+    //      until its stream gets there, which would serialise the streams of the pipeline)
+    std::vector<M3sEncWork> work;          // E1 work items, chunk k = [work_off[k], work_off[k+1])
+    std::vector<int32_t> frame_clip;       // clip index of every chunk-local frame slot, chunk k = [slot_off[k], slot_off[k+1])
+    std::vector<M3sEncClip> cclips((size_t)n_clips * n_chunks);   // chunk-local clip records
+    std::vector<int64_t> work_off(n_chunks + 1, 0), slot_off(n_chunks + 1, 0);
+    for (int64_t k = 0; k < n_chunks; k++) {
+        const int64_t c0 = k * cf;
+        int64_t base = 0;
+        for (int i = 0; i < n_clips; i++) {
+            const int64_t nfc = frames_in_chunk(i, c0);
+            M3sEncClip &cc = cclips[(size_t)k * n_clips + i];
+            cc = clips[i];
+            // chunk-local frame slot of clip frame f is  base + (f - c0)  ==  (frame_base' + f) - chunk_frame0 with frame_base' = base - c0, chunk_frame0 = 0
+            cc.frame_base = base - c0;
+            // staged PCM: sample t of the clip sits at  region * i + t - (c0 * 1152 - 1056)  of this chunk's staging set
+            if (host) cc.pcm_base = 2 * ((int64_t)i * region - (c0 * 1152 - 1056));
+            for (int64_t g = 2 * c0; g < 2 * (c0 + nfc); g += ENC_RUN) {
+                M3sEncWork w;
+                w.clip = i; w.g_first = (int32_t)g; w.count = (int32_t)std::min<int64_t>(ENC_RUN, 2 * (c0 + nfc) - g);
+                w.ch = 0; work.push_back(w);
+                w.ch = 1; work.push_back(w);
+            }
+            for (int64_t q = 0; q < nfc; q++) frame_clip.push_back(i);
+            base += nfc;
+        }
+        work_off[k + 1] = (int64_t)work.size();
+        slot_off[k + 1] = (int64_t)frame_clip.size();
+    }
+    if ((rc = m3s_buf_reserve(h, h->e_work, sizeof(M3sEncWork) * work.size()))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->e_misc, sizeof(int32_t) * frame_clip.size()))) return rc;
+    if ((rc = m3s_buf_reserve(h, h->e_clips, sizeof(M3sEncClip) * cclips.size()))) return rc;
+    M3S_CUDA(h, cudaMemcpyAsync(h->e_work.p, work.data(), sizeof(M3sEncWork) * work.size(), cudaMemcpyHostToDevice, h->stream));
+    M3S_CUDA(h, cudaMemcpyAsync(h->e_misc.p, frame_clip.data(), sizeof(int32_t) * frame_clip.size(), cudaMemcpyHostToDevice, h->stream));
+    M3S_CUDA(h, cudaMemcpyAsync(h->e_clips.p, cclips.data(), sizeof(M3sEncClip) * cclips.size(), cudaMemcpyHostToDevice, h->stream));
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));   // everything uploaded so far (payload, padding table, state, descriptors) is visible to every stream
+
     std::vector<M3sRow> rows;
     bool free_recorded[2] = {false, false};
-    auto frames_in_chunk = [&](int i, int64_t c0) { return std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0)); };
     auto stage_chunk = [&](int64_t k) -> cudaError_t {   // H2D of the PCM that chunk k reads, into staging set k & 1
         const int64_t c0 = k * cf;
         const int pb = (int)(k & 1);
@@ -1042,41 +1069,25 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[pb], h->copy_in);
         return e;
     };
-    // E1 of chunk k on the aux stream: descriptors, (staged) PCM, kernel; ev_ana[k & 1] = spectra + statistics of the chunk are ready
+    // E1 of chunk k on the aux stream; ev_ana[k & 1] = spectra + statistics of the chunk are ready
     auto launch_analysis = [&](int64_t k) -> int {
-        const int64_t c0 = k * cf;
         const int pb = (int)(k & 1);
-        work.clear();
-        cclips = clips;
-        int64_t base = 0;
-        for (int i = 0; i < n_clips; i++) {
-            const int64_t nfc = frames_in_chunk(i, c0);
-            // chunk-local frame slot of clip frame f is  base + (f - c0)  ==  (frame_base' + f) - chunk_frame0 with frame_base' = base - c0, chunk_frame0 = 0
-            cclips[i].frame_base = base - c0;
-            // staged PCM: sample t of the clip sits at  region * i + t - (c0 * 1152 - 1056)  of this chunk's staging set
-            if (host) cclips[i].pcm_base = 2 * ((int64_t)i * region - (c0 * 1152 - 1056));
-            for (int64_t g = 2 * c0; g < 2 * (c0 + nfc); g += ENC_RUN) {
-                M3sEncWork w;
-                w.clip = i; w.g_first = (int32_t)g; w.count = (int32_t)std::min<int64_t>(ENC_RUN, 2 * (c0 + nfc) - g);
-                w.ch = 0; work.push_back(w);
-                w.ch = 1; work.push_back(w);
-            }
-            base += nfc;
-        }
-        if (work.empty()) return M3S_OK;
-        M3sBuf &bc = pb ? h->e_clips2 : h->e_clips;
-        M3S_CUDA(h, cudaMemcpyAsync(bc.p, cclips.data(), sizeof(M3sEncClip) * n_clips, cudaMemcpyHostToDevice, h->aux));
-        M3S_CUDA(h, cudaMemcpyAsync(h->e_work.p, work.data(), sizeof(M3sEncWork) * work.size(), cudaMemcpyHostToDevice, h->aux));
+        const int64_t nw = work_off[k + 1] - work_off[k];
+        if (nw == 0) return M3S_OK;
         const int16_t *k_pcm = d_pcm;
         if (host) {
             k_pcm = (const int16_t *)((const char *)h->e_pcm.p + (size_t)pb * stage_bytes);
             M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_in[pb], 0));
         }
+        // chunk k-2 has left this spectra set (rate loop read it, frames packed).  Waiting for its PACK -- the last kernel in front of
+        // the rate loop of chunk k-1 on the main stream -- also lets that rate loop's CTAs take their SM slots first: the analysis
+        // then fills what is left instead of crowding the critical chain out
+        if (k >= 2) M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_pack[pb], 0));
         h->launch_stream = h->aux;
         M3S_KBEGIN(h, M3S_K_ENC_ANALYSIS);
-        k_enc_analysis<<<(unsigned)work.size(), ANA_THREADS, 0, h->aux>>>(
-            k_pcm, (const M3sEncClip *)bc.p, (const M3sEncWork *)h->e_work.p, h->d_tab, (const EncTables *)h->e_tabs.p, sri, 0,
-            (int32_t *)(pb ? h->e_mdct2.p : h->e_mdct.p), (M3sEncStats *)(pb ? h->e_gran2.p : h->e_gran.p));
+        k_enc_analysis<<<(unsigned)nw, ANA_THREADS, 0, h->aux>>>(
+            k_pcm, (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips, (const M3sEncWork *)h->e_work.p + work_off[k], h->d_tab,
+            (const EncTables *)h->e_tabs.p, sri, 0, (int32_t *)b_mdct[pb]->p, (M3sEncStats *)b_gran[pb]->p);
         M3S_LAUNCH_CHECK(h);
         h->launch_stream = nullptr;
         M3S_CUDA(h, cudaEventRecord(h->ev_ana[pb], h->aux));
@@ -1086,12 +1097,11 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         }
         return M3S_OK;
     };
-    // ---- software pipeline over the chunks (frames [k cf, (k+1) cf) of every clip):
-    //        copy_in   PCM of chunk k+2          (host buffers only)
-    //        aux       analysis of chunk k+1     fills the issue slots the latency-bound rate loop leaves idle
-    //        stream    rate loop + packing of chunk k
-    //        copy_out  MP3 bytes of chunk k      (host buffers only)
-    M3S_CUDA(h, cudaStreamSynchronize(h->stream));   // inputs uploaded above (payload, padding table, state) are visible to aux
+    // ---- software pipeline over the chunks (frames [k cf, (k+1) cf) of every clip); nothing in the loop blocks the host:
+    //        copy_in   PCM of chunk k+2                       (host buffers only)
+    //        aux       analysis of chunk k+1                  fills the issue slots the latency-bound rate loop leaves idle
+    //        stream    rate loop + packing of chunk k         the critical path: back to back, chunk after chunk
+    //        copy_out  MP3 bytes of chunk k                   (host buffers only)
     if (host) {
         M3S_CUDA(h, stage_chunk(0));
         if (n_chunks > 1) M3S_CUDA(h, stage_chunk(1));
@@ -1100,36 +1110,30 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     for (int64_t k = 0; k < n_chunks; k++) {
         const int64_t c0 = k * cf;
         const int pb = (int)(k & 1);
-        frame_clip.clear();
-        for (int i = 0; i < n_clips; i++) {
-            const int64_t nfc = frames_in_chunk(i, c0);
-            for (int64_t q = 0; q < nfc; q++) frame_clip.push_back(i);
-        }
-        const int64_t chunk_total = (int64_t)frame_clip.size();
+        const int64_t chunk_total = slot_off[k + 1] - slot_off[k];
         if (chunk_total == 0) break;
-        const M3sEncClip *d_clips = (const M3sEncClip *)(pb ? h->e_clips2.p : h->e_clips.p);
-        const int32_t *d_mdct = (const int32_t *)(pb ? h->e_mdct2.p : h->e_mdct.p);
-        const M3sEncStats *d_gran = (const M3sEncStats *)(pb ? h->e_gran2.p : h->e_gran.p);
+        const M3sEncClip *d_clips = (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips;
         M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ana[pb], 0));
         M3S_KBEGIN(h, M3S_K_ENC_RATE);
         k_enc_rate<<<(unsigned)n_clips, 32 * RATE_WARPS, sizeof(RateSmem), h->stream>>>(
             d_clips, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p,
             (const uint32_t *)h->e_pad.p, (const uint8_t *)h->e_payload.p, sri, whole, (int32_t)c0, (int32_t)cf, 0,
-            d_mdct, d_gran, (uint32_t *)h->e_ix.p, (int32_t *)h->e_info.p, (uint8_t *)h->e_scfsi.p, (uint32_t *)h->e_lastix.p);
+            (const int32_t *)b_mdct[pb]->p, (const M3sEncStats *)b_gran[pb]->p, (uint32_t *)b_ix[pb]->p, (int32_t *)b_info[pb]->p,
+            (uint8_t *)b_scfsi[pb]->p, (uint32_t *)h->e_lastix.p);
         M3S_LAUNCH_CHECK(h);
+        M3S_CUDA(h, cudaEventRecord(h->ev_rate[pb], h->stream));
         // queued behind the rate loop's CTAs on purpose: the next chunk's analysis takes what they leave free
         if (k + 1 < n_chunks && (rc = launch_analysis(k + 1))) return rc;
         if (host && k + 2 < n_chunks) M3S_CUDA(h, stage_chunk(k + 2));
-        M3S_CUDA(h, cudaMemcpyAsync(h->e_misc.p, frame_clip.data(), sizeof(int32_t) * frame_clip.size(), cudaMemcpyHostToDevice, h->stream));
+        // packing stays on the rate loop's stream: next to the analysis it would only slow the critical chain further
         M3S_KBEGIN(h, M3S_K_ENC_PACK);
         k_enc_pack<<<(unsigned)((chunk_total + PACK_WARPS - 1) / PACK_WARPS), 32 * PACK_WARPS, sizeof(PackSmem), h->stream>>>(
-            d_clips, (const int32_t *)h->e_misc.p, h->d_tab, (const uint32_t *)h->e_pad.p, sri, bri, whole, 0,
-            chunk_total, (const uint32_t *)h->e_ix.p, (const int32_t *)h->e_info.p, (const uint8_t *)h->e_scfsi.p, d_out);
+            d_clips, (const int32_t *)h->e_misc.p + slot_off[k], h->d_tab, (const uint32_t *)h->e_pad.p, sri, bri, whole, 0,
+            chunk_total, (const uint32_t *)b_ix[pb]->p, (const int32_t *)b_info[pb]->p, (const uint8_t *)b_scfsi[pb]->p, d_out);
         M3S_LAUNCH_CHECK(h);
-        if (host) {
-            // this chunk's bytes of every clip go home behind the pack kernel, under the next chunk's kernels
-            M3S_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
-            M3S_CUDA(h, cudaStreamWaitEvent(h->copy_out, h->ev_done, 0));
+        M3S_CUDA(h, cudaEventRecord(h->ev_pack[pb], h->stream));
+        if (host) {   // this chunk's bytes of every clip go home behind the pack kernel
+            M3S_CUDA(h, cudaStreamWaitEvent(h->copy_out, h->ev_pack[pb], 0));
             rows.clear();
             for (int i = 0; i < n_clips; i++) {
                 const int64_t nfc = frames_in_chunk(i, c0);
@@ -1144,15 +1148,15 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
             }
             M3S_CUDA(h, m3s_copy_rows(rows, cudaMemcpyDeviceToHost, h->copy_out));
         }
-        // the next iteration rewrites buffers this chunk's kernels read (ix, info, the other spectra set)
-        M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     }
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     M3S_CUDA(h, cudaStreamSynchronize(h->aux));
+    M3S_CUDA(h, cudaStreamSynchronize(h->copy_out));
+    if (host) M3S_CUDA(h, cudaStreamSynchronize(h->copy_in));
     // ---- results
     std::vector<M3sEncState> states(n_clips);
     M3S_CUDA(h, cudaMemcpyAsync(states.data(), h->e_state.p, sizeof(M3sEncState) * n_clips, cudaMemcpyDeviceToHost, h->stream));
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (host) M3S_CUDA(h, cudaStreamSynchronize(h->copy_out));
     if (hide_str_offset_out)
         for (int i = 0; i < n_clips; i++) hide_str_offset_out[i] = states[i].hide_off;
     h->enc_taps_ok = single_chunk;
