@@ -692,6 +692,7 @@ struct HybSmem {
     R cos12[12][8];
     R sine[4][36];
     R pow43[256];
+    R scale[4][64];             // per slot: 2^(e4/4) of long sfb 0..21 | short (sfb * 3 + window) at 22..60, rebuilt every frame
     R cs[8], ca[8];
     R quarter[4];
     uint16_t reorder[576];
@@ -709,18 +710,13 @@ __device__ __forceinline__ float pow2i(int e)  // 2^e for e in the normal float 
     return __int_as_float((e + 127) << 23);
 }
 
-// requantize magnitude |x|^(4/3) * 2^(e4/4)   (Frame.py:210-215).  FP32: table / cbrt and exact powers of two;
-// FP64 (the `exact` instantiation used by the single-file facade): double-precision pow for the large values.
-__device__ __forceinline__ float requant_mag(const HybSmem<float> &sm, int ax, int e4)
-{
-    float m = ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax);
-    return m * (sm.quarter[e4 & 3] * pow2i(e4 >> 2));
-}
-__device__ __forceinline__ double requant_mag(const HybSmem<double> &sm, int ax, int e4)
-{
-    const double a = ax < 256 ? sm.pow43[ax] : pow((double)ax, 4.0 / 3.0);
-    return a * (sm.quarter[e4 & 3] * scalbn(1.0, e4 >> 2));
-}
+// requantize (Frame.py:210-215): |x|^(4/3) * 2^(e4/4).  The exponent e4 depends only on the scalefactor band (and window), so the factor
+// 2^(e4/4) = quarter[e4 & 3] * 2^(e4 >> 2) is tabulated once per frame and slot (HybSmem::scale); a sample costs one lookup and one multiply.
+// FP32: |x|^(4/3) from a table / cbrt, exact powers of two; FP64 (the `exact` instantiation): double-precision pow for the large values.
+__device__ __forceinline__ float requant_scale(const HybSmem<float> &sm, int e4) { return sm.quarter[e4 & 3] * pow2i(e4 >> 2); }
+__device__ __forceinline__ double requant_scale(const HybSmem<double> &sm, int e4) { return sm.quarter[e4 & 3] * scalbn(1.0, e4 >> 2); }
+__device__ __forceinline__ float requant_pow43(const HybSmem<float> &sm, int ax) { return ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax); }
+__device__ __forceinline__ double requant_pow43(const HybSmem<double> &sm, int ax) { return ax < 256 ? sm.pow43[ax] : pow((double)ax, 4.0 / 3.0); }
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
@@ -765,6 +761,27 @@ __device__ __forceinline__ void imdct_long(const R (&x)[18], const R *sine_bt, c
             pn[18 * sb + d] = acc * sine_bt[18 + d];
             pn[18 * sb + 17 - d] = acc * sine_bt[35 - d];
         }
+    }
+}
+
+// Windowing of NQ same-parity slots t = par + 2 (q0 + q) for one (channel, lane): pcm[32 t + i] = sum_m V_{t-2m}[i] D[64 m + i] +
+// V_{t-2m-1}[32 + i] D[64 m + 32 + i] (Frame.py:89-101).  Slots of one parity share their V rows (row offset 2 (q - m)), so NQ + 7
+// loads per operand feed NQ x 8 FMAs instead of one load per FMA.  va0 / vb0 point at the rows of q = q0, m = 7.
+template <typename R, int NQ>
+__device__ __forceinline__ void window_tile(const R *__restrict__ va0, const R *__restrict__ vb0, const R (&dA)[8], const R (&dB)[8], R (&out)[5])
+{
+    R a[NQ + 7], b[NQ + 7];
+#pragma unroll
+    for (int d = 0; d < NQ + 7; d++) { a[d] = va0[64 * d]; b[d] = vb0[64 * d]; }
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        R acc0 = (R)0, acc1 = (R)0;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            acc0 = fma_t(a[q - m + 7], dA[m], acc0);
+            acc1 = fma_t(b[q - m + 7], dB[m], acc1);
+        }
+        out[q] = acc0 + acc1;
     }
 }
 
@@ -837,6 +854,20 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
         __syncthreads();
         if (tid == 0) sm.sr_loaded = sr;
         const bool ms = (meta & M3S_META_MS) != 0;
+        {   // scale table: thread = (slot, band index)
+            const int slot = tid >> 6, idx = tid & 63;
+            const M3sUnitRec &r = sm.rec[slot];
+            const uint8_t *sf = sm.sf[slot];
+            const int gg = M3S_UA_GG(r.a), mult4 = M3S_UB_SFSCALE(r.b) ? 4 : 2;
+            int e4 = 0;
+            if (idx < 22) e4 = gg - 210 - mult4 * ((int)sf[idx] + (int)M3S_UB_PREFLAG(r.b) * (int)sm.pretab[idx]);
+            else if (idx < 61) {
+                const int q = idx - 22, sfb = q / 3, wnd = q - 3 * sfb;
+                e4 = gg - 210 - 8 * (int)M3S_UC_SBG(r.c, wnd) - mult4 * (int)sf[M3S_SF_SHORT + 13 * wnd + sfb];
+            }
+            sm.scale[slot][idx] = requant_scale(sm, e4);
+        }
+        __syncthreads();
 
         for (int gr = 0; gr < 2; gr++) {
             // ------------------------------------------------ requantize + MS + reorder (fused)
@@ -848,26 +879,15 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                     if (ch >= nch) { val[ch][0] = val[ch][1] = (R)0; continue; }
                     const int slot = 2 * gr + ch;
                     const uint32_t wv = slot == 0 ? w4.x : (slot == 1 ? w4.y : (slot == 2 ? w4.z : w4.w));
-                    const M3sUnitRec &r = sm.rec[slot];
-                    const uint8_t *sf = sm.sf[slot];
-                    const int gg = M3S_UA_GG(r.a);
-                    const int mult4 = M3S_UB_SFSCALE(r.b) ? 4 : 2;
-                    const bool shortp = M3S_UA_BT(r.a) == 2;
+                    const bool shortp = M3S_UA_BT(sm.rec[slot].a) == 2;
+                    const R *sc = sm.scale[slot];
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int i = 2 * p + h;
-                        int x = (int)(int16_t)(h ? (wv >> 16) : (wv & 0xFFFFu));
-                        int e4;
-                        if (shortp) {
-                            const int q = sm.short_sfw[i];
-                            const int sfb = q / 3, wnd = q - 3 * sfb;
-                            e4 = gg - 210 - 8 * (int)M3S_UC_SBG(r.c, wnd) - mult4 * (int)sf[M3S_SF_SHORT + 13 * wnd + sfb];
-                        } else {
-                            const int sfb = sm.long_sfb[i];
-                            e4 = gg - 210 - mult4 * ((int)sf[sfb] + (int)M3S_UB_PREFLAG(r.b) * (int)sm.pretab[sfb]);
-                        }
+                        const int x = (int)(int16_t)(h ? (wv >> 16) : (wv & 0xFFFFu));
+                        const int idx = shortp ? 22 + (int)sm.short_sfw[i] : (int)sm.long_sfb[i];
                         const int ax = x < 0 ? -x : x;
-                        const R m = requant_mag(sm, ax, e4);
+                        const R m = requant_pow43(sm, ax) * sc[idx];
                         val[ch][h] = x < 0 ? -m : m;
                     }
                 }
@@ -897,7 +917,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
             __syncthreads();
             // ------------------------------------------------ alias reduction (long blocks only)
             for (int aidx = tid; aidx < nch * 248; aidx += HYB_THREADS) {
-                const int ch = aidx / 248, r_ = aidx - ch * 248;
+                const int ch = aidx >= 248, r_ = aidx - 248 * ch;
                 const M3sUnitRec &r = sm.rec[2 * gr + ch];
                 if (M3S_UA_BT(r.a) == 2 || M3S_UB_MIXED(r.b)) continue;
                 const int sb = 1 + (r_ >> 3), i = r_ & 7;
@@ -992,39 +1012,31 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                 __syncwarp();
             }
             __syncthreads();
-            // ------------------------------------------------ windowing + output (lane = sample index within the slot)
-            for (int o = tid; o < 576; o += HYB_THREADS) {
-                const int t = o >> 5;
-                R s[2] = {(R)0, (R)0};
+            // ------------------------------------------------ windowing + output: warp = (channel, slot parity, half of the parity's 9 slots)
+            {
+                const int ch = warp >> 2, par = (warp >> 1) & 1, q0 = (warp & 1) ? 5 : 0, nq = (warp & 1) ? 4 : 5;
+                if (ch < nch) {
+                    R out[5];
+                    const R *va0 = &sm.v[ch][15 + par + 2 * (q0 - 7)][idxA], *vb0 = &sm.v[ch][14 + par + 2 * (q0 - 7)][idxB];
+                    if (warp & 1) window_tile<R, 4>(va0, vb0, dA, dB, out);
+                    else window_tile<R, 5>(va0, vb0, dA, dB, out);
+                    if (emit) {
+                        const int reps = (meta & M3S_META_DUP) ? 2 : 1;
+                        for (int rep = 0; rep < reps; rep++) {
+                            const int64_t row0 = (g - wk.g_first + rep) * 1152 + gr * 576 + lane;
 #pragma unroll
-                for (int ch = 0; ch < 2; ch++) {
-                    if (ch >= nch) continue;
-                    const R *va = &sm.v[ch][15 + t][idxA], *vb = &sm.v[ch][14 + t][idxB];   // fixed offsets from two bases
-                    R acc0 = (R)0, acc1 = (R)0;
-#pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        acc0 = fma_t(va[-64 * m], dA[m], acc0);
-                        acc1 = fma_t(vb[-64 * m], dB[m], acc1);
-                    }
-                    s[ch] = acc0 + acc1;
-                }
-                if (emit) {
-                    const int reps = (meta & M3S_META_DUP) ? 2 : 1;
-                    for (int rep = 0; rep < reps; rep++) {
-                        const int64_t row = (g - wk.g_first + rep) * 1152 + gr * 576 + o;
-                        if (FLOAT_OUT) {
-                            float *po = (float *)pcm_out + wk.pcm_elem + row * nch;
-                            po[0] = (float)s[0];
-                            if (nch == 2) po[1] = (float)s[1];
-                        } else {
-                            // (pcm * 32767).astype(int16): truncate toward zero, keep the low 16 bits (A.D8)
-                            int a0, a1;
-                            if constexpr (sizeof(R) == 4) { a0 = __float2int_rz(s[0] * 32767.f); a1 = __float2int_rz(s[1] * 32767.f); }
-                            else { a0 = __double2int_rz(s[0] * 32767.0); a1 = __double2int_rz(s[1] * 32767.0); }
-                            if (nch == 2)
-                                ((uint32_t *)pcm_out)[(wk.pcm_elem >> 1) + row] = ((uint32_t)a0 & 0xFFFFu) | ((uint32_t)a1 << 16);
-                            else
-                                ((int16_t *)pcm_out)[wk.pcm_elem + row] = (int16_t)(a0 & 0xFFFF);
+                            for (int q = 0; q < 5; q++) {
+                                if (q >= nq) break;
+                                const int64_t e = wk.pcm_elem + (row0 + 32 * (par + 2 * (q0 + q))) * nch + ch;
+                                if (FLOAT_OUT) ((float *)pcm_out)[e] = (float)out[q];
+                                else {
+                                    // (pcm * 32767).astype(int16): truncate toward zero, keep the low 16 bits (A.D8)
+                                    int a;
+                                    if constexpr (sizeof(R) == 4) a = __float2int_rz(out[q] * 32767.f);
+                                    else a = __double2int_rz(out[q] * 32767.0);
+                                    ((int16_t *)pcm_out)[e] = (int16_t)(a & 0xFFFF);
+                                }
+                            }
                         }
                     }
                 }
@@ -1222,7 +1234,13 @@ extern "C" int m3s_decode_reveal(m3s_handle_t h, uint8_t *table_ids, uint8_t *re
     return M3S_OK;
 }
 
-#define M3S_HYB_RUN 32  // frames per CTA run (one warm-up frame per run: ~3% recompute)
+// frames per CTA run of k_hybrid.  Every run pays the CTA's table staging and one warm-up frame (together ~9 % of a 32-frame
+// run), so large batches use long runs; small batches keep runs short enough to fill the SMs (3 CTAs per SM, >= 4 waves of them).
+static int hybrid_run_length(int64_t total_frames, int sm_count)
+{
+    const int64_t want = total_frames / ((int64_t)sm_count * 3 * 4);
+    return (int)std::max<int64_t>(16, std::min<int64_t>(128, want));
+}
 
 extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t *pcm_off, int16_t *spectra, uint32_t flags)
 {
@@ -1239,6 +1257,7 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
     // ---- PCM layout
     int64_t total_elems = 0;
     std::vector<M3sWork> work;
+    const int run = hybrid_run_length(nf, h->sm_count);
     for (int i = 0; i < h->n_files; i++) {
         M3sFileRec &f = h->files[i];
         const int64_t rows = 1152LL * (f.n_frames + ((f.flags & M3S_FILE_TRAILING_JUNK) && f.n_frames > 0 ? 1 : 0));
@@ -1246,10 +1265,10 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
         f.pcm_base = pcm_off ? pcm_off[i] : total_elems;
         if (f.channels == 2 && !fl && (f.pcm_base & 1)) return m3s_fail(h, M3S_ERR_ARG, "decode_run: stereo pcm_off must be even");
         total_elems = std::max(total_elems, f.pcm_base + elems);
-        for (int64_t k = 0; k < f.n_frames; k += M3S_HYB_RUN) {
+        for (int64_t k = 0; k < f.n_frames; k += run) {
             M3sWork w;
             w.g_first = f.frame_base + k;
-            w.count = (int32_t)std::min<int64_t>(M3S_HYB_RUN, f.n_frames - k);
+            w.count = (int32_t)std::min<int64_t>(run, f.n_frames - k);
             w.warm = k > 0 ? 1 : 0;
             w.pcm_elem = f.pcm_base + k * 1152 * f.channels;
             w.channels = f.channels;
