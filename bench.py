@@ -221,7 +221,7 @@ def run_reference_arm(args):
                             "e2e": {"value": enc_f / enc_t, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                             "cpu_baseline": {"value": enc_f / enc_t, "unit": "frames/s", "cores": cores, "kind": "port",
                                              "sample": sample}}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -526,9 +526,31 @@ def run_product_arm(args):
                     "clips": args.files, "frames_per_clip": enc_e2e["frames"]},
             "gpu_launches": E["launches"], "clocks": E["clocks"], "roofline": E["roofline"],
             "cpu_baseline": cpu_obj("encode", "encode+hide @128k")}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, the compiler) write to fd 1; the contract is ONE JSON line there.  Everything but
+    emit() goes to stderr from here on."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -545,6 +567,7 @@ def main():
     ap.add_argument("--e2e-sweep", action="store_true", help="diagnostic sweep of the decode e2e leg (no JSON line)")
     ap.add_argument("--e2e-workers", type=int, default=3, help="host worker threads (one handle each) of the decode e2e leg")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
