@@ -561,7 +561,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--files", type=int, default=1000, help="files per GPU")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_FILE, help="frames per file")
-    ap.add_argument("--wave", type=int, default=250, help="files per wave of the device-resident decode leg (bounds the workspaces)")
+    ap.add_argument("--wave", type=int, default=500, help="files per wave of the device-resident decode leg (bounds the workspaces)")
     ap.add_argument("--e2e-wave", type=int, default=50, help="files per wave of the host-buffer (e2e) decode leg")
     ap.add_argument("--no-encode", action="store_true", help="skip the encode+hide half")
     ap.add_argument("--e2e-sweep", action="store_true", help="diagnostic sweep of the decode e2e leg (no JSON line)")

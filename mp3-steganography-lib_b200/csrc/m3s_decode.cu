@@ -687,7 +687,7 @@ struct HybSmem {
     R xr[2][576];
     R prev[2][2][576];
     R tt[2][18][32];
-    R v[2][33][32];            // the 32 DISTINCT matrixing outputs per slot (see "matrixing"): 15 slots of history + 18 new
+    R v[2][51][32];            // the 32 DISTINCT matrixing outputs per slot (see "matrixing"): 15 slots of history + 2 granules x 18 new
     R uw[HYB_THREADS / 32][32];  // per-warp butterfly scratch: u[0..15] | w[0..15]
     R cos12[12][8];
     R sine[4][36];
@@ -806,7 +806,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
     if (tid < 22) sm.pretab[tid] = T->pretab[tid];
     if (tid == 0) sm.sr_loaded = -1;
     for (int i = tid; i < 2 * 2 * 576; i += HYB_THREADS) (&sm.prev[0][0][0])[i] = (R)0;
-    for (int i = tid; i < 2 * 33 * 32; i += HYB_THREADS) (&sm.v[0][0][0])[i] = (R)0;
+    for (int i = tid; i < 2 * 51 * 32; i += HYB_THREADS) (&sm.v[0][0][0])[i] = (R)0;
     // ---- matrixing (Frame.py:81-87): V[i] = sum_j N[i][j] S[j], N[i][j] = cos((16 + i)(2 j + 1) pi / 64).
     // Two exact symmetries shrink the 64 x 32 product to 32 x 16:
     //   (a) N[i][31 - j] = (-1)^i N[i][j]            -> V[i] = sum_{j<16} N[i][j] (S[j] +- S[31 - j])      (u for even i, w for odd i)
@@ -1008,7 +1008,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                         acc = fma_t((R)v2.y, ncoef[2 * j2 + 1], acc);
                     }
                 }
-                sm.v[ch][15 + t][lane] = acc;
+                sm.v[ch][15 + 18 * gr + t][lane] = acc;
                 __syncwarp();
             }
             __syncthreads();
@@ -1017,7 +1017,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                 const int ch = warp >> 2, par = (warp >> 1) & 1, q0 = (warp & 1) ? 5 : 0, nq = (warp & 1) ? 4 : 5;
                 if (ch < nch) {
                     R out[5];
-                    const R *va0 = &sm.v[ch][15 + par + 2 * (q0 - 7)][idxA], *vb0 = &sm.v[ch][14 + par + 2 * (q0 - 7)][idxB];
+                    const R *va0 = &sm.v[ch][15 + 18 * gr + par + 2 * (q0 - 7)][idxA], *vb0 = &sm.v[ch][14 + 18 * gr + par + 2 * (q0 - 7)][idxB];
                     if (warp & 1) window_tile<R, 4>(va0, vb0, dA, dB, out);
                     else window_tile<R, 5>(va0, vb0, dA, dB, out);
                     if (emit) {
@@ -1041,13 +1041,15 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
                     }
                 }
             }
-            __syncthreads();
-            // ------------------------------------------------ slide the V history: slots 18..32 -> 0..14
-            for (int idx = tid; idx < nch * 15 * 32; idx += HYB_THREADS) {
-                const int ch = idx / (15 * 32), r_ = idx - ch * 15 * 32;
-                (&sm.v[ch][0][0])[r_] = (&sm.v[ch][18][0])[r_];
+            // ------------------------------------------------ slide the V history once per frame: slots 36..50 -> 0..14
+            if (gr == 1) {   // granule 0 needs no barrier here: granule 1 writes rows 33..50, nobody reads those yet
+                __syncthreads();
+                for (int idx = tid; idx < nch * 15 * 32; idx += HYB_THREADS) {
+                    const int ch = idx >= 15 * 32, r_ = idx - ch * 15 * 32;
+                    (&sm.v[ch][0][0])[r_] = (&sm.v[ch][36][0])[r_];
+                }
             }
-            pp ^= 1;   // no barrier needed here: the next writers of v[15..32] sit behind the barriers of the next granule's phases
+            pp ^= 1;   // no barrier needed here: the next readers / writers of these rows sit behind the barriers of the next granule's phases
         }
     }
 }

@@ -266,6 +266,7 @@ struct RateSmem {
     int32_t slot[4][4];    // per (gr, ch) slot: address1..3 (stale when big_values == 0, A.E6), quantizerStepSize
     int32_t cnt[2][2];     // [round parity][gr] payload bits the granule consumed
     int32_t p23[2][4];     // [frame parity][slot] part2_3_length before resv_frame_end
+    int32_t prec[16][24];  // probes of warp 1's speculative run: step, then the Pooled words (replayed when the speculation fails)
     int32_t steptabi[128];
     double steptab[128];
     uint16_t sfb[24];
@@ -331,11 +332,22 @@ __device__ __forceinline__ int choose_table(const RateSmem &S, int mx, uint32_t 
     return choice;
 }
 
-// calc_run_len + count1_bit_count + subdivide + big_v_tab_select + big_v_bit_count for the quantised values held
-// pair-interleaved in the warp (lane L holds pairs 32 j + L).  Returns the bit count; updates gi and the slot addresses.
-__device__ __forceinline__ int probe_bits(const RateSmem &S, const uint32_t (&qx)[9], const uint32_t (&qy)[9], int lane, GranInfo &gi,
-                                          int &a1, int &a2, int &a3, bool hiding, int hn, uint32_t hb)
+// Everything a probe derives from the quantised values WITHOUT looking at the payload bits: run lengths, count1 bits, region
+// bounds and, per region, the maximum and the pooled code-length / sign / escape sums.  The table choice (with the stego swap)
+// and the bit count follow from it in a few scalar steps (probe_tables), which is what lets a mispredicted granule be replayed
+// from its recorded probes instead of re-running them (k_enc_rate).
+struct Pooled {
+    int c1bits, c1sel, bv, count1, r0, r1, a1, a2, a3;
+    uint32_t m0, m1, m2, lo0, hi0, cn0, lo1, hi1, cn1, lo2, hi2, cn2;
+};
+#define POOLED_WORDS 21
+
+// calc_run_len + count1_bit_count + subdivide + the pooled sums of big_v_tab_select / big_v_bit_count for the quantised values
+// held pair-interleaved in the warp (lane L holds pairs 32 j + L).  a1..a3 come in as the slot's current addresses.
+__device__ __forceinline__ void probe_pool(const RateSmem &S, const uint32_t (&qx)[9], const uint32_t (&qy)[9], int lane, int a1, int a2,
+                                           int a3, Pooled &P)
 {
+    GranInfo gi;
     const uint32_t FULL = 0xFFFFFFFFu;
     // ---- calc_run_len (:266-291)
     uint32_t lastnz = 0, lastbig = 0, nzmask = 0;
@@ -406,15 +418,24 @@ __device__ __forceinline__ int probe_bits(const RateSmem &S, const uint32_t (&qx
     lo0 = __reduce_add_sync(FULL, lo0); hi0 = __reduce_add_sync(FULL, hi0); cn0 = __reduce_add_sync(FULL, cn0);
     lo1 = __reduce_add_sync(FULL, lo1); hi1 = __reduce_add_sync(FULL, hi1); cn1 = __reduce_add_sync(FULL, cn1);
     lo2 = __reduce_add_sync(FULL, lo2); hi2 = __reduce_add_sync(FULL, hi2); cn2 = __reduce_add_sync(FULL, cn2);
-    // ---- big_v_tab_select with the stego swap; the payload index advances past non-zero tables only
+    P.c1bits = bits; P.c1sel = gi.c1sel; P.bv = gi.bv; P.count1 = gi.count1; P.r0 = gi.r0; P.r1 = gi.r1; P.a1 = a1; P.a2 = a2; P.a3 = a3;
+    P.m0 = m0; P.m1 = m1; P.m2 = m2; P.lo0 = lo0; P.hi0 = hi0; P.cn0 = cn0; P.lo1 = lo1; P.hi1 = hi1; P.cn1 = cn1;
+    P.lo2 = lo2; P.hi2 = hi2; P.cn2 = cn2;
+}
+
+// big_v_tab_select with the stego swap (the payload index advances past non-zero tables only) + big_v_bit_count   (:1147-1168, :294-318)
+__device__ __forceinline__ int probe_tables(const RateSmem &S, const Pooled &P, bool hiding, int hn, uint32_t hb, GranInfo &gi)
+{
+    gi.bv = P.bv; gi.count1 = P.count1; gi.c1sel = P.c1sel; gi.r0 = P.r0; gi.r1 = P.r1;
+    const int e2 = 2 * P.bv;
     int k = 0;
-    gi.ts0 = a1 <= 0 ? 0 : choose_table(S, (int)m0, lo0, hi0, cn0, hiding, k, hn, hb);
+    gi.ts0 = P.a1 <= 0 ? 0 : choose_table(S, (int)P.m0, P.lo0, P.hi0, P.cn0, hiding, k, hn, hb);
     if (gi.ts0 > 0) k++;
-    gi.ts1 = a2 <= a1 ? 0 : choose_table(S, (int)m1, lo1, hi1, cn1, hiding, k, hn, hb);
+    gi.ts1 = P.a2 <= P.a1 ? 0 : choose_table(S, (int)P.m1, P.lo1, P.hi1, P.cn1, hiding, k, hn, hb);
     if (gi.ts1 > 0) k++;
-    gi.ts2 = e2 <= a2 ? 0 : choose_table(S, (int)m2, lo2, hi2, cn2, hiding, k, hn, hb);
-    bits += table_cost(S, gi.ts0, lo0, hi0, cn0) + table_cost(S, gi.ts1, lo1, hi1, cn1) + table_cost(S, gi.ts2, lo2, hi2, cn2);
-    return bits;
+    gi.ts2 = e2 <= P.a2 ? 0 : choose_table(S, (int)P.m2, P.lo2, P.hi2, P.cn2, hiding, k, hn, hb);
+    return P.c1bits + table_cost(S, gi.ts0, P.lo0, P.hi0, P.cn0) + table_cost(S, gi.ts1, P.lo1, P.hi1, P.cn1) +
+           table_cost(S, gi.ts2, P.lo2, P.hi2, P.cn2);
 }
 
 // quantize() of all 576 values (:374-415); callers know from quant_max() that the maximum is <= 8192
@@ -519,7 +540,7 @@ k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ state
             int64_t use_off = off;
             if (gr == 1 && stats[gslot - 1].xrmax) use_off += 3;
             GranInfo gi;
-            int a1 = 0, a2 = 0, a3 = 0, step = 0, part23 = 0, cnt = 0, hn = 0;
+            int a1 = 0, a2 = 0, a3 = 0, step = 0, part23 = 0, cnt = 0, hn = 0, nrec = 0, qstep = 1000;
             uint32_t hb = 0, qx[9], qy[9];
             bool need = true;
 #pragma unroll 1
@@ -530,11 +551,16 @@ k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ state
                     part23 = 0; cnt = 0;
                     if (xrmax) {
                         if (hiding) payload_bits_at(payload, cl, use_off, lane, hn, hb);
+                        // warp 1 records the payload-independent part of every probe of its speculative run; if the speculation
+                        // fails, the second run replays them (a few scalar steps per probe) for as long as it follows the same path
+                        const bool record = gr == 1 && attempt == 0 && hiding;
+                        bool replay = attempt == 1;
+                        int ridx = 0;
+                        if (record) nrec = 0;
                         // ---- bin_search_step_size (:958-996) then inner_loop (:1064-1095), as one loop with a single probe site
-                        int next = -120, count = 120, half = 0, bits = 0;
+                        int next = -120, count = 120, half = 0, bits = 0, s = 0;
                         bool in_bin = true;
                         for (;;) {
-                            int s;
                             bool ovf = false;
                             if (in_bin) {
                                 half = count / 2;
@@ -547,14 +573,45 @@ k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ state
                             }
                             bits = 100000;
                             if (!ovf) {
-                                quantize_all(S, ax, ay, s, qx, qy);
-                                bits = probe_bits(S, qx, qy, lane, gi, a1, a2, a3, hiding, hn, hb);
+                                Pooled P;
+                                if (replay && ridx < min(nrec, 16) && S.prec[ridx][0] == s) {
+                                    const int32_t *w = S.prec[ridx] + 1;
+                                    P.c1bits = w[0]; P.c1sel = w[1]; P.bv = w[2]; P.count1 = w[3]; P.r0 = w[4]; P.r1 = w[5];
+                                    P.a1 = w[6]; P.a2 = w[7]; P.a3 = w[8];
+                                    P.m0 = w[9]; P.m1 = w[10]; P.m2 = w[11]; P.lo0 = w[12]; P.hi0 = w[13]; P.cn0 = w[14];
+                                    P.lo1 = w[15]; P.hi1 = w[16]; P.cn1 = w[17]; P.lo2 = w[18]; P.hi2 = w[19]; P.cn2 = w[20];
+                                    ridx++;
+                                } else {
+                                    replay = false;
+                                    quantize_all(S, ax, ay, s, qx, qy);
+                                    qstep = s;
+                                    probe_pool(S, qx, qy, lane, a1, a2, a3, P);
+                                    if (record) {
+                                        if (nrec < 16 && lane == 0) {
+                                            int32_t *w = S.prec[nrec];
+                                            w[0] = s;
+                                            w[1] = P.c1bits; w[2] = P.c1sel; w[3] = P.bv; w[4] = P.count1; w[5] = P.r0; w[6] = P.r1;
+                                            w[7] = P.a1; w[8] = P.a2; w[9] = P.a3;
+                                            w[10] = (int32_t)P.m0; w[11] = (int32_t)P.m1; w[12] = (int32_t)P.m2;
+                                            w[13] = (int32_t)P.lo0; w[14] = (int32_t)P.hi0; w[15] = (int32_t)P.cn0;
+                                            w[16] = (int32_t)P.lo1; w[17] = (int32_t)P.hi1; w[18] = (int32_t)P.cn1;
+                                            w[19] = (int32_t)P.lo2; w[20] = (int32_t)P.hi2; w[21] = (int32_t)P.cn2;
+                                        }
+                                        nrec++;
+                                    }
+                                }
+                                a1 = P.a1; a2 = P.a2; a3 = P.a3;
+                                bits = probe_tables(S, P, hiding, hn, hb, gi);
                             }
                             if (in_bin) {
                                 if (bits < max_bits) count = half;
                                 else { next += half; count -= half; }
                                 if (count <= 1) { in_bin = false; step = next; }
                             } else if (bits <= max_bits) break;
+                        }
+                        if (qstep != s) {   // the run ended on a replayed probe: the registers hold another step's values
+                            quantize_all(S, ax, ay, s, qx, qy);
+                            qstep = s;
                         }
                         part23 = bits;
                         cnt = (gi.ts0 > 0) + (gi.ts1 > 0) + (gi.ts2 > 0);   // :808-809
