@@ -1180,7 +1180,8 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         M3S_LAUNCH_CHECK(h);
         M3S_CUDA(h, cudaEventRecord(h->ev_rate[pb], h->stream));
         // queued behind the rate loop's CTAs on purpose: the next chunk's analysis takes what they leave free
-        if (k + 1 < n_chunks && (rc = launch_analysis(k + 1))) return rc;
+        const bool serial = getenv("M3S_ENC_SERIAL") != nullptr;   // diagnostic: analysis of chunk k+1 only after chunk k is packed (no overlap)
+        if (!serial && k + 1 < n_chunks && (rc = launch_analysis(k + 1))) return rc;
         if (host && k + 2 < n_chunks) M3S_CUDA(h, stage_chunk(k + 2));
         // packing stays on the rate loop's stream: next to the analysis it would only slow the critical chain further
         M3S_KBEGIN(h, M3S_K_ENC_PACK);
@@ -1189,6 +1190,10 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
             chunk_total, (const uint32_t *)b_ix[pb]->p, (const int32_t *)b_info[pb]->p, (const uint8_t *)b_scfsi[pb]->p, d_out);
         M3S_LAUNCH_CHECK(h);
         M3S_CUDA(h, cudaEventRecord(h->ev_pack[pb], h->stream));
+        if (serial && k + 1 < n_chunks) {
+            M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_pack[pb], 0));
+            if ((rc = launch_analysis(k + 1))) return rc;
+        }
         if (host) {   // this chunk's bytes of every clip go home behind the pack kernel
             M3S_CUDA(h, cudaStreamWaitEvent(h->copy_out, h->ev_pack[pb], 0));
             rows.clear();
