@@ -90,6 +90,7 @@ struct AnaSmem {
     int32_t sb[2][18][32];      // [ping-pong][slot][band] subband samples
     int32_t mf[576];            // [band * 18 + k] MDCT lines
     uint32_t bins[24];          // 0..20 band energies, 21 total, 22 xrmax
+    uint32_t en_thresh[32];     // EncTables::en_thresh
     uint8_t sfb[576];
     int32_t ca[8], cs[8];
 };
@@ -134,6 +135,7 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
     const int ch = wk.ch;
     for (int i = tid; i < 576; i += ANA_THREADS) S.sfb[i] = T->long_sfb_of[sr_idx][i];
     if (tid < 8) { S.ca[tid] = T->enc_ca[tid]; S.cs[tid] = T->enc_cs[tid]; }
+    if (tid < 32) S.en_thresh[tid] = ET->en_thresh[tid];
     for (int i = tid; i < 2 * 18 * 32; i += ANA_THREADS) (&S.sb[0][0][0])[i] = 0;
     // ---- per-thread roles and their register-resident coefficients
     const int wpar = tid >> 6, wi = tid & 63;                                  // windowing: slot parity, output i
@@ -151,6 +153,7 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
     const int g_begin = wk.g_first > 0 ? wk.g_first - 1 : 0;
     const int g_end = wk.g_first + wk.count;
     int pp = 0, xb = 0;
+    uint32_t nx[5] = {0u, 0u, 0u, 0u, 0u};
     for (int G = g_begin; G < g_end; G++, pp ^= 1, xb ^= 1) {
         // ---- PCM window: samples [576 G - 480, 576 G + 576); the history comes from the other buffer
         const int64_t t0 = (int64_t)G * 576 - 480;
@@ -162,12 +165,20 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
             }
         } else {
             for (int i = tid; i < 480; i += ANA_THREADS) S.x[xb][i] = S.x[xb ^ 1][576 + i];
-            for (int i = tid; i < 576; i += ANA_THREADS) {
-                const uint32_t w = __ldg(pcm32 + t0 + 480 + i);
-                S.x[xb][480 + i] = (int32_t)((w << sh) & 0xFFFF0000u);
+#pragma unroll
+            for (int q = 0; q < 5; q++) {   // the 576 new samples were fetched during the previous granule
+                const int i = tid + ANA_THREADS * q;
+                if (i < 576) S.x[xb][480 + i] = (int32_t)((nx[q] << sh) & 0xFFFF0000u);
             }
         }
         __syncthreads();
+        if (G + 1 < g_end) {   // prefetch the next granule's samples: their DRAM latency hides under this granule's arithmetic
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+                const int i = tid + ANA_THREADS * q;
+                if (i < 576) nx[q] = __ldg(pcm32 + (int64_t)(G + 1) * 576 + i);
+            }
+        }
         // ---- windowing: y_s[i] = sum_k mul(x[32 s + 31 - i - 64 k], enwindow[i + 64 k])   (:337-356).  Slots s = p + 2 q of one
         //      parity share their samples: x index = base + 64 (q - k), 16 distinct values for 9 slots x 8 taps
         {
@@ -245,7 +256,7 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
             int en = 0;
             if (temp) {
                 en = -21;
-                for (int j = 0; j < 31; j++) en += ET->en_thresh[j] <= temp;
+                for (int j = 0; j < 31; j++) en += S.en_thresh[j] <= temp;
             }
             M3sEncStats *st = stats + gslot;
             if (tid == 21) { st->en_tot = (int8_t)en; st->xrmax = (int32_t)S.bins[22]; }
@@ -478,7 +489,7 @@ __device__ __forceinline__ void payload_bits_at(const uint8_t *__restrict__ payl
 // per non-empty region; none if granule 0 is silent).  A granule depends on its offset only through the <= 3 bits it
 // reads, so after warp 0 publishes its count warp 1 keeps its result when the bits at the true offset equal the ones it
 // used and re-runs otherwise (the tone+noise corpus mispredicts 1-2 % of the granules, low tones up to 27 %).
-__global__ void __launch_bounds__(32 * RATE_WARPS, 10)
+__global__ void __launch_bounds__(32 * RATE_WARPS, 11)
 k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ states, const M3sDevTables *__restrict__ T,
            const EncTables *__restrict__ ET, const uint32_t *__restrict__ byteoff, const uint8_t *__restrict__ payload,
            int sr_idx, int whole_slots, int32_t chunk_first, int32_t chunk_frames, int64_t chunk_frame0,
