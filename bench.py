@@ -447,7 +447,7 @@ def run_product_arm(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     DEC_K = ("k_walk", "k_fscan", "k_sideinfo", "k_strip", "k_huff", "k_hybrid")
-    ENC_K = ("k_enc_analysis", "k_enc_rate", "k_enc_pack")
+    ENC_K = ("k_enc_analysis", "k_enc_rate", "k_enc_resolve", "k_enc_emit", "k_enc_pack")
 
     def measure(dev_fn, host_fn, knames, bpf):
         for _ in range(args.warmup):

@@ -156,10 +156,10 @@ enum {
     M3S_K_SPEC_EXPORT,   /* parity tap */
     M3S_K_HYBRID,        /* D2+D3 requantize .. polyphase synthesis .. int16 */
     M3S_K_ENC_ANALYSIS,  /* E1 polyphase analysis + MDCT + alias (fixed point) */
-    M3S_K_ENC_RATE,      /* E2 per-granule rate loop incl. table selection + stego swap */
+    M3S_K_ENC_RATE,      /* E2 per-granule rate loop incl. table selection + stego swap, every payload variant of a granule (k_enc_probe) */
     M3S_K_ENC_RESOLVE,   /* E2b per-clip sequential offset scan over granule variants */
     M3S_K_ENC_PACK,      /* E3 side-info + main-data bit packing */
-    M3S_K_ENC_AUX,       /* small helper kernels of the encoder */
+    M3S_K_ENC_AUX,       /* E2c quantisation at the chosen step (k_enc_emit) */
     M3S_K_COUNT
 };
 M3S_API int m3s_timing_enable(m3s_handle_t h, int on);

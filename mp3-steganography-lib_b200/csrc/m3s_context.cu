@@ -393,7 +393,8 @@ extern "C" int m3s_destroy(m3s_handle_t h)
                       &h->b_fr_reveal, &h->b_fr_file, &h->b_units, &h->b_sf, &h->b_S, &h->b_spec, &h->b_tabids,
                       &h->b_reveal, &h->b_work, &h->b_pcm_stage, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
                       &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad, &h->e_tabs, &h->e_state,
-                      &h->e_lastix, &h->e_scfsi, &h->e_work, &h->e_clips2, &h->e_mdct2, &h->e_gran2, &h->e_ix2, &h->e_info2, &h->e_scfsi2};
+                      &h->e_lastix, &h->e_scfsi, &h->e_work, &h->e_clips2, &h->e_mdct2, &h->e_gran2, &h->e_ix2, &h->e_info2, &h->e_scfsi2,
+                      &h->e_var, &h->e_var2, &h->e_sum, &h->e_sum2};
     for (M3sBuf *b : bufs) free_buf(*b);
     if (h->fouts_mapped) cudaFreeHost(h->fouts_mapped);
     if (h->rev_mapped) cudaFreeHost(h->rev_mapped);
@@ -504,7 +505,7 @@ extern "C" int m3s_timing_get(m3s_handle_t h, int kernel_id, double *total_ms, i
 extern "C" const char *m3s_kernel_name(int kernel_id)
 {
     static const char *names[M3S_K_COUNT] = {"k_walk", "k_fscan", "k_sideinfo", "k_strip", "k_huff", "k_spec_export", "k_hybrid",
-                                             "k_enc_analysis", "k_enc_rate", "k_enc_resolve", "k_enc_pack", "k_enc_aux"};
+                                             "k_enc_analysis", "k_enc_rate", "k_enc_resolve", "k_enc_pack", "k_enc_emit"};
     return kernel_id >= 0 && kernel_id < M3S_K_COUNT ? names[kernel_id] : "?";
 }
 

@@ -36,6 +36,8 @@ struct M3sEncClip {
 struct M3sEncState {       // E2 state carried from chunk to chunk (and between frames inside the kernel)
     int64_t hide_off;      // MP3Encoder.hide_str_offset
     int32_t a1[4], a2[4], a3[4], step[4];  // per (gr, ch) slot: address1..3 (stale when big_values == 0, A.E6), quantizerStepSize
+    int32_t src[4];        // per slot: 1 + clip frame of the latest non-silent granule (0 = none yet); l3_enc keeps ITS values while silent
+    int32_t pad[2];
 };
 
 struct __align__(16) M3sEncStats {  // per granule-channel, written by E1
@@ -472,6 +474,18 @@ __device__ __forceinline__ void quantize_all(const RateSmem &S, const uint32_t (
     }
 }
 
+// quantize() when the largest coefficient stays below the table limit (ln < 10000 for every value): no fallback, no clamp
+__device__ __forceinline__ void quantize_small(const RateSmem &S, const uint32_t (&ax)[9], const uint32_t (&ay)[9], int step,
+                                               uint32_t (&qx)[9], uint32_t (&qy)[9])
+{
+    const int32_t scalei = S.steptabi[step + 127];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        qx[j] = S.i2i[mulr32((int32_t)ax[j], scalei)];
+        qy[j] = S.i2i[mulr32((int32_t)ay[j], scalei)];
+    }
+}
+
 // payload bits a granule starting at payload offset `off` can consume: bits[off .. off + 2]   (:1154-1168)
 __device__ __forceinline__ void payload_bits_at(const uint8_t *__restrict__ payload, const M3sEncClip &cl, int64_t off, int lane,
                                                 int &hn, uint32_t &hb)
@@ -482,6 +496,27 @@ __device__ __forceinline__ void payload_bits_at(const uint8_t *__restrict__ payl
     hb = __ballot_sync(0xFFFFFFFFu, one);
 }
 
+// the shared-memory tables of the rate loop (all kernels of E2 stage the same set)
+__device__ __forceinline__ void rate_tables_load(RateSmem &S, const M3sDevTables *__restrict__ T, const EncTables *__restrict__ ET,
+                                                 int sr_idx, int tid, int nthr)
+{
+    for (int i = tid; i < 10000; i += nthr) S.i2i[i] = (uint16_t)T->int2idx[i];
+    for (int i = tid; i < 256; i += nthr) {
+        const uint32_t x = i >> 4, y = i & 15;
+        S.hlc[i] = make_uint2(ET->hl4[i], (uint32_t)(x != 0) + (uint32_t)(y != 0) + (((uint32_t)(x > 14) + (uint32_t)(y > 14)) << 16));
+    }
+    for (int i = tid; i < 128; i += nthr) { S.steptabi[i] = T->steptabi[i]; S.steptab[i] = T->steptab[i]; }
+    if (tid < 24) S.sfb[tid] = tid < 23 ? T->sfb_long[sr_idx][tid] : 576;
+    if (tid < 32) {
+        S.linmax[tid] = T->enc_linmax[tid];
+        S.linbits[tid] = T->enc_linbits[tid];
+        S.pair[tid][0] = T->pair[tid][0];
+        S.pair[tid][1] = T->pair[tid][1];
+    }
+    if (tid < 23) { S.subdv[tid][0] = T->subdv[tid][0]; S.subdv[tid][1] = T->subdv[tid][1]; }
+    if (tid < 16) { S.hlc1[0][tid] = ET->hlc1[0][tid]; S.hlc1[1][tid] = ET->hlc1[1][tid]; }
+}
+
 // One CTA of two warps per clip.  The reference visits a frame's granules as (ch0,gr0) (ch0,gr1) (ch1,gr0) (ch1,gr1) and
 // chains them through hide_str_offset (which payload bits a granule may consume) and through the per-slot stale
 // address1..3 / step.  Warp w owns granule index gr = w, so the slot state never leaves its warp; within a channel the
@@ -490,7 +525,7 @@ __device__ __forceinline__ void payload_bits_at(const uint8_t *__restrict__ payl
 // reads, so after warp 0 publishes its count warp 1 keeps its result when the bits at the true offset equal the ones it
 // used and re-runs otherwise (the tone+noise corpus mispredicts 1-2 % of the granules, low tones up to 27 %).
 __global__ void __launch_bounds__(32 * RATE_WARPS, 11)
-k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ states, const M3sDevTables *__restrict__ T,
+k_enc_rate_chain(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ states, const M3sDevTables *__restrict__ T,
            const EncTables *__restrict__ ET, const uint32_t *__restrict__ byteoff, const uint8_t *__restrict__ payload,
            int sr_idx, int whole_slots, int32_t chunk_first, int32_t chunk_frames, int64_t chunk_frame0,
            const int32_t *__restrict__ mdct, const M3sEncStats *__restrict__ stats, uint32_t *__restrict__ ixout,
@@ -502,21 +537,7 @@ k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ state
     const uint32_t FULL = 0xFFFFFFFFu;
     const int c = blockIdx.x;
     const M3sEncClip cl = clips[c];
-    for (int i = tid; i < 10000; i += 32 * RATE_WARPS) S.i2i[i] = (uint16_t)T->int2idx[i];
-    for (int i = tid; i < 256; i += 32 * RATE_WARPS) {
-        const uint32_t x = i >> 4, y = i & 15;
-        S.hlc[i] = make_uint2(ET->hl4[i], (uint32_t)(x != 0) + (uint32_t)(y != 0) + (((uint32_t)(x > 14) + (uint32_t)(y > 14)) << 16));
-    }
-    for (int i = tid; i < 128; i += 32 * RATE_WARPS) { S.steptabi[i] = T->steptabi[i]; S.steptab[i] = T->steptab[i]; }
-    if (tid < 24) S.sfb[tid] = tid < 23 ? T->sfb_long[sr_idx][tid] : 576;
-    if (tid < 32) {
-        S.linmax[tid] = T->enc_linmax[tid];
-        S.linbits[tid] = T->enc_linbits[tid];
-        S.pair[tid][0] = T->pair[tid][0];
-        S.pair[tid][1] = T->pair[tid][1];
-    }
-    if (tid < 23) { S.subdv[tid][0] = T->subdv[tid][0]; S.subdv[tid][1] = T->subdv[tid][1]; }
-    if (tid < 16) { S.hlc1[0][tid] = ET->hlc1[0][tid]; S.hlc1[1][tid] = ET->hlc1[1][tid]; }
+    rate_tables_load(S, T, ET, sr_idx, tid, 32 * RATE_WARPS);
     if (tid < 4) {
         const M3sEncState *sp = states + c;
         S.slot[tid][0] = sp->a1[tid]; S.slot[tid][1] = sp->a2[tid]; S.slot[tid][2] = sp->a3[tid]; S.slot[tid][3] = sp->step[tid];
@@ -723,6 +744,534 @@ k_enc_rate(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__ state
         M3sEncState *sp = states + c;
         sp->a1[tid] = S.slot[tid][0]; sp->a2[tid] = S.slot[tid][1]; sp->a3[tid] = S.slot[tid][2]; sp->step[tid] = S.slot[tid][3];
         if (tid == 0) sp->hide_off = off;
+    }
+}
+
+// ================================================================================================
+// E2 (parallel form): k_enc_probe -> k_enc_resolve -> k_enc_emit
+//
+// A granule depends on its predecessors only through (a) the <= 3 payload bits at its hide_str_offset -- i.e. through one of
+// 15 "variants": three bits (8), two (4) or one (2) left before the payload ends, or none -- and (b) the slot's stale
+// address1..3, which are read only by probes that find big_values == 0 among non-zero values (A.E6).  So
+//   k_enc_probe    one warp per granule-channel, NO chain: lane v walks the reference's step search for variant v; the
+//                  payload-independent part of a probe (quantise, run lengths, pooled code-length sums: `Pooled`) is computed
+//                  once per distinct step by the whole warp and cached in shared memory -- on the tone+noise corpus the eight
+//                  3-bit variants visit 7 distinct steps together, one fewer than the 8 probes of a single sequential run;
+//   k_enc_resolve  one warp per clip walks the granules in the reference's order with nothing but register arithmetic per
+//                  granule (offset -> variant -> bits consumed), 32 granules per batch; granules that did depend on the
+//                  stale addresses (flagged by the probe kernel) are redone here with the true state;
+//   k_enc_emit     one warp per granule quantises at the chosen step and writes the values the packer reads.
+// ================================================================================================
+#define PROBE_WARPS 8
+#define PROBE_G 8            // granules per warp of k_enc_probe (amortises the CTA's table staging)
+#define PROBE_CACHE 24       // distinct steps cached per granule; more than that (never seen) sends the granule to the resolve kernel
+#define VAR_SILENT 0x80000000u
+#define VAR_SLOW 0x40000000u
+#define VAR_NONE 0xFFFFFFFFu
+#define STEP_NONE 0x7FFFFFFF
+
+// What a probe (one step of one granule) leaves for the variant walks: everything but the payload bits.  The table the
+// reference would choose for a region BEFORE the swap does not depend on the payload, nor does the payload index of a region
+// (the number of earlier regions with a non-zero table, and a swapped table is non-zero iff the original is); so the bit count
+// of a variant is  c1bits + sum over regions of cost[region][mode]  with mode = no swap / swap by a '0' / swap by a '1'.
+struct ProbeRow {
+    int32_t c1bits;
+    uint32_t geo;             // big_values[0:9) count1[9:17) count1table[17] region0[18:22) region1[22:25) table0 != 0 [25] table1 != 0 [26]
+    uint32_t addr;            // address1 | address2 << 10 | address3 << 20 after this probe
+    uint32_t tag;             // the addresses the sums were pooled over when the probe read them (big_values == 0, A.E6), else VAR_NONE
+    uint16_t cost[3][4];      // [region][mode] count_bit() of the region under table tab[region][mode]
+    uint8_t tab[3][4];
+};
+struct ProbeWarpSmem {
+    ProbeRow row[PROBE_CACHE];
+    uint8_t slotmap[128];    // step + 120 -> cache row (0xFF = not computed yet)
+};
+struct ProbeSmem {
+    RateSmem R;
+    ProbeWarpSmem W[PROBE_WARPS];
+};
+
+// variant v <-> (bits left, their values): 0..7 three bits, 8..11 two, 12..13 one, 14 none (also: plain encode)
+__device__ __forceinline__ void variant_bits(int v, int &hn, uint32_t &hb)
+{
+    if (v < 8) { hn = 3; hb = (uint32_t)v; }
+    else if (v < 12) { hn = 2; hb = (uint32_t)(v - 8); }
+    else if (v < 14) { hn = 1; hb = (uint32_t)(v - 12); }
+    else { hn = 0; hb = 0u; }
+}
+__device__ __forceinline__ int variant_index(int hn, uint32_t hb)
+{
+    return hn == 3 ? (int)hb : (hn == 2 ? 8 + (int)hb : (hn == 1 ? 12 + (int)hb : 14));
+}
+
+__device__ __forceinline__ void load_granule(const int32_t *__restrict__ mdct_g, int lane, uint32_t (&ax)[9], uint32_t (&ay)[9], uint32_t &sg)
+{
+    const int2 *xr = (const int2 *)mdct_g;
+    sg = 0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        const int2 v = __ldg(xr + 32 * j + lane);
+        ax[j] = v.x < 0 ? (uint32_t)(-(int64_t)v.x) : (uint32_t)v.x;
+        ay[j] = v.y < 0 ? (uint32_t)(-(int64_t)v.y) : (uint32_t)v.y;
+        sg |= (uint32_t)(v.x < 0) << (2 * j) | (uint32_t)(v.y < 0) << (2 * j + 1);
+    }
+}
+
+__device__ __forceinline__ int frame_max_bits(const uint32_t *__restrict__ byteoff, int f, int whole_slots, int &padding, int &mean_bits)
+{
+    padding = (int)(byteoff[f + 1] - byteoff[f]) - whole_slots;
+    const int bits_per_frame = 8 * (whole_slots + padding);
+    mean_bits = (bits_per_frame - 288) / 2;                  // :634-636 (side info 8 * (4 + 32) bits)
+    return min(mean_bits / 2, 4095);                         // :894-912 with the reservoir never enabled (A.E7)
+}
+
+__global__ void __launch_bounds__(32 * PROBE_WARPS, 3)
+k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ frame_clip, const M3sDevTables *__restrict__ T,
+            const EncTables *__restrict__ ET, const uint32_t *__restrict__ byteoff, int sr_idx, int whole_slots, int64_t n_gran,
+            const int32_t *__restrict__ mdct, const M3sEncStats *__restrict__ stats, uint4 *__restrict__ var,
+            uint32_t *__restrict__ sum, uint8_t *__restrict__ scfsi_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ProbeSmem &PS = *reinterpret_cast<ProbeSmem *>(smem_raw);
+    RateSmem &S = PS.R;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    ProbeWarpSmem &W = PS.W[warp];
+    rate_tables_load(S, T, ET, sr_idx, tid, 32 * PROBE_WARPS);
+    __syncthreads();
+    int vhn;
+    uint32_t vhb;
+    variant_bits(lane, vhn, vhb);
+    // tiles of PROBE_WARPS * PROBE_G granules; a grid smaller than the tile count walks them with a stride (M3S_PROBE_CTAS: a
+    // fixed number of CTAs per SM leaves room for the analysis kernel of the next chunk to run beside this one)
+    const int64_t n_iter = ((n_gran + PROBE_WARPS * PROBE_G - 1) / (PROBE_WARPS * PROBE_G) - blockIdx.x + gridDim.x - 1) / gridDim.x * PROBE_G;
+#pragma unroll 1
+    for (int64_t it = 0; it < n_iter; it++) {
+        const int64_t tile = blockIdx.x + (it / PROBE_G) * gridDim.x;
+        const int64_t gs = tile * (PROBE_WARPS * PROBE_G) + warp + (it % PROBE_G) * PROBE_WARPS;
+        if (gs >= n_gran) continue;
+        const int64_t fl_ = gs >> 2;
+        const int q = (int)(gs & 3);                         // position in the reference's order: (ch0,gr0) (ch0,gr1) (ch1,gr0) (ch1,gr1)
+        const int c = frame_clip[fl_];
+        const int64_t payload_len = clips[c].payload_len;
+        const int f = (int)(fl_ - clips[c].frame_base);      // frame index inside the clip
+        int padding, mean_bits;
+        const int max_bits = frame_max_bits(byteoff, f, whole_slots, padding, mean_bits);
+        const int32_t xrmax = stats[gs].xrmax;
+        if (q & 1) {
+            // ---- calc_scfsi (:862-892) of this channel: needs the statistics of both granules
+            const M3sEncStats *s0 = stats + gs - 1, *s1 = stats + gs;
+            const int d = lane < 21 ? abs((int)s0->en[lane] - (int)s1->en[lane]) : 0;
+            const int tp = __reduce_add_sync(FULL, d);
+            int condition = 2 + (s0->xrmax != 0) + (s1->xrmax != 0);
+            if (abs((int)s0->en_tot - (int)s1->en_tot) < 10) condition++;
+            if (tp < 100) condition++;
+            const int b0 = __reduce_add_sync(FULL, lane < 6 ? d : 0), b1 = __reduce_add_sync(FULL, lane >= 6 && lane < 11 ? d : 0);
+            const int b2 = __reduce_add_sync(FULL, lane >= 11 && lane < 16 ? d : 0), b3 = __reduce_add_sync(FULL, lane >= 16 ? d : 0);
+            if (lane < 4) {
+                const int sum0 = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+                scfsi_out[(fl_ * 2 + (q >> 1)) * 4 + lane] = (condition == 6 && sum0 < 10) ? 1 : 0;   // xm[] is all zero: sum1 = 0
+            }
+        }
+        if (!xrmax) {
+            if (lane == 0) sum[gs] = VAR_SILENT;
+            continue;
+        }
+        uint32_t ax[9], ay[9], sg;
+        load_granule(mdct + gs * 576, lane, ax, ay, sg);
+        // which variants can occur: the offset in front of this granule is at most 3 bits per earlier granule of the clip
+        const bool hiding = payload_len > 0;
+        const bool sure3 = payload_len - 3 * (4 * (int64_t)f + q) >= 3;
+        const bool active = hiding ? lane < (sure3 ? 8 : 15) : lane == 14;
+        ((uint32_t *)W.slotmap)[lane] = 0xFFFFFFFFu;
+        __syncwarp();
+        // ---- per-lane walk of bin_search_step_size (:958-996) then inner_loop (:1064-1095)
+        int next = -120, count = 120, half = 0, step = 0, s = 0, bits = 0, nslots = 0, have = 0, mode0 = 0, mode1 = 0, mode2 = 0;
+        uint32_t la = 0;
+        bool in_bin = true, done = !active, slow = false;
+        for (;;) {
+            bool ovf = false;
+            if (!done) {
+                if (in_bin) {
+                    half = count / 2;
+                    s = next + half;
+                    ovf = quant_max(S, xrmax, s) > 8192;
+                } else {
+                    while (quant_max(S, xrmax, step + 1) > 8192) step++;
+                    step++;
+                    s = step;
+                }
+            }
+            // ---- every step some lane needs and the cache lacks is probed once, by the whole warp
+            for (;;) {
+                const bool need = !done && !ovf && W.slotmap[s + 120] == 0xFF;
+                const uint32_t m = __ballot_sync(FULL, need);
+                if (!m) break;
+                if (nslots == PROBE_CACHE) { slow = true; break; }
+                const int ldr = __ffs(m) - 1;
+                const int sc = __shfl_sync(FULL, s, ldr);
+                // a probe that finds big_values == 0 among non-zero values pools over the addresses of the latest probe with big values
+                // (A.E6): the requesting lane's own, if its walk has met one in this granule -- else the slot's stale ones, which only
+                // the resolve kernel knows
+                const int lhave = __shfl_sync(FULL, have, ldr);
+                const uint32_t lla = __shfl_sync(FULL, la, ldr);
+                uint32_t qx[9], qy[9];
+                if (mulr32(xrmax, S.steptabi[sc + 127]) < 10000) quantize_small(S, ax, ay, sc, qx, qy);
+                else quantize_all(S, ax, ay, sc, qx, qy);
+                Pooled P;
+                probe_pool(S, qx, qy, lane, (int)(lla & 1023u), (int)((lla >> 10) & 1023u), (int)((lla >> 20) & 1023u), P);
+                const bool uses_addr = P.bv == 0 && P.count1 > 0;
+                if (uses_addr && !lhave) { slow = true; break; }
+                // the three regions' table choices and costs, lane r (< 3) takes region r
+                {
+                    const int r = lane % 3;
+                    const uint32_t lo = r == 0 ? P.lo0 : (r == 1 ? P.lo1 : P.lo2), hi = r == 0 ? P.hi0 : (r == 1 ? P.hi1 : P.hi2);
+                    const uint32_t cn = r == 0 ? P.cn0 : (r == 1 ? P.cn1 : P.cn2), mx = r == 0 ? P.m0 : (r == 1 ? P.m1 : P.m2);
+                    const bool exists = r == 0 ? P.a1 > 0 : (r == 1 ? P.a2 > P.a1 : 2 * P.bv > P.a2);
+                    const int ch0 = exists ? choose_table(S, (int)mx, lo, hi, cn, false, 0, 0, 0u) : 0;
+                    const int t0 = S.pair[ch0][0], t1 = S.pair[ch0][1];
+                    const uint32_t nz = __ballot_sync(FULL, ch0 > 0);
+                    ProbeRow &R = W.row[nslots];
+                    if (lane < 3) {
+                        R.cost[r][0] = (uint16_t)table_cost(S, ch0, lo, hi, cn);
+                        R.cost[r][1] = (uint16_t)table_cost(S, t0, lo, hi, cn);
+                        R.cost[r][2] = (uint16_t)table_cost(S, t1, lo, hi, cn);
+                        R.tab[r][0] = (uint8_t)ch0; R.tab[r][1] = (uint8_t)t0; R.tab[r][2] = (uint8_t)t1;
+                    }
+                    if (lane == 0) {
+                        R.c1bits = P.c1bits;
+                        R.geo = (uint32_t)P.bv | (uint32_t)P.count1 << 9 | (uint32_t)P.c1sel << 17 | (uint32_t)P.r0 << 18 | (uint32_t)P.r1 << 22 |
+                                (nz & 3u) << 25;
+                        R.addr = (uint32_t)P.a1 | (uint32_t)P.a2 << 10 | (uint32_t)P.a3 << 20;
+                        R.tag = uses_addr ? lla : VAR_NONE;
+                        W.slotmap[sc + 120] = (uint8_t)nslots;
+                    }
+                }
+                nslots++;
+                __syncwarp();
+            }
+            if (slow) break;
+            bool stray = false;
+            if (!done) {
+                bits = 100000;
+                if (!ovf) {
+                    const ProbeRow &R = W.row[W.slotmap[s + 120]];
+                    const uint32_t geo = R.geo, tag = R.tag;
+                    stray = tag != VAR_NONE && (!have || tag != la);   // pooled over another walk's addresses
+                    const int k1 = (int)((geo >> 25) & 1u), k2 = k1 + (int)((geo >> 26) & 1u);
+                    mode0 = 0 < vhn ? 1 + (int)(vhb & 1u) : 0;
+                    mode1 = k1 < vhn ? 1 + (int)((vhb >> k1) & 1u) : 0;
+                    mode2 = k2 < vhn ? 1 + (int)((vhb >> k2) & 1u) : 0;
+                    bits = R.c1bits + (int)R.cost[0][mode0] + (int)R.cost[1][mode1] + (int)R.cost[2][mode2];
+                    if (geo & 0x1FFu) { have = 1; la = R.addr; }
+                }
+                if (in_bin) {
+                    if (bits < max_bits) count = half;
+                    else { next += half; count -= half; }
+                    if (count <= 1) { in_bin = false; step = next; }
+                } else if (bits <= max_bits) done = true;
+            }
+            if (__any_sync(FULL, stray)) { slow = true; break; }
+            if (__all_sync(FULL, done)) break;
+        }
+        if (slow) {
+            if (lane == 0) sum[gs] = VAR_SLOW;
+            continue;
+        }
+        uint32_t cntw = 0;
+        if (active) {   // the last probe of the walk is the accepted one: its row, under this variant's modes
+            const ProbeRow &R = W.row[W.slotmap[s + 120]];
+            const uint32_t geo = R.geo;
+            const int ts0 = R.tab[0][mode0], ts1 = R.tab[1][mode1], ts2 = R.tab[2][mode2];
+            const int cnt = (ts0 > 0) + (ts1 > 0) + (ts2 > 0);   // :808-809
+            cntw = (uint32_t)cnt << (2 * lane);
+            uint4 r;
+            r.x = (uint32_t)bits | (geo & 0x1FFu) << 12 | ((geo >> 9) & 0xFFu) << 21 | ((geo >> 17) & 1u) << 29;
+            r.y = (uint32_t)(step + 128) | (uint32_t)ts0 << 8 | (uint32_t)ts1 << 13 | (uint32_t)ts2 << 18 | ((geo >> 18) & 15u) << 23 |
+                  ((geo >> 22) & 7u) << 27 | (uint32_t)have << 30;
+            r.z = la;
+            r.w = 0u;
+            var[gs * 16 + lane] = r;
+        }
+        cntw = __reduce_or_sync(FULL, cntw);
+        if (lane == 0) sum[gs] = cntw;
+    }
+}
+
+// The reference's own sequential search for ONE granule with the true state (the slow path of k_enc_resolve).
+__device__ __noinline__ void search_granule(const RateSmem &S, const int32_t *__restrict__ mdct_g, int32_t xrmax, int max_bits, int hn,
+                                            uint32_t hb, int lane, int &a1, int &a2, int &a3, int &step, GranInfo &gi, int &part23)
+{
+    uint32_t ax[9], ay[9], qx[9], qy[9], sg;
+    load_granule(mdct_g, lane, ax, ay, sg);
+    gi.bv = 0; gi.count1 = 0; gi.c1sel = 0; gi.r0 = 0; gi.r1 = 0; gi.ts0 = 0; gi.ts1 = 0; gi.ts2 = 0;
+    int next = -120, count = 120, half = 0, bits = 0, s = 0;
+    bool in_bin = true;
+    for (;;) {
+        bool ovf = false;
+        if (in_bin) {
+            half = count / 2;
+            s = next + half;
+            ovf = quant_max(S, xrmax, s) > 8192;
+        } else {
+            while (quant_max(S, xrmax, step + 1) > 8192) step++;
+            step++;
+            s = step;
+        }
+        bits = 100000;
+        if (!ovf) {
+            Pooled P;
+            quantize_all(S, ax, ay, s, qx, qy);
+            probe_pool(S, qx, qy, lane, a1, a2, a3, P);
+            a1 = P.a1; a2 = P.a2; a3 = P.a3;
+            bits = probe_tables(S, P, true, hn, hb, gi);
+        }
+        if (in_bin) {
+            if (bits < max_bits) count = half;
+            else { next += half; count -= half; }
+            if (count <= 1) { in_bin = false; step = next; }
+        } else if (bits <= max_bits) break;
+    }
+    part23 = bits;
+}
+
+// "latest value at or before my lane among the lanes of my slot" (lanes 4 apart), VAR_NONE where a lane has nothing to say
+__device__ __forceinline__ uint32_t slot_scan(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int d = 4; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d && v == VAR_NONE) v = t;
+    }
+    return v;
+}
+
+#define RESOLVE_WARPS 2
+__global__ void __launch_bounds__(32 * RESOLVE_WARPS)
+k_enc_resolve(const M3sEncClip *__restrict__ clips, int n_clips, M3sEncState *__restrict__ states, const M3sDevTables *__restrict__ T,
+              const EncTables *__restrict__ ET, const uint32_t *__restrict__ byteoff, const uint8_t *__restrict__ payload, int sr_idx,
+              int whole_slots, int32_t chunk_first, int32_t chunk_frames, const int32_t *__restrict__ mdct,
+              const M3sEncStats *__restrict__ stats, const uint4 *__restrict__ var, uint32_t *__restrict__ sum, int32_t *__restrict__ info)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RateSmem &S = *reinterpret_cast<RateSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    rate_tables_load(S, T, ET, sr_idx, tid, 32 * RESOLVE_WARPS);
+    __syncthreads();
+    const int c = blockIdx.x * RESOLVE_WARPS + warp;
+    if (c >= n_clips) return;
+    const M3sEncClip cl = clips[c];
+    const int f_end = min(cl.n_frames, chunk_first + chunk_frames);
+    if (f_end <= chunk_first) return;
+    const int ng = 4 * (f_end - chunk_first);
+    const bool hiding = cl.payload_len > 0;
+    M3sEncState *sp = states + c;
+    int64_t off = sp->hide_off;
+    const int q = lane & 3, slot = 2 * (q & 1) + (q >> 1);   // my position in the reference's order; the (gr, ch) slot it belongs to
+    // carried slot state, replicated in every lane of the slot
+    uint32_t car_a = (uint32_t)sp->a1[slot] | (uint32_t)sp->a2[slot] << 10 | (uint32_t)sp->a3[slot] << 20;
+    uint32_t car_step = (uint32_t)(sp->step[slot] + 128);    // steps travel as step + 128 (8..128) so that none collides with VAR_NONE
+    uint32_t car_src = (uint32_t)sp->src[slot];
+#pragma unroll 1
+    for (int gb = 0; gb < ng; gb += 32) {
+        const int i = gb + lane;
+        const bool valid = i < ng;
+        const int f = chunk_first + (i >> 2);
+        const int64_t fl_ = cl.frame_base + f;
+        const int64_t gs = fl_ * 4 + q;
+        const uint32_t wsum = valid ? sum[gs] : VAR_SILENT;
+        // payload window: the 128 chars from `off` on (a batch consumes at most 96)
+        const int64_t woff = off;
+        uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        if (hiding) {
+            const uint8_t *pp = payload + cl.payload_base;
+            const int64_t i0 = woff + lane;
+            w0 = __ballot_sync(FULL, i0 < cl.payload_len && __ldg(pp + i0) == '1');
+            w1 = __ballot_sync(FULL, i0 + 32 < cl.payload_len && __ldg(pp + i0 + 32) == '1');
+            w2 = __ballot_sync(FULL, i0 + 64 < cl.payload_len && __ldg(pp + i0 + 64) == '1');
+            w3 = __ballot_sync(FULL, i0 + 96 < cl.payload_len && __ldg(pp + i0 + 96) == '1');
+        }
+        auto bits_at = [&](int64_t o, int &hn, uint32_t &hb) {
+            const int64_t left = cl.payload_len - o;
+            hn = !hiding ? 0 : (left > 3 ? 3 : (left < 0 ? 0 : (int)left));
+            const int rel = (int)(o - woff), k = rel >> 5;
+            const uint32_t lo = k == 0 ? w0 : (k == 1 ? w1 : (k == 2 ? w2 : w3));
+            const uint32_t hi = k == 0 ? w1 : (k == 1 ? w2 : (k == 2 ? w3 : 0u));
+            hb = __funnelshift_r(lo, hi, rel & 31) & ((1u << hn) - 1u);
+        };
+        // per-lane results of my granule
+        int r_p23 = 0, r_bv = 0, r_c1 = 0, r_c1sel = 0, r_ts0 = 0, r_ts1 = 0, r_ts2 = 0, r_r0 = 0, r_r1 = 0, r_cnt = 0;
+        uint32_t r_a = 0, r_step = 0, r_src = 0;
+        int64_t my_off = 0;
+        int i0 = 0;
+        while (i0 < 32) {
+            // ---- sequential part: offset -> variant -> bits consumed, registers only
+            int my_v = 14, stop = 32;
+#pragma unroll 1
+            for (int j = i0; j < 32; j++) {
+                const uint32_t ws = __shfl_sync(FULL, wsum, j);
+                if (ws & VAR_SLOW) { stop = j; break; }
+                int v = 14, cnt = 0;
+                if (!(ws & VAR_SILENT)) {
+                    int hn;
+                    uint32_t hb;
+                    bits_at(off, hn, hb);
+                    v = variant_index(hn, hb);
+                    cnt = (int)((ws >> (2 * v)) & 3u);
+                }
+                if (lane == j) { my_v = v; my_off = off; r_cnt = cnt; }
+                off += cnt;
+            }
+            // ---- parallel part: lanes [i0, stop) fetch the chosen variant's record
+            const bool mine = lane >= i0 && lane < stop && valid;
+            const bool live = mine && !(wsum & VAR_SILENT);
+            uint32_t va = VAR_NONE, vs = VAR_NONE, vsrc = VAR_NONE;
+            if (live) {
+                const uint4 r = var[gs * 16 + my_v];
+                r_p23 = (int)(r.x & 0xFFFu); r_bv = (int)((r.x >> 12) & 0x1FFu); r_c1 = (int)((r.x >> 21) & 0xFFu); r_c1sel = (int)((r.x >> 29) & 1u);
+                vs = r.y & 0xFFu;
+                r_ts0 = (int)((r.y >> 8) & 31u); r_ts1 = (int)((r.y >> 13) & 31u); r_ts2 = (int)((r.y >> 18) & 31u);
+                r_r0 = (int)((r.y >> 23) & 15u); r_r1 = (int)((r.y >> 27) & 7u);
+                if ((r.y >> 30) & 1u) va = r.z;
+                vsrc = (uint32_t)(f + 1);
+            }
+            va = slot_scan(va, lane); vs = slot_scan(vs, lane); vsrc = slot_scan(vsrc, lane);
+            if (va == VAR_NONE) va = car_a;
+            if (vs == VAR_NONE) vs = car_step;
+            if (vsrc == VAR_NONE) vsrc = car_src;
+            if (mine) { r_a = va; r_step = vs; r_src = vsrc; }
+            car_a = __shfl_sync(FULL, va, 28 + q); car_step = __shfl_sync(FULL, vs, 28 + q); car_src = __shfl_sync(FULL, vsrc, 28 + q);
+            if (stop == 32) break;
+            // ---- granule `stop` depends on the slot's stale addresses: the reference's own search with the true state
+            {
+                const int j = stop, jq = j & 3;
+                const uint32_t sa = __shfl_sync(FULL, car_a, jq);
+                int a1 = (int)(sa & 1023u), a2 = (int)((sa >> 10) & 1023u), a3 = (int)((sa >> 20) & 1023u);
+                int step = (int)__shfl_sync(FULL, car_step, jq) - 128;
+                const int fj = chunk_first + ((gb + j) >> 2);
+                const int64_t gsj = (cl.frame_base + fj) * 4 + jq;
+                int padding, mean_bits, hn, part23 = 0;
+                uint32_t hb;
+                const int max_bits = frame_max_bits(byteoff, fj, whole_slots, padding, mean_bits);
+                bits_at(off, hn, hb);
+                GranInfo gi;
+                search_granule(S, mdct + gsj * 576, stats[gsj].xrmax, max_bits, hn, hb, lane, a1, a2, a3, step, gi, part23);
+                const int cnt = (gi.ts0 > 0) + (gi.ts1 > 0) + (gi.ts2 > 0);
+                const uint32_t na = (uint32_t)a1 | (uint32_t)a2 << 10 | (uint32_t)a3 << 20;
+                if (lane == j) {
+                    my_off = off; r_cnt = cnt; r_p23 = part23; r_bv = gi.bv; r_c1 = gi.count1; r_c1sel = gi.c1sel;
+                    r_ts0 = gi.ts0; r_ts1 = gi.ts1; r_ts2 = gi.ts2; r_r0 = gi.r0; r_r1 = gi.r1;
+                    r_a = na; r_step = (uint32_t)(step + 128); r_src = (uint32_t)(fj + 1);
+                }
+                if (q == jq) { car_a = na; car_step = (uint32_t)(step + 128); car_src = (uint32_t)(fj + 1); }
+                off += cnt;
+                i0 = j + 1;
+            }
+        }
+        // ---- per frame (4 lanes): resv_frame_end (:1097-1145) -- every unused bit of the frame becomes stuffing -- and the records
+        {
+            int padding = 0, mean_bits = 0;
+            if (valid) frame_max_bits(byteoff, f, whole_slots, padding, mean_bits);
+            const int base = lane & ~3;
+            // part2_3_length in the order gr0ch0, gr0ch1, gr1ch0, gr1ch1 = my positions 0, 2, 1, 3
+            int p23[4];
+            p23[0] = __shfl_sync(FULL, r_p23, base); p23[1] = __shfl_sync(FULL, r_p23, base + 2);
+            p23[2] = __shfl_sync(FULL, r_p23, base + 1); p23[3] = __shfl_sync(FULL, r_p23, base + 3);
+            const int64_t off_after = __shfl_sync(FULL, my_off + r_cnt, base + 3);
+            int stuffing = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) stuffing += mean_bits / 2 - p23[k];   // :812 (mean_bits is even)
+            if (stuffing > 0) {
+                if (p23[0] + stuffing < 4095) p23[0] += stuffing;
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int t = min(4095 - p23[k], max(stuffing, 0));
+                        p23[k] += t;
+                        stuffing -= t;
+                    }
+                }
+            }
+            if (valid) {
+                const int mine23 = slot == 0 ? p23[0] : (slot == 1 ? p23[1] : (slot == 2 ? p23[2] : p23[3]));
+                const int step = (int)r_step - 128;
+                int4 *r = (int4 *)(info + (fl_ * 4 + slot) * ENC_INFO_FIELDS);
+                r[0] = make_int4(mine23, r_bv, r_c1, step + 210);
+                r[1] = make_int4(r_ts0, r_ts1, r_ts2, r_r0);
+                r[2] = make_int4(r_r1, r_c1sel, (int)(r_a & 1023u), (int)((r_a >> 10) & 1023u));
+                r[3] = make_int4((int)((r_a >> 20) & 1023u), step, padding, (int)off_after);
+                sum[gs] = r_src;   // the summary word has been consumed: the emit kernel finds the source frame of a silent granule here
+            }
+        }
+    }
+    // ---- hand the state to the next chunk
+    if (lane < 4) {
+        sp->a1[slot] = (int32_t)(car_a & 1023u); sp->a2[slot] = (int32_t)((car_a >> 10) & 1023u); sp->a3[slot] = (int32_t)((car_a >> 20) & 1023u);
+        sp->step[slot] = (int32_t)car_step - 128;
+        sp->src[slot] = (int32_t)car_src;
+        if (lane == 0) sp->hide_off = off;
+    }
+}
+
+// One warp per granule-channel: quantise at the chosen step and write the signed values format_bitstream codes (:1272-1276).
+// A silent granule keeps what l3_enc held for its slot (never coded: big_values = count1 = 0): the values of the latest
+// non-silent granule of the slot, re-derived from that granule's spectra, or read from `last_in` when it lies in an earlier chunk.
+#define EMIT_WARPS 8
+#define EMIT_G 8
+__global__ void __launch_bounds__(32 * EMIT_WARPS)
+k_enc_emit(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ frame_clip, const M3sDevTables *__restrict__ T,
+           const EncTables *__restrict__ ET, int sr_idx, int32_t chunk_first, int32_t chunk_frames, int64_t n_gran,
+           const int32_t *__restrict__ mdct, const M3sEncStats *__restrict__ stats, const uint32_t *__restrict__ srcs,
+           const int32_t *__restrict__ info, uint32_t *__restrict__ ixout, const uint32_t *__restrict__ last_in,
+           uint32_t *__restrict__ last_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RateSmem &S = *reinterpret_cast<RateSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    rate_tables_load(S, T, ET, sr_idx, tid, 32 * EMIT_WARPS);
+    __syncthreads();
+    const int64_t g0 = (int64_t)blockIdx.x * (EMIT_WARPS * EMIT_G) + warp;
+#pragma unroll 1
+    for (int it = 0; it < EMIT_G; it++) {
+        const int64_t gs = g0 + (int64_t)it * EMIT_WARPS;
+        if (gs >= n_gran) break;
+        const int64_t fl_ = gs >> 2;
+        const int q = (int)(gs & 3), slot = 2 * (q & 1) + (q >> 1);
+        const int c = frame_clip[fl_];
+        const int f = (int)(fl_ - clips[c].frame_base);
+        const int n_frames = clips[c].n_frames;
+        const int src = (int)srcs[gs] - 1;                   // clip frame whose values this slot holds (-1: none yet)
+        uint32_t out[9];
+        if (src < 0) {
+#pragma unroll
+            for (int j = 0; j < 9; j++) out[j] = 0u;
+        } else if (src < chunk_first) {
+            const uint32_t *lp = last_in + ((int64_t)c * 4 + q) * 288;
+#pragma unroll
+            for (int j = 0; j < 9; j++) out[j] = lp[32 * j + lane];
+        } else {
+            const int64_t back = f - src;                    // 0 for a granule that was coded itself
+            const int step = info[((fl_ - back) * 4 + slot) * ENC_INFO_FIELDS + 13];
+            uint32_t ax[9], ay[9], qx[9], qy[9], sg;
+            load_granule(mdct + (gs - 4 * back) * 576, lane, ax, ay, sg);
+            quantize_all(S, ax, ay, step, qx, qy);
+#pragma unroll
+            for (int j = 0; j < 9; j++) {
+                const int vx = ((sg >> (2 * j)) & 1u) ? -(int)qx[j] : (int)qx[j];
+                const int vy = ((sg >> (2 * j + 1)) & 1u) ? -(int)qy[j] : (int)qy[j];
+                out[j] = ((uint32_t)vx & 0xFFFFu) | ((uint32_t)vy << 16);
+            }
+        }
+        uint32_t *ixd = ixout + gs * 288;
+#pragma unroll
+        for (int j = 0; j < 9; j++) ixd[32 * j + lane] = out[j];
+        const int f_end = min(n_frames, chunk_first + chunk_frames);
+        if (f == f_end - 1 && f_end < n_frames) {            // what the slot holds when the next chunk starts
+            uint32_t *lp = last_out + ((int64_t)c * 4 + q) * 288;
+#pragma unroll
+            for (int j = 0; j < 9; j++) lp[32 * j + lane] = out[j];
+        }
     }
 }
 
@@ -1046,7 +1595,10 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     M3S_CUDA(h, cudaMemcpyAsync(h->e_pad.p, byteoff.data(), sizeof(uint32_t) * byteoff.size(), cudaMemcpyHostToDevice, h->stream));
     if ((rc = m3s_buf_reserve(h, h->e_state, sizeof(M3sEncState) * n_clips))) return rc;
     M3S_CUDA(h, cudaMemsetAsync(h->e_state.p, 0, sizeof(M3sEncState) * n_clips, h->stream));
-    if ((rc = m3s_buf_reserve(h, h->e_lastix, (size_t)n_clips * 4 * 288 * 4))) return rc;
+    const size_t lastix_bytes = (size_t)n_clips * 4 * 288 * 4;
+    if ((rc = m3s_buf_reserve(h, h->e_lastix, 2 * lastix_bytes))) return rc;   // two sets: chunk k reads set k & 1 and writes the other
+    // M3S_ENC_CHAIN=1 selects the sequential form of the rate loop (one CTA per clip walking its granules in order)
+    const bool chain = getenv("M3S_ENC_CHAIN") != nullptr;
 
     // ---- chunking: all clips advance together through windows of `cf` frames so that the intermediates
     //      (MDCT spectra 9.2 KB/frame, quantised values 4.6 KB/frame) stay bounded while every clip keeps its warp busy
@@ -1060,16 +1612,25 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     const int nset = n_chunks > 1 ? 2 : 1;   // every per-chunk intermediate exists twice: chunk k uses set k & 1
     M3sBuf *b_mdct[2] = {&h->e_mdct, &h->e_mdct2}, *b_gran[2] = {&h->e_gran, &h->e_gran2}, *b_ix[2] = {&h->e_ix, &h->e_ix2};
     M3sBuf *b_info[2] = {&h->e_info, &h->e_info2}, *b_scfsi[2] = {&h->e_scfsi, &h->e_scfsi2};
+    M3sBuf *b_var[2] = {&h->e_var, &h->e_var2}, *b_sum[2] = {&h->e_sum, &h->e_sum2};
     for (int q = 0; q < nset; q++) {
         if ((rc = m3s_buf_reserve(h, *b_mdct[q], (size_t)chunk_cap * 4 * 576 * 4))) return rc;
         if ((rc = m3s_buf_reserve(h, *b_gran[q], (size_t)chunk_cap * 4 * sizeof(M3sEncStats)))) return rc;
         if ((rc = m3s_buf_reserve(h, *b_ix[q], (size_t)chunk_cap * 4 * 288 * 4))) return rc;
         if ((rc = m3s_buf_reserve(h, *b_info[q], (size_t)chunk_cap * 4 * ENC_INFO_FIELDS * 4))) return rc;
         if ((rc = m3s_buf_reserve(h, *b_scfsi[q], (size_t)chunk_cap * 8))) return rc;
+        if (!chain) {
+            if ((rc = m3s_buf_reserve(h, *b_var[q], (size_t)chunk_cap * 4 * 16 * sizeof(uint4)))) return rc;
+            if ((rc = m3s_buf_reserve(h, *b_sum[q], (size_t)chunk_cap * 4 * sizeof(uint32_t)))) return rc;
+        }
     }
 
-    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
-    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 7 CTAs x 24 KB per SM
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate_chain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 7 CTAs x 24 KB per SM
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem)));
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
+    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
     auto frames_in_chunk = [&](int i, int64_t c0) { return std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0)); };
@@ -1182,18 +1743,43 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         if (chunk_total == 0) break;
         const M3sEncClip *d_clips = (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips;
         M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ana[pb], 0));
+        const bool serial = getenv("M3S_ENC_SERIAL") != nullptr;   // diagnostic: analysis of chunk k+1 only after chunk k is packed (no overlap)
+        const int64_t n_gran = 4 * chunk_total;
+        const int64_t probe_tiles = (n_gran + PROBE_WARPS * PROBE_G - 1) / (PROBE_WARPS * PROBE_G);
+        const int64_t probe_ctas = getenv("M3S_PROBE_CTAS") ? atoll(getenv("M3S_PROBE_CTAS")) : 0;
         M3S_KBEGIN(h, M3S_K_ENC_RATE);
-        k_enc_rate<<<(unsigned)n_clips, 32 * RATE_WARPS, sizeof(RateSmem), h->stream>>>(
-            d_clips, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p,
-            (const uint32_t *)h->e_pad.p, (const uint8_t *)h->e_payload.p, sri, whole, (int32_t)c0, (int32_t)cf, 0,
-            (const int32_t *)b_mdct[pb]->p, (const M3sEncStats *)b_gran[pb]->p, (uint32_t *)b_ix[pb]->p, (int32_t *)b_info[pb]->p,
-            (uint8_t *)b_scfsi[pb]->p, (uint32_t *)h->e_lastix.p);
+        if (chain)
+            k_enc_rate_chain<<<(unsigned)n_clips, 32 * RATE_WARPS, sizeof(RateSmem), h->stream>>>(
+                d_clips, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p,
+                (const uint32_t *)h->e_pad.p, (const uint8_t *)h->e_payload.p, sri, whole, (int32_t)c0, (int32_t)cf, 0,
+                (const int32_t *)b_mdct[pb]->p, (const M3sEncStats *)b_gran[pb]->p, (uint32_t *)b_ix[pb]->p, (int32_t *)b_info[pb]->p,
+                (uint8_t *)b_scfsi[pb]->p, (uint32_t *)h->e_lastix.p);
+        else
+            k_enc_probe<<<(unsigned)std::min<int64_t>(probe_tiles, probe_ctas > 0 ? probe_ctas : probe_tiles), 32 * PROBE_WARPS, sizeof(ProbeSmem), h->stream>>>(
+                d_clips, (const int32_t *)h->e_misc.p + slot_off[k], h->d_tab, (const EncTables *)h->e_tabs.p, (const uint32_t *)h->e_pad.p,
+                sri, whole, n_gran, (const int32_t *)b_mdct[pb]->p, (const M3sEncStats *)b_gran[pb]->p, (uint4 *)b_var[pb]->p,
+                (uint32_t *)b_sum[pb]->p, (uint8_t *)b_scfsi[pb]->p);
         M3S_LAUNCH_CHECK(h);
         M3S_CUDA(h, cudaEventRecord(h->ev_rate[pb], h->stream));
         // queued behind the rate loop's CTAs on purpose: the next chunk's analysis takes what they leave free
-        const bool serial = getenv("M3S_ENC_SERIAL") != nullptr;   // diagnostic: analysis of chunk k+1 only after chunk k is packed (no overlap)
         if (!serial && k + 1 < n_chunks && (rc = launch_analysis(k + 1))) return rc;
         if (host && k + 2 < n_chunks) M3S_CUDA(h, stage_chunk(k + 2));
+        if (!chain) {
+            M3S_KBEGIN(h, M3S_K_ENC_RESOLVE);
+            k_enc_resolve<<<(unsigned)((n_clips + RESOLVE_WARPS - 1) / RESOLVE_WARPS), 32 * RESOLVE_WARPS, sizeof(RateSmem), h->stream>>>(
+                d_clips, n_clips, (M3sEncState *)h->e_state.p, h->d_tab, (const EncTables *)h->e_tabs.p, (const uint32_t *)h->e_pad.p,
+                (const uint8_t *)h->e_payload.p, sri, whole, (int32_t)c0, (int32_t)cf, (const int32_t *)b_mdct[pb]->p,
+                (const M3sEncStats *)b_gran[pb]->p, (const uint4 *)b_var[pb]->p, (uint32_t *)b_sum[pb]->p, (int32_t *)b_info[pb]->p);
+            M3S_LAUNCH_CHECK(h);
+            M3S_KBEGIN(h, M3S_K_ENC_AUX);
+            k_enc_emit<<<(unsigned)((n_gran + EMIT_WARPS * EMIT_G - 1) / (EMIT_WARPS * EMIT_G)), 32 * EMIT_WARPS, sizeof(RateSmem), h->stream>>>(
+                d_clips, (const int32_t *)h->e_misc.p + slot_off[k], h->d_tab, (const EncTables *)h->e_tabs.p, sri, (int32_t)c0, (int32_t)cf,
+                n_gran, (const int32_t *)b_mdct[pb]->p, (const M3sEncStats *)b_gran[pb]->p, (const uint32_t *)b_sum[pb]->p,
+                (const int32_t *)b_info[pb]->p, (uint32_t *)b_ix[pb]->p,
+                (const uint32_t *)((const char *)h->e_lastix.p + (size_t)(k & 1) * lastix_bytes),
+                (uint32_t *)((char *)h->e_lastix.p + (size_t)((k + 1) & 1) * lastix_bytes));
+            M3S_LAUNCH_CHECK(h);
+        }
         // packing stays on the rate loop's stream: next to the analysis it would only slow the critical chain further
         M3S_KBEGIN(h, M3S_K_ENC_PACK);
         k_enc_pack<<<(unsigned)((chunk_total + PACK_WARPS - 1) / PACK_WARPS), 32 * PACK_WARPS, sizeof(PackSmem), h->stream>>>(
