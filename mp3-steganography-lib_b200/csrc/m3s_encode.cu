@@ -762,7 +762,6 @@ k_enc_rate_chain(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__
 //                  stale addresses (flagged by the probe kernel) are redone here with the true state;
 //   k_enc_emit     one warp per granule quantises at the chosen step and writes the values the packer reads.
 // ================================================================================================
-#define PROBE_WARPS 8
 #define PROBE_G 8            // granules per warp of k_enc_probe (amortises the CTA's table staging)
 #define PROBE_CACHE 24       // distinct steps cached per granule; more than that (never seen) sends the granule to the resolve kernel
 #define VAR_SILENT 0x80000000u
@@ -786,11 +785,6 @@ struct ProbeWarpSmem {
     ProbeRow row[PROBE_CACHE];
     uint8_t slotmap[128];    // step + 120 -> cache row (0xFF = not computed yet)
 };
-struct ProbeSmem {
-    RateSmem R;
-    ProbeWarpSmem W[PROBE_WARPS];
-};
-
 // variant v <-> (bits left, their values): 0..7 three bits, 8..11 two, 12..13 one, 14 none (also: plain encode)
 __device__ __forceinline__ void variant_bits(int v, int &hn, uint32_t &hb)
 {
@@ -825,25 +819,241 @@ __device__ __forceinline__ int frame_max_bits(const uint32_t *__restrict__ byteo
     return min(mean_bits / 2, 4095);                         // :894-912 with the reservoir never enabled (A.E7)
 }
 
-__global__ void __launch_bounds__(32 * PROBE_WARPS, 3)
-k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ frame_clip, const M3sDevTables *__restrict__ T,
+// Shared-memory tables of k_enc_probe.  The quantiser table carries, next to int2idx[ln], what the passes after it would
+// otherwise re-derive per value: the value clamped to 15 in BOTH nibble positions of a Huffman-table index byte and the
+// "non-zero" / "above one" flags in both positions of a pair's flag group, so that one LOP3 merges the two values of a pair
+// into (index byte, flag group):  M = (ex & XROLE) | (ey & ~XROLE).
+#define I2X_XROLE 0x05F00000u   // bits an entry contributes as the FIRST value of a pair: index nibble [20:24), non-zero [24], above-one [26]
+struct ProbeTab {
+    uint32_t i2x[10000];     // q | min(q,15) << 16 | min(q,15) << 20 | (q != 0) * 0x03000000 | (q > 1) * 0x0C000000
+    uint2 hlc[256];          // .x = code lengths of books 13 | 15 << 8 | 16 << 16 | 24 << 24 at [x * 16 + y], .y = signs | escapes << 16
+    int32_t steptabi[128];
+    double steptab[128];
+    uint16_t sfb[24];
+    uint8_t linbits[32];
+    uint8_t subdv[23][2];
+    uint8_t pair[32][2];
+};
+template <int NW>
+struct ProbeSmem {
+    ProbeTab T;
+    ProbeWarpSmem W[NW];
+};
+
+__device__ __forceinline__ uint32_t i2x_entry(uint32_t q)
+{
+    const uint32_t c = min(q, 15u);
+    return q | c << 16 | c << 20 | (q != 0 ? 0x03000000u : 0u) | (q > 1 ? 0x0C000000u : 0u);
+}
+
+// quantize() of one value (:374-415) as a table entry
+__device__ __forceinline__ uint32_t quant_entry(const ProbeTab &T, uint32_t a, int32_t scalei, double scale)
+{
+    const int32_t ln = mulr32((int32_t)a, scalei);
+    if (ln < 10000) return T.i2x[ln];
+    return i2x_entry((uint32_t)quant_slow((int32_t)a, scale));
+}
+
+// quantize() > 8192 for the granule's largest coefficient (ix is monotone in |xr|)
+__device__ __forceinline__ bool quant_overflows(const ProbeTab &T, int32_t xrmax, int step)
+{
+    const int32_t ln = mulr32(xrmax, T.steptabi[step + 127]);
+    if (ln > 165140) return true;
+    if (ln < 10000) return false;   // int2idx stays below 1000
+    return quant_slow(xrmax, T.steptab[step + 127]) > 8192;
+}
+
+// count_bit() of table t over a region from the region's pooled sums (:215-263); lo = books 13 | 16 << 16, hi = books 15 | 24 << 16
+__device__ __forceinline__ int table_cost_p(const ProbeTab &T, int t, uint32_t lo, uint32_t hi, uint32_t cnt)
+{
+    const int nsign = cnt & 0xFFFF, n15 = cnt >> 16;
+    if (t == 0) return 0;
+    if (t == 13) return (int)(lo & 0xFFFF) + nsign;
+    if (t == 15) return (int)(hi & 0xFFFF) + nsign;
+    return (int)(t < 24 ? (lo >> 16) : (hi >> 16)) + nsign + (int)T.linbits[t] * n15;
+}
+
+// One probe = quantize + calc_run_len + count1_bit_count + subdivide + the table choice and bit count of every region under
+// "no swap / swap by 0 / swap by 1", for step `sc`; written to row R by lanes 0..2.  Returns false when the probe reads the
+// slot's stale addresses that only the resolve kernel knows (big_values == 0 among non-zero values before any probe of this walk
+// had big values, A.E6).
+__device__ __forceinline__ bool probe_row(const ProbeTab &T, const uint32_t (&ax)[9], const uint32_t (&ay)[9], int32_t xrmax, int sc, int lane,
+                                          int lhave, uint32_t lla, ProbeRow &R)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int32_t scalei = T.steptabi[sc + 127];
+    uint32_t M[9], X[9], accA = 0, accB = 0;
+    // ---- quantize (:374-415): M = index byte + flag group of the pair, X = the larger entry (entries are monotone in the value)
+    if (mulr32(xrmax, scalei) < 10000) {
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const uint32_t ex = T.i2x[mulr32((int32_t)ax[j], scalei)], ey = T.i2x[mulr32((int32_t)ay[j], scalei)];
+            M[j] = (ex & I2X_XROLE) | (ey & ~I2X_XROLE);
+            X[j] = max(ex, ey);
+        }
+    } else {
+        const double scale = T.steptab[sc + 127];
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const uint32_t ex = quant_entry(T, ax[j], scalei, scale), ey = quant_entry(T, ay[j], scalei, scale);
+            M[j] = (ex & I2X_XROLE) | (ey & ~I2X_XROLE);
+            X[j] = max(ex, ey);
+        }
+    }
+    // flag groups {x != 0, y != 0, x > 1, y > 1} of my pairs: pair j at accA[4j : 4j + 4), pair 8 in accB
+#pragma unroll
+    for (int j = 0; j < 8; j++) accA |= j < 6 ? (M[j] & 0x0F000000u) >> (24 - 4 * j) : (M[j] & 0x0F000000u) << (4 * j - 24);
+    accB = (M[8] >> 24) & 15u;
+    // ---- calc_run_len (:266-291)
+    uint32_t lastnz = 0, lastbig = 0;
+    {
+        const uint32_t nzA = accA & 0x33333333u, bgA = accA & 0xCCCCCCCCu;
+        if (accB & 3u) lastnz = 256 + lane + 1;
+        else if (nzA) lastnz = 32 * ((31 - __clz(nzA)) >> 2) + lane + 1;
+        if (accB & 12u) lastbig = 2 * (256 + lane) + 1 + ((accB >> 3) & 1u);
+        else if (bgA) {
+            const int pos = 31 - __clz(bgA);
+            lastbig = 2 * (32 * (pos >> 2) + lane) + 1 + (pos & 1);
+        }
+    }
+    lastnz = __reduce_max_sync(FULL, lastnz);
+    lastbig = __reduce_max_sync(FULL, lastbig);
+    const int i_end = 2 * (int)lastnz;
+    const int count1 = (i_end - (int)lastbig) >> 2;
+    const int bv = (i_end - 4 * count1) >> 1;
+    // ---- count1_bit_count (:171-211): quads start at pair bv; the partner pair lives in the next lane (lane 31: lane 0, next row)
+    int c1bits, c1sel;
+    {
+        uint32_t nbA = __shfl_sync(FULL, accA, (lane + 1) & 31), nbB = __shfl_sync(FULL, accB, (lane + 1) & 31);
+        if (lane == 31) { nbA = (nbA >> 4) | (nbB << 28); nbB = 0; }
+        uint32_t c1s = 0;
+        const int c1end = bv + 2 * count1;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            if (32 * j + 31 >= bv && 32 * j < c1end) {   // warp-uniform: the row overlaps the count1 region
+                const int rel = 32 * j + lane - bv;
+                const uint32_t me = j < 8 ? (accA >> (4 * j)) & 3u : accB & 3u, nx = j < 8 ? (nbA >> (4 * j)) & 3u : nbB & 3u;
+                const uint32_t idx = me | (nx << 2);  // v + 2 w + 4 x + 8 y
+                const uint32_t nn = __popc(idx);
+                // code lengths: table A = {1,4,4,5,4,6,5,6,4,5,5,6,5,6,6,6} (one nibble each), table B = 4 everywhere
+                const uint32_t la4 = ((idx & 8u ? 0x66656554u : 0x65645441u) >> (4 * (idx & 7u))) & 15u;
+                if (rel >= 0 && rel < 2 * count1 && !(rel & 1)) c1s += (la4 + nn) | ((4u + nn) << 16);
+            }
+        }
+        c1s = __reduce_add_sync(FULL, c1s);
+        if ((c1s & 0xFFFF) < (c1s >> 16)) { c1sel = 0; c1bits = (int)(c1s & 0xFFFF); }
+        else { c1sel = 1; c1bits = (int)(c1s >> 16); }
+    }
+    // ---- subdivide (:998-1036); with big_values == 0 the addresses keep their old values (A.E6)
+    int a1 = (int)(lla & 1023u), a2 = (int)((lla >> 10) & 1023u), a3 = (int)((lla >> 20) & 1023u), r0 = 0, r1 = 0;
+    const bool uses_addr = bv == 0 && count1 > 0;
+    if (uses_addr && !lhave) return false;
+    if (bv != 0) {
+        const int bvr = 2 * bv;
+        const int anz = __popc(__ballot_sync(FULL, lane < 23 && (int)T.sfb[lane] < bvr));
+        int tc = T.subdv[anz][0];
+        while (tc > 0 && (int)T.sfb[tc + 1] > bvr) tc--;
+        r0 = tc;
+        a1 = T.sfb[tc + 1];
+        const int base = tc + 1;
+        tc = T.subdv[anz][1];
+        while (tc > 0 && (int)T.sfb[min(base + tc + 1, 23)] > bvr) tc--;
+        r1 = tc;
+        a2 = T.sfb[min(base + tc + 1, 23)];
+        a3 = bvr;
+    }
+    // ---- pooled region sums over pairs [0, a1/2) [a1/2, a2/2) [a2/2, bv)   (:1147-1168, :294-318); per lane a region holds at
+    //      most 9 pairs of code length <= 19, so the four books' sums travel as the four bytes of the table word
+    uint32_t A0 = 0, A1 = 0, A2 = 0, C0 = 0, C1 = 0, C2 = 0, m0 = 0, m1 = 0, m2 = 0;
+    {
+        const int h1 = a1 >> 1, h2 = a2 >> 1;          // region bounds are even (scalefactor band edges)
+        const int pend = max(bv, max(h1, h2));
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            if (32 * j < pend) {   // warp-uniform
+                const int p = 32 * j + lane;
+                const uint2 w2 = T.hlc[(M[j] >> 16) & 0xFFu];
+                if (p < h1) { A0 += w2.x; C0 += w2.y; m0 = max(m0, X[j]); }
+                else if (p < h2) { A1 += w2.x; C1 += w2.y; m1 = max(m1, X[j]); }
+                else if (p < bv) { A2 += w2.x; C2 += w2.y; m2 = max(m2, X[j]); }
+            }
+        }
+    }
+    // lanes 0..2 end up with the totals of region `lane`: every lane contributes to all three reductions
+    uint32_t lo = 0, hi = 0, cn = 0, mx = 0;
+    {
+        const uint32_t l0 = __reduce_add_sync(FULL, A0 & 0x00FF00FFu), h0 = __reduce_add_sync(FULL, (A0 >> 8) & 0x00FF00FFu);
+        const uint32_t l1 = __reduce_add_sync(FULL, A1 & 0x00FF00FFu), h1_ = __reduce_add_sync(FULL, (A1 >> 8) & 0x00FF00FFu);
+        const uint32_t l2 = __reduce_add_sync(FULL, A2 & 0x00FF00FFu), h2_ = __reduce_add_sync(FULL, (A2 >> 8) & 0x00FF00FFu);
+        const uint32_t c0 = __reduce_add_sync(FULL, C0), c1 = __reduce_add_sync(FULL, C1), c2 = __reduce_add_sync(FULL, C2);
+        const uint32_t x0 = __reduce_max_sync(FULL, m0), x1 = __reduce_max_sync(FULL, m1), x2 = __reduce_max_sync(FULL, m2);
+        const int r = lane == 0 ? 0 : (lane == 1 ? 1 : 2);
+        lo = r == 0 ? l0 : (r == 1 ? l1 : l2); hi = r == 0 ? h0 : (r == 1 ? h1_ : h2_);
+        cn = r == 0 ? c0 : (r == 1 ? c1 : c2); mx = (r == 0 ? x0 : (r == 1 ? x1 : x2)) & 0xFFFFu;
+    }
+    // ---- new_choose_table (:1170-1264) before the swap, and the cost of the region under the choice and under either swap
+    {
+        const int r = lane == 0 ? 0 : (lane == 1 ? 1 : 2);
+        const bool exists = r == 0 ? a1 > 0 : (r == 1 ? a2 > a1 : 2 * bv > a2);
+        int ch0 = 0;
+        if (exists && mx != 0) {
+            if (mx < 15) {
+                ch0 = 13;  // the count-down search always stops at 13 (A.E4); only its 13-vs-15 arm is live
+                if (table_cost_p(T, 15, lo, hi, cn) <= table_cost_p(T, 13, lo, hi, cn)) ch0 = 15;
+            } else {
+                // first table of 15..23 / 24..31 whose lin_max covers mx - 15: a function of the bit length of mx - 15 (<= 13 bits)
+                const int nb = 32 - __clz((int)mx - 15);
+                const int c0 = 15 + (int)((0x88877665543210ULL >> (4 * nb)) & 15);
+                const int c1 = 24 + (int)((0x77665432100000ULL >> (4 * nb)) & 15);
+                ch0 = c0;
+                if (table_cost_p(T, c1, lo, hi, cn) < table_cost_p(T, c0, lo, hi, cn)) ch0 = c1;
+            }
+        }
+        const int t0 = T.pair[ch0][0], t1 = T.pair[ch0][1];
+        const uint32_t nz = __ballot_sync(FULL, ch0 > 0);
+        if (lane < 3) {
+            R.cost[r][0] = (uint16_t)table_cost_p(T, ch0, lo, hi, cn);
+            R.cost[r][1] = (uint16_t)table_cost_p(T, t0, lo, hi, cn);
+            R.cost[r][2] = (uint16_t)table_cost_p(T, t1, lo, hi, cn);
+            R.tab[r][0] = (uint8_t)ch0; R.tab[r][1] = (uint8_t)t0; R.tab[r][2] = (uint8_t)t1;
+        }
+        if (lane == 0) {
+            R.c1bits = c1bits;
+            R.geo = (uint32_t)bv | (uint32_t)count1 << 9 | (uint32_t)c1sel << 17 | (uint32_t)r0 << 18 | (uint32_t)r1 << 22 | (nz & 3u) << 25;
+            R.addr = (uint32_t)a1 | (uint32_t)a2 << 10 | (uint32_t)a3 << 20;
+            R.tag = uses_addr ? lla : VAR_NONE;
+        }
+    }
+    return true;
+}
+
+template <int PROBE_WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(32 * PROBE_WARPS, MIN_CTAS)
+k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ frame_clip, const M3sDevTables *__restrict__ DT,
             const EncTables *__restrict__ ET, const uint32_t *__restrict__ byteoff, int sr_idx, int whole_slots, int64_t n_gran,
             const int32_t *__restrict__ mdct, const M3sEncStats *__restrict__ stats, uint4 *__restrict__ var,
             uint32_t *__restrict__ sum, uint8_t *__restrict__ scfsi_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ProbeSmem &PS = *reinterpret_cast<ProbeSmem *>(smem_raw);
-    RateSmem &S = PS.R;
+    ProbeSmem<PROBE_WARPS> &PS = *reinterpret_cast<ProbeSmem<PROBE_WARPS> *>(smem_raw);
+    ProbeTab &T = PS.T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t FULL = 0xFFFFFFFFu;
     ProbeWarpSmem &W = PS.W[warp];
-    rate_tables_load(S, T, ET, sr_idx, tid, 32 * PROBE_WARPS);
+    for (int i = tid; i < 10000; i += 32 * PROBE_WARPS) T.i2x[i] = i2x_entry((uint32_t)DT->int2idx[i]);
+    for (int i = tid; i < 256; i += 32 * PROBE_WARPS) {
+        const uint32_t x = i >> 4, y = i & 15;
+        T.hlc[i] = make_uint2(ET->hl4[i], (uint32_t)(x != 0) + (uint32_t)(y != 0) + (((uint32_t)(x > 14) + (uint32_t)(y > 14)) << 16));
+    }
+    for (int i = tid; i < 128; i += 32 * PROBE_WARPS) { T.steptabi[i] = DT->steptabi[i]; T.steptab[i] = DT->steptab[i]; }
+    if (tid < 24) T.sfb[tid] = tid < 23 ? DT->sfb_long[sr_idx][tid] : 576;
+    if (tid < 32) { T.linbits[tid] = DT->enc_linbits[tid]; T.pair[tid][0] = DT->pair[tid][0]; T.pair[tid][1] = DT->pair[tid][1]; }
+    if (tid < 23) { T.subdv[tid][0] = DT->subdv[tid][0]; T.subdv[tid][1] = DT->subdv[tid][1]; }
     __syncthreads();
     int vhn;
     uint32_t vhb;
     variant_bits(lane, vhn, vhb);
-    // tiles of PROBE_WARPS * PROBE_G granules; a grid smaller than the tile count walks them with a stride (M3S_PROBE_CTAS: a
-    // fixed number of CTAs per SM leaves room for the analysis kernel of the next chunk to run beside this one)
+    // tiles of PROBE_WARPS * PROBE_G granules; a grid smaller than the tile count walks them with a stride (M3S_PROBE_CTAS)
     const int64_t n_iter = ((n_gran + PROBE_WARPS * PROBE_G - 1) / (PROBE_WARPS * PROBE_G) - blockIdx.x + gridDim.x - 1) / gridDim.x * PROBE_G;
 #pragma unroll 1
     for (int64_t it = 0; it < n_iter; it++) {
@@ -884,6 +1094,17 @@ k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fr
         const bool sure3 = payload_len - 3 * (4 * (int64_t)f + q) >= 3;
         const bool active = hiding ? lane < (sure3 ? 8 : 15) : lane == 14;
         ((uint32_t *)W.slotmap)[lane] = 0xFFFFFFFFu;
+        // quantize(step) > 8192 holds exactly for the steps below s_min (the quantised maximum shrinks as the step grows)
+        int s_min = -120;
+        if (quant_overflows(T, xrmax, -120)) {
+            int n = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int st = -120 + 32 * k + lane;
+                n += __popc(__ballot_sync(FULL, st <= 0 && quant_overflows(T, xrmax, st)));
+            }
+            s_min = -120 + n;
+        }
         __syncwarp();
         // ---- per-lane walk of bin_search_step_size (:958-996) then inner_loop (:1064-1095)
         int next = -120, count = 120, half = 0, step = 0, s = 0, bits = 0, nslots = 0, have = 0, mode0 = 0, mode1 = 0, mode2 = 0;
@@ -895,10 +1116,9 @@ k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fr
                 if (in_bin) {
                     half = count / 2;
                     s = next + half;
-                    ovf = quant_max(S, xrmax, s) > 8192;
+                    ovf = s < s_min;
                 } else {
-                    while (quant_max(S, xrmax, step + 1) > 8192) step++;
-                    step++;
+                    step = max(step, s_min - 1) + 1;   // while quantize(step + 1) > 8192: step += 1; then step += 1
                     s = step;
                 }
             }
@@ -911,42 +1131,11 @@ k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fr
                 const int ldr = __ffs(m) - 1;
                 const int sc = __shfl_sync(FULL, s, ldr);
                 // a probe that finds big_values == 0 among non-zero values pools over the addresses of the latest probe with big values
-                // (A.E6): the requesting lane's own, if its walk has met one in this granule -- else the slot's stale ones, which only
-                // the resolve kernel knows
+                // (A.E6): the requesting lane's own, if its walk has met one in this granule -- else the slot's stale ones
                 const int lhave = __shfl_sync(FULL, have, ldr);
                 const uint32_t lla = __shfl_sync(FULL, la, ldr);
-                uint32_t qx[9], qy[9];
-                if (mulr32(xrmax, S.steptabi[sc + 127]) < 10000) quantize_small(S, ax, ay, sc, qx, qy);
-                else quantize_all(S, ax, ay, sc, qx, qy);
-                Pooled P;
-                probe_pool(S, qx, qy, lane, (int)(lla & 1023u), (int)((lla >> 10) & 1023u), (int)((lla >> 20) & 1023u), P);
-                const bool uses_addr = P.bv == 0 && P.count1 > 0;
-                if (uses_addr && !lhave) { slow = true; break; }
-                // the three regions' table choices and costs, lane r (< 3) takes region r
-                {
-                    const int r = lane % 3;
-                    const uint32_t lo = r == 0 ? P.lo0 : (r == 1 ? P.lo1 : P.lo2), hi = r == 0 ? P.hi0 : (r == 1 ? P.hi1 : P.hi2);
-                    const uint32_t cn = r == 0 ? P.cn0 : (r == 1 ? P.cn1 : P.cn2), mx = r == 0 ? P.m0 : (r == 1 ? P.m1 : P.m2);
-                    const bool exists = r == 0 ? P.a1 > 0 : (r == 1 ? P.a2 > P.a1 : 2 * P.bv > P.a2);
-                    const int ch0 = exists ? choose_table(S, (int)mx, lo, hi, cn, false, 0, 0, 0u) : 0;
-                    const int t0 = S.pair[ch0][0], t1 = S.pair[ch0][1];
-                    const uint32_t nz = __ballot_sync(FULL, ch0 > 0);
-                    ProbeRow &R = W.row[nslots];
-                    if (lane < 3) {
-                        R.cost[r][0] = (uint16_t)table_cost(S, ch0, lo, hi, cn);
-                        R.cost[r][1] = (uint16_t)table_cost(S, t0, lo, hi, cn);
-                        R.cost[r][2] = (uint16_t)table_cost(S, t1, lo, hi, cn);
-                        R.tab[r][0] = (uint8_t)ch0; R.tab[r][1] = (uint8_t)t0; R.tab[r][2] = (uint8_t)t1;
-                    }
-                    if (lane == 0) {
-                        R.c1bits = P.c1bits;
-                        R.geo = (uint32_t)P.bv | (uint32_t)P.count1 << 9 | (uint32_t)P.c1sel << 17 | (uint32_t)P.r0 << 18 | (uint32_t)P.r1 << 22 |
-                                (nz & 3u) << 25;
-                        R.addr = (uint32_t)P.a1 | (uint32_t)P.a2 << 10 | (uint32_t)P.a3 << 20;
-                        R.tag = uses_addr ? lla : VAR_NONE;
-                        W.slotmap[sc + 120] = (uint8_t)nslots;
-                    }
-                }
+                if (!probe_row(T, ax, ay, xrmax, sc, lane, lhave, lla, W.row[nslots])) { slow = true; break; }
+                if (lane == 0) W.slotmap[sc + 120] = (uint8_t)nslots;
                 nslots++;
                 __syncwarp();
             }
@@ -997,6 +1186,7 @@ k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fr
         if (lane == 0) sum[gs] = cntw;
     }
 }
+
 
 // The reference's own sequential search for ONE granule with the true state (the slow path of k_enc_resolve).
 __device__ __noinline__ void search_granule(const RateSmem &S, const int32_t *__restrict__ mdct_g, int32_t xrmax, int max_bits, int hn,
@@ -1627,8 +1817,18 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
 
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_rate_chain, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // 7 CTAs x 24 KB per SM
-    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ProbeSmem)));
-    M3S_CUDA(h, cudaFuncSetAttribute(k_enc_probe, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // shape of the probe kernel's CTAs (warps per CTA, CTAs per SM the register budget allows); M3S_PROBE_CFG picks another for experiments
+    typedef void (*probe_fn_t)(const M3sEncClip *, const int32_t *, const M3sDevTables *, const EncTables *, const uint32_t *, int, int, int64_t,
+                               const int32_t *, const M3sEncStats *, uint4 *, uint32_t *, uint8_t *);
+    static const struct { probe_fn_t fn; int warps; size_t smem; } kProbeCfg[] = {
+        {k_enc_probe<8, 2>, 8, sizeof(ProbeSmem<8>)}, {k_enc_probe<8, 3>, 8, sizeof(ProbeSmem<8>)}, {k_enc_probe<4, 4>, 4, sizeof(ProbeSmem<4>)}};
+    int probe_cfg = getenv("M3S_PROBE_CFG") ? atoi(getenv("M3S_PROBE_CFG")) : 0;
+    if (probe_cfg < 0 || probe_cfg >= (int)(sizeof kProbeCfg / sizeof kProbeCfg[0])) probe_cfg = 0;
+    const probe_fn_t probe_fn = kProbeCfg[probe_cfg].fn;
+    const int probe_warps = kProbeCfg[probe_cfg].warps;
+    const size_t probe_smem = kProbeCfg[probe_cfg].smem;
+    M3S_CUDA(h, cudaFuncSetAttribute(probe_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe_smem));
+    M3S_CUDA(h, cudaFuncSetAttribute(probe_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1745,7 +1945,7 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ana[pb], 0));
         const bool serial = getenv("M3S_ENC_SERIAL") != nullptr;   // diagnostic: analysis of chunk k+1 only after chunk k is packed (no overlap)
         const int64_t n_gran = 4 * chunk_total;
-        const int64_t probe_tiles = (n_gran + PROBE_WARPS * PROBE_G - 1) / (PROBE_WARPS * PROBE_G);
+        const int64_t probe_tiles = (n_gran + probe_warps * PROBE_G - 1) / (probe_warps * PROBE_G);
         const int64_t probe_ctas = getenv("M3S_PROBE_CTAS") ? atoll(getenv("M3S_PROBE_CTAS")) : 0;
         M3S_KBEGIN(h, M3S_K_ENC_RATE);
         if (chain)
@@ -1755,7 +1955,7 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
                 (const int32_t *)b_mdct[pb]->p, (const M3sEncStats *)b_gran[pb]->p, (uint32_t *)b_ix[pb]->p, (int32_t *)b_info[pb]->p,
                 (uint8_t *)b_scfsi[pb]->p, (uint32_t *)h->e_lastix.p);
         else
-            k_enc_probe<<<(unsigned)std::min<int64_t>(probe_tiles, probe_ctas > 0 ? probe_ctas : probe_tiles), 32 * PROBE_WARPS, sizeof(ProbeSmem), h->stream>>>(
+            probe_fn<<<(unsigned)std::min<int64_t>(probe_tiles, probe_ctas > 0 ? probe_ctas : probe_tiles), 32 * probe_warps, probe_smem, h->stream>>>(
                 d_clips, (const int32_t *)h->e_misc.p + slot_off[k], h->d_tab, (const EncTables *)h->e_tabs.p, (const uint32_t *)h->e_pad.p,
                 sri, whole, n_gran, (const int32_t *)b_mdct[pb]->p, (const M3sEncStats *)b_gran[pb]->p, (uint4 *)b_var[pb]->p,
                 (uint32_t *)b_sum[pb]->p, (uint8_t *)b_scfsi[pb]->p);

@@ -33,11 +33,13 @@ def main():
     configs = [("default", {}), ("probe_ctas=296", {"M3S_PROBE_CTAS": "296"}), ("probe_ctas=444", {"M3S_PROBE_CTAS": "444"}),
                ("serial", {"M3S_ENC_SERIAL": "1"}), ("chain (old rate loop)", {"M3S_ENC_CHAIN": "1"}),
                ("chain serial", {"M3S_ENC_CHAIN": "1", "M3S_ENC_SERIAL": "1"})]
-    if len(sys.argv) > 3:   # only the named configurations
-        configs = [c for c in configs if any(c[0].startswith(a) for a in sys.argv[3:])]
+    configs += [(f"cfg{k} serial", {"M3S_PROBE_CFG": str(k), "M3S_ENC_SERIAL": "1"}) for k in range(6)]
+    if len(sys.argv) > 3:   # only the named configurations; "env:A=1,B=2" adds an ad-hoc one
+        adhoc = [(a[4:], dict(kv.split("=") for kv in a[4:].split(","))) for a in sys.argv[3:] if a.startswith("env:")]
+        configs = [c for c in configs if any(c[0].startswith(a) for a in sys.argv[3:])] + adhoc
     ref = None
     for name, env in configs:
-        for k in ("M3S_PROBE_CTAS", "M3S_ENC_SERIAL", "M3S_ENC_CHAIN"):
+        for k in ("M3S_PROBE_CTAS", "M3S_ENC_SERIAL", "M3S_ENC_CHAIN", "M3S_PROBE_CFG"):
             os.environ.pop(k, None)
         os.environ.update(env)
         out.zero_()

@@ -25,20 +25,23 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, cap
 lines = None
 for f in sorted(os.listdir(tmp)):
     txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-    m = re.search(r"^\.text\.(\S*%s\S*):$" % re.escape(kname), txt, re.M)
-    if not m:
-        continue
-    seg = txt[m.end():]
-    nxt = re.search(r"^//-+ \.text\.", seg, re.M)
-    seg = seg[: nxt.start()] if nxt else seg
-    cur, lines = 0, []
-    for ln in seg.splitlines():
-        mm = re.search(r"//## File \"([^\"]+)\", line (\d+)", ln)
-        if mm:
-            cur = (os.path.basename(mm.group(1)), int(mm.group(2)))
-        elif re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
-            lines.append(cur)
-    break
+    base = re.sub(r"<.*", "", kname).split()[-1]
+    for m in re.finditer(r"^\.text\.(\S*%s\S*):$" % re.escape(base), txt, re.M):   # template instances: take the one of equal length
+        seg = txt[m.end():]
+        nxt = re.search(r"^//-+ \.text\.", seg, re.M)
+        seg = seg[: nxt.start()] if nxt else seg
+        cur, cand = 0, []
+        for ln in seg.splitlines():
+            mm = re.search(r"//## File \"([^\"]+)\", line (\d+)", ln)
+            if mm:
+                cur = (os.path.basename(mm.group(1)), int(mm.group(2)))
+            elif re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
+                cand.append(cur)
+        if len(cand) == len(body):
+            lines = cand
+            break
+    if lines is not None:
+        break
 if lines is None or len(lines) != len(body):
     sys.exit(f"cannot align: {0 if lines is None else len(lines)} disassembled vs {len(body)} profiled instructions")
 agg = {}
