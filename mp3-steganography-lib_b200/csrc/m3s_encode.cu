@@ -780,6 +780,7 @@ struct ProbeRow {
     uint32_t tag;             // the addresses the sums were pooled over when the probe read them (big_values == 0, A.E6), else VAR_NONE
     uint16_t cost[3][4];      // [region][mode] count_bit() of the region under table tab[region][mode]
     uint8_t tab[3][4];
+    uint32_t lt, le;          // bit v: variant v's bit count of this probe is < / <= max_bits (the two decisions the step search takes)
 };
 struct ProbeWarpSmem {
     ProbeRow row[PROBE_CACHE];
@@ -833,6 +834,8 @@ struct ProbeTab {
     uint8_t linbits[32];
     uint8_t subdv[23][2];
     uint8_t pair[32][2];
+    uint32_t subdiv[289];    // subdivide() by big_values: region0_count | region1_count << 4 | address1 << 8 | address2 << 18
+    uint32_t c1cost[256];    // count1 quads two at a time: sum over the byte's two 4-bit patterns of (table A bits | table B bits << 16)
 };
 template <int NW>
 struct ProbeSmem {
@@ -863,14 +866,15 @@ __device__ __forceinline__ bool quant_overflows(const ProbeTab &T, int32_t xrmax
     return quant_slow(xrmax, T.steptab[step + 127]) > 8192;
 }
 
-// count_bit() of table t over a region from the region's pooled sums (:215-263); lo = books 13 | 16 << 16, hi = books 15 | 24 << 16
-__device__ __forceinline__ int table_cost_p(const ProbeTab &T, int t, uint32_t lo, uint32_t hi, uint32_t cnt)
+// bit count of a probe under variant (hn, hb): the payload index of a region is the number of earlier regions with a table
+__device__ __forceinline__ int row_bits(const ProbeRow &R, int hn, uint32_t hb, int &mode0, int &mode1, int &mode2)
 {
-    const int nsign = cnt & 0xFFFF, n15 = cnt >> 16;
-    if (t == 0) return 0;
-    if (t == 13) return (int)(lo & 0xFFFF) + nsign;
-    if (t == 15) return (int)(hi & 0xFFFF) + nsign;
-    return (int)(t < 24 ? (lo >> 16) : (hi >> 16)) + nsign + (int)T.linbits[t] * n15;
+    const uint32_t geo = R.geo;
+    const int k1 = (int)((geo >> 25) & 1u), k2 = k1 + (int)((geo >> 26) & 1u);
+    mode0 = 0 < hn ? 1 + (int)(hb & 1u) : 0;
+    mode1 = k1 < hn ? 1 + (int)((hb >> k1) & 1u) : 0;
+    mode2 = k2 < hn ? 1 + (int)((hb >> k2) & 1u) : 0;
+    return R.c1bits + (int)R.cost[0][mode0] + (int)R.cost[1][mode1] + (int)R.cost[2][mode2];
 }
 
 // One probe = quantize + calc_run_len + count1_bit_count + subdivide + the table choice and bit count of every region under
@@ -878,7 +882,7 @@ __device__ __forceinline__ int table_cost_p(const ProbeTab &T, int t, uint32_t l
 // slot's stale addresses that only the resolve kernel knows (big_values == 0 among non-zero values before any probe of this walk
 // had big values, A.E6).
 __device__ __forceinline__ bool probe_row(const ProbeTab &T, const uint32_t (&ax)[9], const uint32_t (&ay)[9], int32_t xrmax, int sc, int lane,
-                                          int lhave, uint32_t lla, ProbeRow &R)
+                                          int lhave, uint32_t lla, int max_bits, int vhn, uint32_t vhb, ProbeRow &R)
 {
     const uint32_t FULL = 0xFFFFFFFFu;
     const int32_t scalei = T.steptabi[sc + 127];
@@ -921,25 +925,22 @@ __device__ __forceinline__ bool probe_row(const ProbeTab &T, const uint32_t (&ax
     const int i_end = 2 * (int)lastnz;
     const int count1 = (i_end - (int)lastbig) >> 2;
     const int bv = (i_end - 4 * count1) >> 1;
-    // ---- count1_bit_count (:171-211): quads start at pair bv; the partner pair lives in the next lane (lane 31: lane 0, next row)
+    // ---- count1_bit_count (:171-211): quads start at pair bv; the partner pair lives in the next lane (lane 31: lane 0, next row).
+    //      A lane's pairs all have the parity of (lane - bv), so it either starts a quad at each of its in-range pairs or at none; the
+    //      quads' 4-bit patterns v + 2 w + 4 x + 8 y are looked up two at a time, out-of-range ones zeroed and their cost taken back
     int c1bits, c1sel;
     {
         uint32_t nbA = __shfl_sync(FULL, accA, (lane + 1) & 31), nbB = __shfl_sync(FULL, accB, (lane + 1) & 31);
         if (lane == 31) { nbA = (nbA >> 4) | (nbB << 28); nbB = 0; }
-        uint32_t c1s = 0;
-        const int c1end = bv + 2 * count1;
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-            if (32 * j + 31 >= bv && 32 * j < c1end) {   // warp-uniform: the row overlaps the count1 region
-                const int rel = 32 * j + lane - bv;
-                const uint32_t me = j < 8 ? (accA >> (4 * j)) & 3u : accB & 3u, nx = j < 8 ? (nbA >> (4 * j)) & 3u : nbB & 3u;
-                const uint32_t idx = me | (nx << 2);  // v + 2 w + 4 x + 8 y
-                const uint32_t nn = __popc(idx);
-                // code lengths: table A = {1,4,4,5,4,6,5,6,4,5,5,6,5,6,6,6} (one nibble each), table B = 4 everywhere
-                const uint32_t la4 = ((idx & 8u ? 0x66656554u : 0x65645441u) >> (4 * (idx & 7u))) & 15u;
-                if (rel >= 0 && rel < 2 * count1 && !(rel & 1)) c1s += (la4 + nn) | ((4u + nn) << 16);
-            }
-        }
+        const uint32_t idxA = (accA & 0x33333333u) | ((nbA & 0x33333333u) << 2), idxB = (accB & 3u) | ((nbB & 3u) << 2);
+        const int d = bv - lane, e = bv + 2 * count1 - lane;
+        int jlo = d <= 0 ? 0 : (d + 31) >> 5, jhi = e <= 0 ? 0 : min(9, (e + 31) >> 5);
+        if ((lane - bv) & 1) { jlo = 0; jhi = 0; }
+        const int n_in = max(0, jhi - jlo), ja = min(jlo, 8), jb = min(jhi, 8);
+        const uint32_t ma = (jb >= 8 ? 0xFFFFFFFFu : (1u << (4 * jb)) - 1u) & ~(ja >= 8 ? 0xFFFFFFFFu : (1u << (4 * ja)) - 1u);
+        const uint32_t w = idxA & ma, w8 = (jlo <= 8 && jhi == 9) ? idxB : 0u;
+        uint32_t c1s = T.c1cost[w & 0xFFu] + T.c1cost[(w >> 8) & 0xFFu] + T.c1cost[(w >> 16) & 0xFFu] + T.c1cost[w >> 24] + T.c1cost[w8];
+        c1s -= (uint32_t)(10 - n_in) * (1u | 4u << 16);   // ten patterns were looked up; the empty ones cost 1 | 4 bits each
         c1s = __reduce_add_sync(FULL, c1s);
         if ((c1s & 0xFFFF) < (c1s >> 16)) { c1sel = 0; c1bits = (int)(c1s & 0xFFFF); }
         else { c1sel = 1; c1bits = (int)(c1s >> 16); }
@@ -949,18 +950,8 @@ __device__ __forceinline__ bool probe_row(const ProbeTab &T, const uint32_t (&ax
     const bool uses_addr = bv == 0 && count1 > 0;
     if (uses_addr && !lhave) return false;
     if (bv != 0) {
-        const int bvr = 2 * bv;
-        const int anz = __popc(__ballot_sync(FULL, lane < 23 && (int)T.sfb[lane] < bvr));
-        int tc = T.subdv[anz][0];
-        while (tc > 0 && (int)T.sfb[tc + 1] > bvr) tc--;
-        r0 = tc;
-        a1 = T.sfb[tc + 1];
-        const int base = tc + 1;
-        tc = T.subdv[anz][1];
-        while (tc > 0 && (int)T.sfb[min(base + tc + 1, 23)] > bvr) tc--;
-        r1 = tc;
-        a2 = T.sfb[min(base + tc + 1, 23)];
-        a3 = bvr;
+        const uint32_t sd = T.subdiv[bv];
+        r0 = (int)(sd & 15u); r1 = (int)((sd >> 4) & 15u); a1 = (int)((sd >> 8) & 1023u); a2 = (int)((sd >> 18) & 1023u); a3 = 2 * bv;
     }
     // ---- pooled region sums over pairs [0, a1/2) [a1/2, a2/2) [a2/2, bv)   (:1147-1168, :294-318); per lane a region holds at
     //      most 9 pairs of code length <= 19, so the four books' sums travel as the four bytes of the table word
@@ -995,26 +986,28 @@ __device__ __forceinline__ bool probe_row(const ProbeTab &T, const uint32_t (&ax
     {
         const int r = lane == 0 ? 0 : (lane == 1 ? 1 : 2);
         const bool exists = r == 0 ? a1 > 0 : (r == 1 ? a2 > a1 : 2 * bv > a2);
+        // count_bit() (:215-263) of the four code books the search can reach, from the pooled sums
+        const int nsign = (int)(cn & 0xFFFFu), n15 = (int)(cn >> 16);
+        const int c13 = (int)(lo & 0xFFFFu) + nsign, c15 = (int)(hi & 0xFFFFu) + nsign, b16 = (int)(lo >> 16) + nsign, b24 = (int)(hi >> 16) + nsign;
+        auto cost_of = [&](int t) { return t == 0 ? 0 : (t == 13 ? c13 : (t == 15 ? c15 : (t < 24 ? b16 : b24) + (int)T.linbits[t] * n15)); };
         int ch0 = 0;
         if (exists && mx != 0) {
             if (mx < 15) {
-                ch0 = 13;  // the count-down search always stops at 13 (A.E4); only its 13-vs-15 arm is live
-                if (table_cost_p(T, 15, lo, hi, cn) <= table_cost_p(T, 13, lo, hi, cn)) ch0 = 15;
+                ch0 = c15 <= c13 ? 15 : 13;   // the count-down search always stops at 13 (A.E4); only its 13-vs-15 arm is live
             } else {
                 // first table of 15..23 / 24..31 whose lin_max covers mx - 15: a function of the bit length of mx - 15 (<= 13 bits)
                 const int nb = 32 - __clz((int)mx - 15);
                 const int c0 = 15 + (int)((0x88877665543210ULL >> (4 * nb)) & 15);
                 const int c1 = 24 + (int)((0x77665432100000ULL >> (4 * nb)) & 15);
-                ch0 = c0;
-                if (table_cost_p(T, c1, lo, hi, cn) < table_cost_p(T, c0, lo, hi, cn)) ch0 = c1;
+                ch0 = cost_of(c1) < cost_of(c0) ? c1 : c0;
             }
         }
         const int t0 = T.pair[ch0][0], t1 = T.pair[ch0][1];
         const uint32_t nz = __ballot_sync(FULL, ch0 > 0);
         if (lane < 3) {
-            R.cost[r][0] = (uint16_t)table_cost_p(T, ch0, lo, hi, cn);
-            R.cost[r][1] = (uint16_t)table_cost_p(T, t0, lo, hi, cn);
-            R.cost[r][2] = (uint16_t)table_cost_p(T, t1, lo, hi, cn);
+            R.cost[r][0] = (uint16_t)cost_of(ch0);
+            R.cost[r][1] = (uint16_t)cost_of(t0);
+            R.cost[r][2] = (uint16_t)cost_of(t1);
             R.tab[r][0] = (uint8_t)ch0; R.tab[r][1] = (uint8_t)t0; R.tab[r][2] = (uint8_t)t1;
         }
         if (lane == 0) {
@@ -1024,6 +1017,14 @@ __device__ __forceinline__ bool probe_row(const ProbeTab &T, const uint32_t (&ax
             R.tag = uses_addr ? lla : VAR_NONE;
         }
     }
+    __syncwarp();
+    {   // the two decisions the step search can take on this probe, for every variant at once (lane = variant)
+        int m0, m1, m2;
+        const int b = row_bits(R, vhn, vhb, m0, m1, m2);
+        const uint32_t lt = __ballot_sync(FULL, b < max_bits), le = __ballot_sync(FULL, b <= max_bits);
+        if (lane == 0) { R.lt = lt; R.le = le; }
+    }
+    __syncwarp();
     return true;
 }
 
@@ -1049,6 +1050,31 @@ k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fr
     if (tid < 24) T.sfb[tid] = tid < 23 ? DT->sfb_long[sr_idx][tid] : 576;
     if (tid < 32) { T.linbits[tid] = DT->enc_linbits[tid]; T.pair[tid][0] = DT->pair[tid][0]; T.pair[tid][1] = DT->pair[tid][1]; }
     if (tid < 23) { T.subdv[tid][0] = DT->subdv[tid][0]; T.subdv[tid][1] = DT->subdv[tid][1]; }
+    for (int i = tid; i < 256; i += 32 * PROBE_WARPS) {
+        uint32_t v = 0;
+        for (int h = 0; h < 2; h++) {
+            const uint32_t idx = (i >> (4 * h)) & 15u, nn = __popc(idx);
+            // code lengths: table A = {1,4,4,5,4,6,5,6,4,5,5,6,5,6,6,6} (one nibble each), table B = 4 everywhere
+            v += ((uint32_t)((0x6665655465645441ULL >> (4 * idx)) & 15) + nn) | ((4u + nn) << 16);
+        }
+        T.c1cost[i] = v;
+    }
+    __syncthreads();
+    for (int bvv = tid; bvv < 289; bvv += 32 * PROBE_WARPS) {   // subdivide (:998-1036) for every big_values
+        uint32_t v = 0;
+        if (bvv > 0) {
+            const int bvr = 2 * bvv;
+            int anz = 0;
+            while ((int)T.sfb[anz] < bvr) anz++;
+            int tc = T.subdv[anz][0];
+            while (tc > 0 && (int)T.sfb[tc + 1] > bvr) tc--;
+            const int r0 = tc, a1 = T.sfb[tc + 1], base = tc + 1;
+            tc = T.subdv[anz][1];
+            while (tc > 0 && (int)T.sfb[min(base + tc + 1, 23)] > bvr) tc--;
+            v = (uint32_t)r0 | (uint32_t)tc << 4 | (uint32_t)a1 << 8 | (uint32_t)T.sfb[min(base + tc + 1, 23)] << 18;
+        }
+        T.subdiv[bvv] = v;
+    }
     __syncthreads();
     int vhn;
     uint32_t vhb;
@@ -1092,7 +1118,6 @@ k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fr
         // which variants can occur: the offset in front of this granule is at most 3 bits per earlier granule of the clip
         const bool hiding = payload_len > 0;
         const bool sure3 = payload_len - 3 * (4 * (int64_t)f + q) >= 3;
-        const bool active = hiding ? lane < (sure3 ? 8 : 15) : lane == 14;
         ((uint32_t *)W.slotmap)[lane] = 0xFFFFFFFFu;
         // quantize(step) > 8192 holds exactly for the steps below s_min (the quantised maximum shrinks as the step grows)
         int s_min = -120;
@@ -1106,71 +1131,115 @@ k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fr
             s_min = -120 + n;
         }
         __syncwarp();
-        // ---- per-lane walk of bin_search_step_size (:958-996) then inner_loop (:1064-1095)
-        int next = -120, count = 120, half = 0, step = 0, s = 0, bits = 0, nslots = 0, have = 0, mode0 = 0, mode1 = 0, mode2 = 0;
+        // ---- bin_search_step_size (:958-996) then inner_loop (:1064-1095).  The variants nearly always take the same decisions, so
+        //      the walk runs ONCE, warp-uniform, on the per-probe decision masks, for as long as the active variants agree ...
+        const uint32_t act = hiding ? (sure3 ? 0xFFu : 0x7FFFu) : 0x4000u;
+        int next = -120, count = 120, step = 0, s = 0, nslots = 0, have = 0;
         uint32_t la = 0;
-        bool in_bin = true, done = !active, slow = false;
+        bool in_bin = true, slow = false, diverged = false;
         for (;;) {
+            int half = 0, nstep = step;
             bool ovf = false;
-            if (!done) {
-                if (in_bin) {
-                    half = count / 2;
-                    s = next + half;
-                    ovf = s < s_min;
-                } else {
-                    step = max(step, s_min - 1) + 1;   // while quantize(step + 1) > 8192: step += 1; then step += 1
-                    s = step;
-                }
+            if (in_bin) {
+                half = count / 2;
+                s = next + half;
+                ovf = s < s_min;
+            } else {
+                nstep = max(step, s_min - 1) + 1;   // while quantize(step + 1) > 8192: step += 1; then step += 1
+                s = nstep;
             }
-            // ---- every step some lane needs and the cache lacks is probed once, by the whole warp
+            uint32_t lt = 0, le = 0, geo = 0, addr = 0;   // an overflowing probe counts 100000 bits: neither < nor <= max_bits
+            if (!ovf) {
+                int slot = W.slotmap[s + 120];
+                if (slot == 0xFF) {
+                    if (nslots == PROBE_CACHE) { slow = true; break; }
+                    if (!probe_row(T, ax, ay, xrmax, s, lane, have, la, max_bits, vhn, vhb, W.row[nslots])) { slow = true; break; }
+                    slot = nslots++;
+                    if (lane == 0) W.slotmap[s + 120] = (uint8_t)slot;
+                    __syncwarp();
+                }
+                const ProbeRow &R = W.row[slot];
+                if (R.tag != VAR_NONE && (!have || R.tag != la)) { slow = true; break; }   // a revisited probe pooled over older addresses
+                lt = R.lt & act; le = R.le & act; geo = R.geo; addr = R.addr;
+            }
+            if (in_bin) {
+                if (lt == act) count = half;
+                else if (lt == 0) { next += half; count -= half; }
+                else { diverged = true; break; }
+                if (geo & 0x1FFu) { have = 1; la = addr; }
+                if (count <= 1) { in_bin = false; step = next; }
+            } else {
+                if (le != act && le != 0) { diverged = true; break; }
+                step = nstep;
+                if (geo & 0x1FFu) { have = 1; la = addr; }
+                if (le == act) break;
+            }
+        }
+        // ---- ... and per lane from the first probe on which they disagree (that probe is taken again, lane by lane)
+        if (diverged && !slow) {
+            bool done = !((act >> lane) & 1u);
             for (;;) {
-                const bool need = !done && !ovf && W.slotmap[s + 120] == 0xFF;
-                const uint32_t m = __ballot_sync(FULL, need);
-                if (!m) break;
-                if (nslots == PROBE_CACHE) { slow = true; break; }
-                const int ldr = __ffs(m) - 1;
-                const int sc = __shfl_sync(FULL, s, ldr);
-                // a probe that finds big_values == 0 among non-zero values pools over the addresses of the latest probe with big values
-                // (A.E6): the requesting lane's own, if its walk has met one in this granule -- else the slot's stale ones
-                const int lhave = __shfl_sync(FULL, have, ldr);
-                const uint32_t lla = __shfl_sync(FULL, la, ldr);
-                if (!probe_row(T, ax, ay, xrmax, sc, lane, lhave, lla, W.row[nslots])) { slow = true; break; }
-                if (lane == 0) W.slotmap[sc + 120] = (uint8_t)nslots;
-                nslots++;
-                __syncwarp();
-            }
-            if (slow) break;
-            bool stray = false;
-            if (!done) {
-                bits = 100000;
-                if (!ovf) {
-                    const ProbeRow &R = W.row[W.slotmap[s + 120]];
-                    const uint32_t geo = R.geo, tag = R.tag;
-                    stray = tag != VAR_NONE && (!have || tag != la);   // pooled over another walk's addresses
-                    const int k1 = (int)((geo >> 25) & 1u), k2 = k1 + (int)((geo >> 26) & 1u);
-                    mode0 = 0 < vhn ? 1 + (int)(vhb & 1u) : 0;
-                    mode1 = k1 < vhn ? 1 + (int)((vhb >> k1) & 1u) : 0;
-                    mode2 = k2 < vhn ? 1 + (int)((vhb >> k2) & 1u) : 0;
-                    bits = R.c1bits + (int)R.cost[0][mode0] + (int)R.cost[1][mode1] + (int)R.cost[2][mode2];
-                    if (geo & 0x1FFu) { have = 1; la = R.addr; }
+                int half = 0;
+                bool ovf = false;
+                if (!done) {
+                    if (in_bin) {
+                        half = count / 2;
+                        s = next + half;
+                        ovf = s < s_min;
+                    } else {
+                        step = max(step, s_min - 1) + 1;
+                        s = step;
+                    }
                 }
-                if (in_bin) {
-                    if (bits < max_bits) count = half;
-                    else { next += half; count -= half; }
-                    if (count <= 1) { in_bin = false; step = next; }
-                } else if (bits <= max_bits) done = true;
+                // every step some lane needs and the cache lacks is probed once, by the whole warp
+                for (;;) {
+                    const bool need = !done && !ovf && W.slotmap[s + 120] == 0xFF;
+                    const uint32_t m = __ballot_sync(FULL, need);
+                    if (!m) break;
+                    if (nslots == PROBE_CACHE) { slow = true; break; }
+                    const int ldr = __ffs(m) - 1;
+                    const int sc = __shfl_sync(FULL, s, ldr);
+                    // a probe that finds big_values == 0 among non-zero values pools over the addresses of the latest probe with big
+                    // values (A.E6): the requesting lane's own, if its walk has met one in this granule -- else the slot's stale ones
+                    const int lhave = __shfl_sync(FULL, have, ldr);
+                    const uint32_t lla = __shfl_sync(FULL, la, ldr);
+                    if (!probe_row(T, ax, ay, xrmax, sc, lane, lhave, lla, max_bits, vhn, vhb, W.row[nslots])) { slow = true; break; }
+                    if (lane == 0) W.slotmap[sc + 120] = (uint8_t)nslots;
+                    nslots++;
+                    __syncwarp();
+                }
+                if (slow) break;
+                bool stray = false;
+                if (!done) {
+                    int bits = 100000;
+                    if (!ovf) {
+                        const ProbeRow &R = W.row[W.slotmap[s + 120]];
+                        const uint32_t tag = R.tag;
+                        stray = tag != VAR_NONE && (!have || tag != la);   // pooled over another walk's addresses
+                        int m0, m1, m2;
+                        bits = row_bits(R, vhn, vhb, m0, m1, m2);
+                        if (R.geo & 0x1FFu) { have = 1; la = R.addr; }
+                    }
+                    if (in_bin) {
+                        if (bits < max_bits) count = half;
+                        else { next += half; count -= half; }
+                        if (count <= 1) { in_bin = false; step = next; }
+                    } else if (bits <= max_bits) done = true;
+                }
+                if (__any_sync(FULL, stray)) { slow = true; break; }
+                if (__all_sync(FULL, done)) break;
             }
-            if (__any_sync(FULL, stray)) { slow = true; break; }
-            if (__all_sync(FULL, done)) break;
         }
         if (slow) {
             if (lane == 0) sum[gs] = VAR_SLOW;
             continue;
         }
         uint32_t cntw = 0;
-        if (active) {   // the last probe of the walk is the accepted one: its row, under this variant's modes
+        if ((act >> lane) & 1u) {   // the last probe of the walk is the accepted one: its row, under this variant's modes
             const ProbeRow &R = W.row[W.slotmap[s + 120]];
             const uint32_t geo = R.geo;
+            int mode0, mode1, mode2;
+            const int bits = row_bits(R, vhn, vhb, mode0, mode1, mode2);
             const int ts0 = R.tab[0][mode0], ts1 = R.tab[1][mode1], ts2 = R.tab[2][mode2];
             const int cnt = (ts0 > 0) + (ts1 > 0) + (ts2 > 0);   // :808-809
             cntw = (uint32_t)cnt << (2 * lane);
