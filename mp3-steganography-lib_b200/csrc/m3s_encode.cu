@@ -961,13 +961,13 @@ __device__ __forceinline__ bool probe_row(const ProbeTab &T, const uint32_t (&ax
         const int pend = max(bv, max(h1, h2));
 #pragma unroll
         for (int j = 0; j < 9; j++) {
-            if (32 * j < pend) {   // warp-uniform
-                const int p = 32 * j + lane;
-                const uint2 w2 = T.hlc[(M[j] >> 16) & 0xFFu];
-                if (p < h1) { A0 += w2.x; C0 += w2.y; m0 = max(m0, X[j]); }
-                else if (p < h2) { A1 += w2.x; C1 += w2.y; m1 = max(m1, X[j]); }
-                else if (p < bv) { A2 += w2.x; C2 += w2.y; m2 = max(m2, X[j]); }
-            }
+            if (32 * j >= pend) break;   // warp-uniform: no pair of this row or a later one lies in a region
+            const int p = 32 * j + lane;
+            const uint2 w2 = T.hlc[(M[j] >> 16) & 0xFFu];
+            const bool p0 = p < h1, p1 = !p0 && p < h2, p2 = !p0 && !p1 && p < bv;
+            A0 += p0 ? w2.x : 0u; C0 += p0 ? w2.y : 0u; m0 = max(m0, p0 ? X[j] : 0u);
+            A1 += p1 ? w2.x : 0u; C1 += p1 ? w2.y : 0u; m1 = max(m1, p1 ? X[j] : 0u);
+            A2 += p2 ? w2.x : 0u; C2 += p2 ? w2.y : 0u; m2 = max(m2, p2 ? X[j] : 0u);
         }
     }
     // lanes 0..2 end up with the totals of region `lane`: every lane contributes to all three reductions
@@ -989,7 +989,10 @@ __device__ __forceinline__ bool probe_row(const ProbeTab &T, const uint32_t (&ax
         // count_bit() (:215-263) of the four code books the search can reach, from the pooled sums
         const int nsign = (int)(cn & 0xFFFFu), n15 = (int)(cn >> 16);
         const int c13 = (int)(lo & 0xFFFFu) + nsign, c15 = (int)(hi & 0xFFFFu) + nsign, b16 = (int)(lo >> 16) + nsign, b24 = (int)(hi >> 16) + nsign;
-        auto cost_of = [&](int t) { return t == 0 ? 0 : (t == 13 ? c13 : (t == 15 ? c15 : (t < 24 ? b16 : b24) + (int)T.linbits[t] * n15)); };
+        auto cost_of = [&](int t) {   // linbits is zero below table 16: one select chain, no branch
+            const int base = t == 0 ? 0 : (t == 13 ? c13 : (t == 15 ? c15 : (t < 24 ? b16 : b24)));
+            return base + (int)T.linbits[t] * n15;
+        };
         int ch0 = 0;
         if (exists && mx != 0) {
             if (mx < 15) {
