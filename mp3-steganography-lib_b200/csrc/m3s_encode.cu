@@ -1864,7 +1864,8 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
 
     // ---- chunking: all clips advance together through windows of `cf` frames so that the intermediates
     //      (MDCT spectra 9.2 KB/frame, quantised values 4.6 KB/frame) stay bounded while every clip keeps its warp busy
-    const int64_t budget_frames = h->enc_chunk_budget > 0 ? h->enc_chunk_budget : (1 << 19);
+    // host buffers: smaller chunks, because nothing runs before the first chunk's PCM has crossed PCIe (measured: 10.1 -> 10.5 M frames/s e2e)
+    const int64_t budget_frames = h->enc_chunk_budget > 0 ? h->enc_chunk_budget : (mem == M3S_MEM_HOST ? (1 << 17) : (1 << 19));
     int64_t cf = std::max<int64_t>(1, budget_frames / n_clips);
     if (cf >= max_frames) cf = max_frames;
     const bool single_chunk = cf >= max_frames;

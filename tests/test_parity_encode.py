@@ -158,6 +158,27 @@ def test_chunked_equals_single(built, oracle):
     h.close()
 
 
+def test_sequential_rate_loop_equals_parallel(built, oracle, monkeypatch):
+    """M3S_ENC_CHAIN=1 selects the sequential form of the rate loop (one CTA per clip walking its granules in order); both forms
+    must produce the oracle's bytes, taps and offsets."""
+    from mp3stego_b200 import _lib
+    clips = [synth_wav(21, 14), _clicks(5, 9 * 1152, 9), synth_wav(22, 5)]
+    bits = ["011" * 200, "10" * 300, ""]
+    outs = {}
+    for mode in ("parallel", "chain"):
+        if mode == "chain":
+            monkeypatch.setenv("M3S_ENC_CHAIN", "1")
+        h = _lib.Handle(0)
+        outs[mode] = _encode(h, clips, 128, payloads=bits)
+        h.close()
+    monkeypatch.delenv("M3S_ENC_CHAIN")
+    for c, p, a, b in zip(clips, bits, outs["parallel"], outs["chain"]):
+        ref = oracle.encode(c, 44100, 128, p)
+        for g in (a, b):
+            _check_taps(g, ref)
+            assert g["mp3"] == ref["mp3"] and g["hide_str_offset"] == ref["hide_str_offset"]
+
+
 def test_chunked_regular_batch_host_and_device(built, oracle):
     """Equal-length clips take the strided (2-D) PCIe staging path of the host pipeline; host and device buffers and the
     oracle must agree byte for byte across chunk boundaries."""
