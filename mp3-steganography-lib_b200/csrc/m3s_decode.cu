@@ -684,6 +684,7 @@ struct M3sWork {
 
 template <typename R>
 struct HybSmem {
+    uint4 specw[2][288];       // integer spectra of the current / next frame: [pair] = (x, y) int16 of the four granule-channels
     R xr[2][576];
     R prev[2][2][576];
     R tt[2][18][32];
@@ -837,9 +838,22 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
     int pp = 0;  // ping-pong index of the overlap buffer: prev[pp] is read, prev[pp ^ 1] written
     const int64_t g_begin = wk.g_first - (wk.warm ? 1 : 0);
     const int64_t g_end = wk.g_first + wk.count;
+    // the frame's integer spectra (one 16-byte word per pair: the four granule-channels) are fetched one frame ahead with cp.async
+    // into shared memory, so that the requantize phase does not wait for DRAM in front of its barrier (and no registers are held)
+    const uint4 *spec4 = (const uint4 *)spec;
+    auto fetch_spec = [&](int64_t gf, int buf) {
+        for (int p = tid; p < 288; p += HYB_THREADS) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.specw[buf][p]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(spec4 + gf * 288 + p) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch_spec(g_begin, 0);
     for (int64_t g = g_begin; g < g_end; g++) {
         const bool emit = g >= wk.g_first;
         const uint32_t meta = fr_meta[g];
+        const int sbuf = (int)((g - g_begin) & 1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // my part of this frame's spectra has landed; the barrier below publishes everyone's
         const int sr = (meta >> M3S_META_SR_SHIFT) & 3;
         // ---- per-frame records
         if (tid < 4) sm.rec[tid] = units[4 * g + tid];
@@ -853,6 +867,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
         }
         __syncthreads();
         if (tid == 0) sm.sr_loaded = sr;
+        if (g + 1 < g_end) fetch_spec(g + 1, sbuf ^ 1);   // the other buffer was last read two barriers or more ago (previous frame's requantize)
         const bool ms = (meta & M3S_META_MS) != 0;
         {   // scale table: thread = (slot, band index)
             const int slot = tid >> 6, idx = tid & 63;
@@ -872,7 +887,7 @@ k_hybrid(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units
         for (int gr = 0; gr < 2; gr++) {
             // ------------------------------------------------ requantize + MS + reorder (fused)
             for (int p = tid; p < 288; p += HYB_THREADS) {
-                const uint4 w4 = ((const uint4 *)spec)[g * 288 + p];
+                const uint4 w4 = sm.specw[sbuf][p];
                 R val[2][2];
 #pragma unroll
                 for (int ch = 0; ch < 2; ch++) {
