@@ -400,7 +400,7 @@ def run_product_arm(args):
                     f"mean call ms: scan {sc:6.1f} reveal {rv:6.1f} run {rn:6.1f}")
         return
 
-    # encode+hide: ONE call over all clips -- the rate loop runs one warp per clip, so the whole corpus goes in together
+    # encode+hide: ONE call over all clips (the per-clip offset scan of the rate loop wants every clip's chain in flight together)
     # (the library walks it in frame windows to bound its intermediates)
     def enc_device():
         r = h.encode(pcm_all, ns_all, 44100, 128, payload_packed=(pay_all, pay_off_all), mp3_out=enc_out_dev)
@@ -408,7 +408,7 @@ def run_product_arm(args):
         check["enc_bytes"] = int(r["out_len"].sum())
         return total_frames
 
-    # host leg of encode+hide: the same 1,000 clips (the rate loop needs all of its chains), each cut to `enc_e2e_frames` frames
+    # host leg of encode+hide: the same 1,000 clips (same call shape as the device-resident leg), each cut to `enc_e2e_frames` frames
     # when the box's RAM cannot pin the whole PCM corpus of every rank (8 x 31.7 GB on a 251 GB host)
     enc_e2e = dict(frames=args.frames)
 

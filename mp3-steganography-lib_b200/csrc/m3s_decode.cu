@@ -431,15 +431,15 @@ struct BitReader {
     int lim;            // bits readable relative to w (reads at or beyond read as zero)
     int pos;            // current bit position relative to w
     int idx;
-    uint32_t hi, lo;
+    uint32_t hi, lo, nx;   // words idx, idx + 1 and idx + 2: the third one is fetched a whole word ahead of its first use, so its
+                           // latency hides under the pairs decoded in between
     __device__ __forceinline__ uint32_t load(int wi) const
     {
-        int b = wi * 32;
+        if (wi < (lim >> 5)) return __byte_perm(__ldg(w + wi), 0, 0x0123);   // whole word inside the limit: the common case
+        const int b = wi * 32;
         if (b >= lim) return 0u;
-        uint32_t v = __byte_perm(__ldg(w + wi), 0, 0x0123);
-        int rem = lim - b;
-        if (rem < 32) v &= ~(0xFFFFFFFFu >> rem);
-        return v;
+        const uint32_t v = __byte_perm(__ldg(w + wi), 0, 0x0123);
+        return v & ~(0xFFFFFFFFu >> (lim - b));
     }
     __device__ __forceinline__ void init(const uint8_t *S, uint64_t bit_start, int limit_bits)
     {
@@ -450,6 +450,7 @@ struct BitReader {
         idx = 0;
         hi = load(0);
         lo = load(1);
+        nx = load(2);
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos & 31); }
     __device__ __forceinline__ void skip(int n)  // n <= 32
@@ -458,7 +459,8 @@ struct BitReader {
         int ni = pos >> 5;
         if (ni != idx) {
             hi = lo;
-            lo = load(ni + 1);
+            lo = nx;
+            nx = load(ni + 2);
             idx = ni;
         }
     }

@@ -2,10 +2,14 @@
 //
 //   E1 k_enc_analysis  polyphase analysis + MDCT + alias butterflies, exact 32-bit fixed point; also the per-granule
 //                      spectral statistics the rate loop and scfsi need (xrmax, en_tot, en[21]).           (:322-370, :652-758, :817-861)
-//   E2 k_enc_rate      per-granule quantisation / rate loop with table selection and the stego table swap.
-//                      One WARP per clip walks the clip's granules in the reference's order (frame, ch, gr), because
-//                      hide_str_offset and the stale address1/2/3 (SURVEY A.E5/A.E6) chain every granule to the one
-//                      before it; the 576 coefficients of a granule are spread over the 32 lanes.                  (:760-1264)
+//   E2 the per-granule quantisation / rate loop with table selection and the stego table swap (:760-1264), in three kernels:
+//      k_enc_probe    one warp per granule-channel and NO chain between granules: the reference's step search is walked for every
+//                     payload variant the granule can meet (the <= 3 payload bits at its hide_str_offset: 15 cases), the
+//                     payload-independent part of a probe computed once per distinct step;
+//      k_enc_resolve  one warp per clip turns offsets into variants in the reference's order (frame, ch, gr) on registers,
+//                     and redoes the few granules that read the slot's stale address1/2/3 (SURVEY A.E5/A.E6);
+//      k_enc_emit     one warp per granule-channel quantises at the chosen step.
+//      (k_enc_rate_chain is the sequential form, one CTA per clip, kept as a cross-check: M3S_ENC_CHAIN=1.)
 //   E3 k_enc_pack      header, side info and Huffman bit packing, one warp per frame (frames are self-contained:
 //                      main_data_begin = 0 and every frame is filled to its nominal size by stuffing).            (:1266-1552)
 //
