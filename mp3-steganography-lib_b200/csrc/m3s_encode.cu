@@ -92,7 +92,7 @@ __constant__ int32_t c_enc_cos[18][36];   // MP3Encoder.__cos_l (:557-566), wind
 
 struct AnaSmem {
     int32_t x[2][1056];         // [buffer]: 480 samples of history + 576 new of this channel, as int16 << 16 (double buffered: no shift barrier)
-    __align__(16) int32_t y[18][64];   // [slot][i] windowed vectors
+    __align__(16) int32_t y[18][72];   // [slot][i + 4 (i >= 32)] windowed vectors; the gap puts the two halves a matrixing warp reads together on different banks
     int32_t sb[2][18][32];      // [ping-pong][slot][band] subband samples
     int32_t mf[576];            // [band * 18 + k] MDCT lines
     uint32_t bins[24];          // 0..20 band energies, 21 total, 22 xrmax
@@ -198,7 +198,7 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
 #pragma unroll
                 for (int k = 0; k < 8; k += 2)
                     acc += (uint32_t)__mulhi(xv[q - k + 7], wcoef[k]) + (uint32_t)__mulhi(xv[q - k + 6], wcoef[k + 1]);
-                S.y[wpar + 2 * q][wi] = (int32_t)acc;
+                S.y[wpar + 2 * q][wi + ((wi >> 5) << 2)] = (int32_t)acc;
             }
         }
         __syncthreads();
@@ -206,7 +206,7 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
 #pragma unroll 1
         for (int q = 0; q < 9; q++) {
             const int s = 9 * mhalf + q;
-            const int4 *y4 = (const int4 *)&S.y[s][32 * mh];
+            const int4 *y4 = (const int4 *)&S.y[s][36 * mh];
             uint32_t acc = 0;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
