@@ -53,7 +53,10 @@ enum {
     M3S_FILE_OK = 0,
     M3S_FILE_NO_SYNC = 1,        /* first audio bytes are not 0xFF 0xEx: MP3Parser.__valid False (MP3_Parser.py:36-44) */
     M3S_FILE_UNSUPPORTED = 2,    /* a frame header outside MPEG-1 Layer III / reserved sample rate or bitrate index 15 */
-    M3S_FILE_TRAILING_JUNK = 4   /* parsing stopped at a bad sync word; the last frame's PCM is repeated once (MP3_Parser.py:68-79) */
+    M3S_FILE_TRAILING_JUNK = 4,  /* parsing stopped at a bad sync word; the last frame's PCM is repeated once (MP3_Parser.py:68-79) */
+    M3S_FILE_STATE_CARRY = 8     /* some granule takes scalefactors from EARLIER frames through the reference's persistent arrays: a mixed
+                                    block (scale_fac_s[..][0..2], Frame.py:387-403 vs :198) or scfsi over a short-block granule 0
+                                    (Frame.py:419-437).  A frame-range shard of such a file needs the whole prefix as its halo. */
 };
 
 /* flags for m3s_decode_run */
@@ -105,6 +108,11 @@ M3S_API int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, const
  *   reveal_bits  ['0'/'1' chars] file i's string starts at 12 * (sum of n_frames of files < i); May be NULL.
  *   reveal_len   [n_files] host: number of chars of each file's string (MP3Parser.output_bits). */
 M3S_API int m3s_decode_reveal(m3s_handle_t h, uint8_t *table_ids, uint8_t *reveal_bits, int mem, int64_t *reveal_len);
+
+/* Byte position of every frame of the last scan, relative to the start of its file: [total_frames] host array, file i's frames
+ * at [sum of n_frames of files < i, ...).  What Frame.set_frame_size accumulates into MP3Parser's offset (MP3_Parser.py:75,
+ * Frame.py:288-316); a host that splits one long file into frame ranges for several GPUs cuts the byte stream here. */
+M3S_API int m3s_decode_frame_pos(m3s_handle_t h, int64_t *frame_pos);
 
 /* Huffman decode -> requantize -> stereo -> reorder/alias -> IMDCT/overlap -> polyphase synthesis of the
  * last scanned batch: Frame.init_frame_params (Frame.py:244-286) for every frame, then

@@ -205,6 +205,7 @@ k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec
     const bool junk = (fr.flags & M3S_FILE_TRAILING_JUNK) != 0;
     uint32_t carry_in = 0;   // 5 bits per (gr, ch) slot
     uint32_t P_in = 0, reveal_in = 0;
+    bool state_carry = false;   // a granule inherits scalefactors from earlier frames (M3S_FILE_STATE_CARRY)
     for (int n0 = 0; n0 < fr.n_frames; n0 += 32) {
         const int n = n0 + lane;
         const bool valid = n < fr.n_frames;
@@ -239,12 +240,17 @@ k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec
             const int si = 4 + (h.crc_present ? 2 : 0);
             int rb = h.mono ? 18 : 20;
             wsmask = 0xFu;
+            const uint32_t scfsi_all = h.mono ? sbits(wb + si, 14, 4) << 4 : sbits(wb + si, 12, 8);   // ch0 in the high nibble
             for (int gr = 0; gr < 2; gr++)
                 for (int ch = 0; ch < (h.mono ? 1 : 2); ch++) {
                     const int slot = 2 * gr + ch;
                     uint32_t ws, t0, t1, t2 = 0;
                     const uint8_t *sp = wb + si;
                     ws = sbits(sp, rb + 33, 1);
+                    if (ws && sbits(sp, rb + 34, 2) == 2) {   // short block: mixed, or granule 0 under a non-zero scfsi of its channel
+                        if (sbits(sp, rb + 36, 1)) state_carry = true;
+                        if (gr == 0 && ((scfsi_all >> (ch ? 0 : 4)) & 15u)) state_carry = true;
+                    }
                     if (ws) { t0 = sbits(sp, rb + 37, 5); t1 = sbits(sp, rb + 42, 5); }
                     else { t0 = sbits(sp, rb + 34, 5); t1 = sbits(sp, rb + 39, 5); t2 = sbits(sp, rb + 44, 5); }
                     nz01 += (t0 != 0) + (t1 != 0);
@@ -287,7 +293,11 @@ k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec
         reveal_in += __shfl_sync(0xFFFFFFFFu, pR, 31);
         __syncwarp();
     }
-    if (lane == 0) fouts[f].reveal_len = (int32_t)reveal_in;
+    state_carry = __any_sync(0xFFFFFFFFu, state_carry);
+    if (lane == 0) {
+        fouts[f].reveal_len = (int32_t)reveal_in;
+        if (state_carry) fouts[f].status |= M3S_FILE_STATE_CARRY;
+    }
 }
 
 // ================================================================================================
@@ -1250,6 +1260,20 @@ extern "C" int m3s_decode_reveal(m3s_handle_t h, uint8_t *table_ids, uint8_t *re
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     if (table_ids) memcpy(table_ids, h->rev_mapped, nb);
     if (reveal_bits) memcpy(reveal_bits, h->rev_mapped + nb, nb);
+    return M3S_OK;
+}
+
+extern "C" int m3s_decode_frame_pos(m3s_handle_t h, int64_t *frame_pos)
+{
+    if (!h) return M3S_ERR_ARG;
+    if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_frame_pos: call m3s_decode_scan first");
+    if (!frame_pos) return m3s_fail(h, M3S_ERR_ARG, "decode_frame_pos: null output");
+    if (h->total_frames == 0) return M3S_OK;
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    M3S_CUDA(h, cudaMemcpyAsync(frame_pos, h->b_fr_pos.p, sizeof(int64_t) * (size_t)h->total_frames, cudaMemcpyDeviceToHost, h->stream));
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < h->n_files; i++)   // absolute batch positions -> file-relative
+        for (int64_t g = h->files[i].frame_base; g < h->files[i].frame_base + h->files[i].n_frames; g++) frame_pos[g] -= h->files[i].begin;
     return M3S_OK;
 }
 

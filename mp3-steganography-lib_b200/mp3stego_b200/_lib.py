@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmp3stego_b200.so")
 
 M3S_MEM_HOST, M3S_MEM_DEVICE = 0, 1
-M3S_FILE_NO_SYNC, M3S_FILE_UNSUPPORTED, M3S_FILE_TRAILING_JUNK = 1, 2, 4
+M3S_FILE_NO_SYNC, M3S_FILE_UNSUPPORTED, M3S_FILE_TRAILING_JUNK, M3S_FILE_STATE_CARRY = 1, 2, 4, 8
 M3S_DEC_PCM_FLOAT = 1
 M3S_DEC_EXACT = 2
 
@@ -30,6 +30,7 @@ SYMBOLS = [
     ("m3s_version", ctypes.c_int, []),
     ("m3s_decode_scan", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, _c_i64p, ctypes.c_int32,
                                        _c_i64p, _c_i64p, _c_i32p, _c_i32p, _c_i32p, _c_i32p]),
+    ("m3s_decode_frame_pos", ctypes.c_int, [ctypes.c_void_p, _c_i64p]),
     ("m3s_decode_reveal", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p]),
     ("m3s_decode_run", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, ctypes.c_void_p,
                                       ctypes.c_uint32]),
@@ -164,6 +165,13 @@ class Handle:
         self._check(rc, "m3s_decode_scan")
         self._scan = out
         return out
+
+    def decode_frame_pos(self):
+        """File-relative byte position of every frame of the last scan (all files' frames back to back)."""
+        total = int(self._scan["n_frames"].sum())
+        pos = np.zeros(max(total, 1), np.int64)
+        self._check(self._L.m3s_decode_frame_pos(self._h, pos.ctypes.data_as(_c_i64p)), "m3s_decode_frame_pos")
+        return pos[:total]
 
     def decode_reveal(self):
         """Table ids [frames, 12] and the per-file reveal bit strings of the last scan."""

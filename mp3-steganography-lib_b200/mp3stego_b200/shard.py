@@ -32,11 +32,67 @@ def frame_ranges(n_frames: int, parts: int) -> List[Dict[str, int]]:
     warm-up frame (two granules: overlap-add tail + the 15 earlier V vectors of the 1024-sample synthesis fifo,
     Frame.py:81-92,150-153) whose PCM is discarded, which reproduces the full decode exactly (measured
     with the reference itself).  The frame walk and side-info scan still run over the whole file (no resync in the
-    reference), which is what m3s_decode_scan does."""
+    reference), which is what m3s_decode_scan does.  decode_frame_range() below is the driver that uses it."""
     parts = max(1, min(parts, max(n_frames, 1)))
     edges = [n_frames * k // parts for k in range(parts + 1)]
     return [dict(first=edges[k], count=edges[k + 1] - edges[k], warm=1 if edges[k] > 0 else 0)
             for k in range(parts) if edges[k + 1] > edges[k]]
+
+
+# frames a range shard decodes in front of its first frame: one warm-up frame (overlap + V history) whose own main data may
+# reach 511 bytes back through the bit reservoir, i.e. through at most 9 frames of the smallest legal payload (60 bytes)
+HALO_FRAMES = 10
+
+
+def plan_frame_shard(n_frames: int, status: int, rank: int, world: int, halo: int = HALO_FRAMES) -> Dict[str, int]:
+    """The frame range rank `rank` of `world` decodes of ONE long file, and how many frames in front of it it has to decode as
+    well (`lead`, PCM discarded): `halo` frames cover the warm-up frame and its bit reservoir; a file whose granules inherit
+    scalefactors from earlier frames (M3S_FILE_STATE_CARRY) needs its whole prefix.  Every rank computes every rank's plan from
+    the same scan result: no communication."""
+    from . import _lib
+    rs = frame_ranges(n_frames, world)
+    if rank >= len(rs):
+        return dict(first=n_frames, count=0, lead=0)
+    r = rs[rank]
+    lead = r["first"] if status & _lib.M3S_FILE_STATE_CARRY else min(r["first"], max(halo, 1))
+    return dict(first=r["first"], count=r["count"], lead=lead)
+
+
+_H0 = frozenset((3, 6, 8, 11, 12, 15, 17, 19, 21, 23, 24, 26, 28, 30))   # tables that reveal a '0' (decoder/util.py:3)
+
+
+def decode_frame_range(handle, blob: bytes, rank: int, world: int, audio_start: int = 0, exact: bool = False,
+                       halo: int = HALO_FRAMES):
+    """Range-sharded decode+reveal of one long file: rank `rank` of `world` returns the PCM rows and the reveal
+    bits of ITS frame range only; the ranges of all ranks, concatenated in rank order, equal the whole-file decode bit for bit.
+
+    The frame walk and the side-info scan (D0 + D4: no Huffman decode, ~36 bytes read per frame) run over the WHOLE file on
+    every rank, because the reference never resynchronises: frame positions, the reveal bits and the carried table ids of
+    window-switched granules (A.D3) all come from that scan.  The expensive part (D1-D3) runs on the bytes of the range plus
+    its halo, cut out at frame boundaries and decoded as a file of its own; the halo's PCM is dropped."""
+    data = np.frombuffer(blob, np.uint8)
+    sc = handle.decode_scan(data, [0, len(blob)], [audio_start])
+    n_frames, status, ch = int(sc["n_frames"][0]), int(sc["status"][0]), max(int(sc["channels"][0]), 1)
+    meta = dict(n_frames=n_frames, sample_rate=int(sc["sample_rate"][0]), channels=ch, bitrate=int(sc["bitrate"][0]), status=status)
+    plan = plan_frame_shard(n_frames, status, rank, world, halo)
+    first, count, lead = plan["first"], plan["count"], plan["lead"]
+    if count == 0:
+        return dict(meta, first=first, count=0, pcm=np.zeros((0, ch), np.int16), bits="")
+    ids, _ = handle.decode_reveal()
+    own = ids[first:first + count].reshape(-1)
+    bits = "".join("0" if t in _H0 else "1" for t in own.tolist() if t)
+    pos = handle.decode_frame_pos()
+    last = first + count == n_frames
+    lo = int(pos[first - lead])
+    hi = len(blob) if last else int(pos[first + count])     # the last range keeps the file's tail (trailing junk repeats its last frame)
+    sub = data[lo:hi]
+    s2 = handle.decode_scan(sub, [0, len(sub)])
+    if int(s2["n_frames"][0]) != lead + count:
+        raise RuntimeError(f"range shard parsed {int(s2['n_frames'][0])} frames, expected {lead + count}")
+    pcm, _ = handle.decode_run(exact=exact)
+    rows = int(s2["pcm_rows"][0])
+    pcm = pcm[: rows * ch].reshape(rows, ch)[lead * 1152:]
+    return dict(meta, first=first, count=count, pcm=pcm, bits=bits)
 
 
 def rank_world():

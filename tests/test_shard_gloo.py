@@ -39,6 +39,24 @@ def test_frame_ranges_cover_and_warm_up():
             pos += x["count"]
 
 
+def test_frame_shard_plans_agree_and_cover():
+    """Every rank derives every rank's frame range of a long file from the same scan result: exact cover, the halo rule, and the
+    whole-prefix halo of files whose granules inherit state from earlier frames."""
+    sys.path.insert(0, PKG)
+    from mp3stego_b200 import shard
+    CARRY = 8   # M3S_FILE_STATE_CARRY (include/mp3stego_b200.h)
+    for n, world in ((6890, 8), (25, 4), (3, 8), (0, 2), (1148, 3)):
+        for status in (0, 4, CARRY):
+            plans = [shard.plan_frame_shard(n, status, r, world) for r in range(world)]
+            pos = 0
+            for p in plans:
+                if p["count"]:
+                    assert p["first"] == pos
+                    assert p["lead"] == (p["first"] if status & CARRY else min(p["first"], shard.HALO_FRAMES))
+                    pos += p["count"]
+            assert pos == n
+
+
 def _worker(rank, world, port, blobs, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
