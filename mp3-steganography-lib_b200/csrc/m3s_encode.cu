@@ -1125,6 +1125,7 @@ k_enc_probe(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fr
         // which variants can occur: the offset in front of this granule is at most 3 bits per earlier granule of the clip
         const bool hiding = payload_len > 0;
         const bool sure3 = payload_len - 3 * (4 * (int64_t)f + q) >= 3;
+        __syncwarp();   // the previous granule's lanes have finished reading this warp's rows and slot map
         ((uint32_t *)W.slotmap)[lane] = 0xFFFFFFFFu;
         // quantize(step) > 8192 holds exactly for the steps below s_min (the quantised maximum shrinks as the step grows)
         int s_min = -120;
