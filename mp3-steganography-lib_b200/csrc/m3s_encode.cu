@@ -771,7 +771,6 @@ k_enc_rate_chain(const M3sEncClip *__restrict__ clips, M3sEncState *__restrict__
 #define VAR_SILENT 0x80000000u
 #define VAR_SLOW 0x40000000u
 #define VAR_NONE 0xFFFFFFFFu
-#define STEP_NONE 0x7FFFFFFF
 
 // What a probe (one step of one granule) leaves for the variant walks: everything but the payload bits.  The table the
 // reference would choose for a region BEFORE the swap does not depend on the payload, nor does the payload index of a region
@@ -2021,7 +2020,11 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         if (chunk_total == 0) break;
         const M3sEncClip *d_clips = (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips;
         M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_ana[pb], 0));
-        const bool serial = getenv("M3S_ENC_SERIAL") != nullptr;   // diagnostic: analysis of chunk k+1 only after chunk k is packed (no overlap)
+        // The sequential rate loop (latency chains) leaves issue slots for the next chunk's analysis, so that form overlaps the two
+        // (880 -> 741 ms/step); the parallel form and the analysis are both issue-bound and run back to back (measured: overlapping
+        // them gains nothing and stretches the analysis kernel's own time).  M3S_ENC_OVERLAP=0/1 and M3S_ENC_SERIAL override.
+        const bool overlap = getenv("M3S_ENC_SERIAL") ? false : (getenv("M3S_ENC_OVERLAP") ? atoi(getenv("M3S_ENC_OVERLAP")) != 0 : chain);
+        const bool serial = !overlap;
         const int64_t n_gran = 4 * chunk_total;
         const int64_t probe_tiles = (n_gran + probe_warps * PROBE_G - 1) / (probe_warps * PROBE_G);
         const int64_t probe_ctas = getenv("M3S_PROBE_CTAS") ? atoll(getenv("M3S_PROBE_CTAS")) : 0;
@@ -2039,7 +2042,7 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
                 (uint32_t *)b_sum[pb]->p, (uint8_t *)b_scfsi[pb]->p);
         M3S_LAUNCH_CHECK(h);
         M3S_CUDA(h, cudaEventRecord(h->ev_rate[pb], h->stream));
-        // queued behind the rate loop's CTAs on purpose: the next chunk's analysis takes what they leave free
+        // (overlapped order) queued behind the rate loop's CTAs on purpose: the next chunk's analysis takes what they leave free
         if (!serial && k + 1 < n_chunks && (rc = launch_analysis(k + 1))) return rc;
         if (host && k + 2 < n_chunks) M3S_CUDA(h, stage_chunk(k + 2));
         if (!chain) {
@@ -2058,7 +2061,7 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
                 (uint32_t *)((char *)h->e_lastix.p + (size_t)((k + 1) & 1) * lastix_bytes));
             M3S_LAUNCH_CHECK(h);
         }
-        // packing stays on the rate loop's stream: next to the analysis it would only slow the critical chain further
+        // packing stays on the rate loop's stream
         M3S_KBEGIN(h, M3S_K_ENC_PACK);
         k_enc_pack<<<(unsigned)((chunk_total + PACK_WARPS - 1) / PACK_WARPS), 32 * PACK_WARPS, sizeof(PackSmem), h->stream>>>(
             d_clips, (const int32_t *)h->e_misc.p + slot_off[k], h->d_tab, (const uint32_t *)h->e_pad.p, sri, bri, whole, 0,

@@ -1,6 +1,6 @@
 """A/B timing of the encoder pipeline variants on one GPU (diagnostic; no JSON contract).
 usage: python tools/enc_ab.py [clips] [frames]   -- device-resident encode+hide @128k of the tone+noise corpus under each
-environment setting of m3s_encode (M3S_ENC_CHAIN, M3S_ENC_SERIAL, M3S_PROBE_CTAS), per-kernel device milliseconds."""
+environment setting of m3s_encode (M3S_ENC_CHAIN, M3S_ENC_SERIAL / M3S_ENC_OVERLAP, M3S_PROBE_CTAS, M3S_PROBE_CFG), per-kernel device milliseconds."""
 import os
 import sys
 import time
@@ -30,7 +30,7 @@ def main():
     cap = int(_lib.load().m3s_encode_bound(n_samp, 44100, 128)) * clips + 64
     out = torch.empty(cap, dtype=torch.uint8, device=dev)
     ns = [n_samp] * clips
-    configs = [("default", {}), ("probe_ctas=296", {"M3S_PROBE_CTAS": "296"}), ("probe_ctas=444", {"M3S_PROBE_CTAS": "444"}),
+    configs = [("default", {}), ("overlap", {"M3S_ENC_OVERLAP": "1"}), ("probe_ctas=296", {"M3S_PROBE_CTAS": "296"}), ("probe_ctas=444", {"M3S_PROBE_CTAS": "444"}),
                ("serial", {"M3S_ENC_SERIAL": "1"}), ("chain (old rate loop)", {"M3S_ENC_CHAIN": "1"}),
                ("chain serial", {"M3S_ENC_CHAIN": "1", "M3S_ENC_SERIAL": "1"})]
     configs += [(f"cfg{k} serial", {"M3S_PROBE_CFG": str(k), "M3S_ENC_SERIAL": "1"}) for k in range(6)]
@@ -39,7 +39,7 @@ def main():
         configs = [c for c in configs if any(c[0].startswith(a) for a in sys.argv[3:])] + adhoc
     ref = None
     for name, env in configs:
-        for k in ("M3S_PROBE_CTAS", "M3S_ENC_SERIAL", "M3S_ENC_CHAIN", "M3S_PROBE_CFG"):
+        for k in ("M3S_PROBE_CTAS", "M3S_ENC_SERIAL", "M3S_ENC_OVERLAP", "M3S_ENC_CHAIN", "M3S_PROBE_CFG"):
             os.environ.pop(k, None)
         os.environ.update(env)
         out.zero_()
