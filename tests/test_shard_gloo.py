@@ -106,3 +106,76 @@ def test_sharded_decode_reveal_world2_gloo():
     for _, _, merged, t in got:
         assert merged == single               # every rank sees the whole job's results, identical to one process
         assert t == pytest.approx(2.0)        # max over ranks of (1.0, 2.0)
+
+
+class _OracleHandle:
+    """Stands in for _lib.Handle in the CPU suite: the same four calls decode_frame_range makes, answered by the oracle
+    (whole-file sequential decode), so the host logic of range sharding is exercised without a GPU."""
+
+    def __init__(self, O):
+        self.O, self.r = O, None
+
+    def decode_scan(self, data, file_off, audio_start=None):
+        blob = bytes(np.asarray(data, np.uint8)[int(file_off[0]):int(file_off[1])])
+        self.r = self.O.decode(blob, 0 if audio_start is None else int(audio_start[0]), taps=False)
+        r = self.r
+        return dict(n_frames=np.array([r["n_frames"]], np.int64), pcm_rows=np.array([r["pcm16"].shape[0]], np.int64),
+                    sample_rate=np.array([r["sampling_rate"]], np.int32), channels=np.array([r["channels"]], np.int32),
+                    bitrate=np.array([r["bit_rate"]], np.int32), status=np.array([0], np.int32))
+
+    def decode_reveal(self):
+        return self.r["tables"], [self.r["bits"]]
+
+    def decode_frame_pos(self):
+        return self.r["frame_off"]
+
+    def decode_run(self, exact=False):
+        return self.r["pcm16"].reshape(-1), None
+
+
+def _range_worker(rank, world, port, blob, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, PKG)
+    import torch.distributed as dist
+    from mp3stego_b200 import shard
+    from oracle import oracle as O
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        part = shard.decode_frame_range(_OracleHandle(O), blob, rank, world)
+        merged = shard.gather_results({rank: (part["first"], part["count"], part["bits"], part["pcm"].tobytes())})
+        q.put((rank, merged))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_range_sharded_decode_world2_gloo():
+    """One long file split by frame range over two ranks (each decodes its range + halo as a file of its own): the ranges,
+    gathered, are the whole-file decode sample for sample and bit for bit."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import synth_wav
+    from oracle import oracle as O
+    O.build()
+    wav = synth_wav(31, 48)
+    bits = O.str_to_bits("11#frame range")
+    blob = O.encode(wav, 44100, 128, bits, taps=False)["mp3"]
+    whole = O.decode(blob, 0, taps=False)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_range_worker, args=(r, 2, port, blob, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, merged in got:
+        assert sorted(merged) == [0, 1]
+        assert merged[0][0] == 0 and merged[1][0] == merged[0][1] and merged[0][1] + merged[1][1] == whole["n_frames"]
+        assert merged[0][2] + merged[1][2] == whole["bits"]
+        assert merged[0][3] + merged[1][3] == whole["pcm16"].tobytes()
+    assert O.reveal_parse(whole["bits"]) == "frame range"
