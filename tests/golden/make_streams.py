@@ -291,7 +291,58 @@ STREAMS = {
 }
 
 
+def fuzz_config(seed):
+    """A random combination of everything the writer can vary (BASELINE configs[3] as a corpus rather than eight hand-picked
+    streams): sample rate, CBR / VBR, padding, mono / stereo / joint stereo with either mode-extension bit, CRC, bit reservoir,
+    window switching with short / mixed / start / stop blocks, scalefactors + scfsi, loud spectra."""
+    rng = np.random.default_rng(1000 + seed)
+    sr = int(rng.choice([44100, 48000, 32000]))
+    mode = 3 if seed % 5 == 2 else int(rng.choice([0, 0, 1, 1]))   # every fifth stream is mono (17-byte side info)
+    kw = dict(seed=seed, n_frames=int(rng.integers(16, 29)), sr=sr, mode=mode, mode_ext=int(rng.integers(0, 4)) if mode == 1 else 0,
+              crc=bool(rng.integers(0, 2)), reservoir=bool(rng.integers(0, 2)))
+    rates = [64, 96, 128, 160, 192, 256, 320] if mode != 3 else [48, 64, 96, 128, 160]
+    if rng.random() < 0.3:
+        kw["vbr"] = [int(v) for v in rng.choice(rates, size=3, replace=False)]
+    else:
+        kw["bitrate"] = int(rng.choice(rates))
+    lo = min(kw.get("vbr", [kw.get("bitrate", 128)]))
+    opts = dict(switching=bool(rng.random() < 0.7), padding=bool(rng.integers(0, 2)), scfsi=bool(rng.random() < 0.8),
+                stuff_ones=bool(rng.integers(0, 2)), max_bv=int(min(200, 40 + lo * (2 if mode == 3 else 1) // 2)),
+                max_quads=int(rng.integers(10, 61)))
+    if rng.random() < 0.2:
+        opts.update(amp=15, gain_lo=170, gain_hi=186)
+    kw["opts"] = opts
+    return kw
+
+
+N_FUZZ = 16
+
+
+def main_fuzz():
+    """tests/golden/fuzz_NN.mp3 + ref_fuzz.json: digests of what the UNMODIFIED reference decoder makes of each stream."""
+    import hashlib
+    import json
+    digests = {}
+    for k in range(N_FUZZ):
+        kw = fuzz_config(k)
+        data = make_stream(**kw)
+        d = MG.ref_decode_taps(data)
+        name = "fuzz_%02d" % k
+        open(os.path.join(HERE, name + ".mp3"), "wb").write(data)
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+        digests[name] = dict(n_frames=int(d["n_frames"]), bitrate=int(d["bitrate"]), sampling_rate=int(d["sampling_rate"]),
+                             channels=int(d["pcm16"].shape[1]) if d["pcm16"].ndim == 2 else 1,
+                             pcm16_sha256=sha(d["pcm16"].astype(np.int16)), spectra_sha256=sha(d["spectra"].astype(np.int16)),
+                             tables_sha256=sha(np.asarray(d["tables"], np.uint8)), bits=d["bits"],
+                             config={k2: (v if not isinstance(v, dict) else v) for k2, v in kw.items()})
+        print("%-8s bytes %6d frames %3d sr %5d mode %d |pcm|max %.3f bits %d" % (
+            name, len(data), d["n_frames"], kw["sr"], kw["mode"], np.abs(d["pcm"]).max() if d["pcm"].size else 0, len(d["bits"])))
+    json.dump(digests, open(os.path.join(HERE, "ref_fuzz.json"), "w"), indent=1, sort_keys=True)
+
+
 def main():
+    if "--fuzz" in sys.argv:
+        return main_fuzz()
     for name, kw in STREAMS.items():
         data = make_stream(**kw)
         d = MG.ref_decode_taps(data)

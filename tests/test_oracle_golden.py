@@ -114,3 +114,24 @@ def test_decode_writer_streams(oracle, case):
     assert np.array_equal(r["tables"][:, :k], z["tables"]) and not r["tables"][:, k:].any()
     assert r["bits"] == str(z["bits"])
     assert np.array_equal(r["pcm16"].reshape(z["pcm16"].shape), z["pcm16"])
+
+
+def _fuzz_cases():
+    import os
+    return sorted(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fuzz.json"))))
+
+
+@pytest.mark.parametrize("name", _fuzz_cases())
+def test_decode_fuzz_corpus(oracle, name):
+    """BASELINE configs[3] as a corpus: 16 writer streams over random combinations of sample rate, CBR / VBR, padding, mono /
+    stereo / joint stereo, CRC, bit reservoir, short / mixed / start / stop blocks, scalefactors + scfsi and loud spectra
+    (tests/golden/make_streams.py --fuzz), decoded by the unmodified reference: digests of its int16 PCM, integer spectra, table ids,
+    and its reveal bits."""
+    ref = json.load(open(golden_path("ref_fuzz.json")))[name]
+    r = oracle.decode(open(golden_path(name + ".mp3"), "rb").read())
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    assert r["n_frames"] == ref["n_frames"] and r["bit_rate"] == ref["bitrate"] and r["sampling_rate"] == ref["sampling_rate"]
+    assert r["bits"] == ref["bits"]
+    assert sha(r["tables"][:, :6 * ref["channels"]].astype(np.uint8)) == ref["tables_sha256"]   # the reference lists 6 ids per channel
+    assert sha(r["spectra"].astype(np.int16)) == ref["spectra_sha256"]
+    assert sha(r["pcm16"].astype(np.int16)) == ref["pcm16_sha256"]

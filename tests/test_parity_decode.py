@@ -114,6 +114,7 @@ def test_batch_of_all_goldens_vs_oracle(handle, oracle):
     blobs += [np.load(p)["mp3"].tobytes() for p in sorted(glob.glob(os.path.join(GOLDEN, "ref_synth_*.npz")))]
     blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "ref_test_*.mp3")))]
     blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "stream_*.mp3")))]
+    blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "fuzz_*.mp3")))]   # configs[3] as a corpus
     res = _decode_batch(handle, blobs)
     resf = _decode_batch(handle, blobs, spectra=False, as_float=True)
     for b, g, gf in zip(blobs, res, resf):
@@ -188,3 +189,28 @@ def test_full_size_properties(handle, oracle):
         assert np.abs(seg[1152:] - ref[1152:]).max() <= PCM_TOL_LSB
         pos += 65
     _check(got[1], singles[0])
+
+
+def test_fuzz_corpus_exact_decode_vs_reference_digests(handle):
+    """The float64 instantiation on the 16 fuzz streams (short / mixed blocks, MS, reservoir, CRC, mono, VBR ...): the int16 PCM, the
+    integer spectra, the table ids and the reveal bits equal the unmodified reference's, by digest."""
+    import hashlib
+    import json
+    ref = json.load(open(golden_path("ref_fuzz.json")))
+    names = sorted(ref)
+    blobs = [open(golden_path(n + ".mp3"), "rb").read() for n in names]
+    data = np.frombuffer(b"".join(blobs), np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])])
+    sc = handle.decode_scan(data, off)
+    ids, bits = handle.decode_reveal()
+    pcm, sp = handle.decode_run(spectra=True, exact=True)
+    fb = np.concatenate([[0], np.cumsum(sc["n_frames"])])
+    eb = np.concatenate([[0], np.cumsum(sc["pcm_rows"] * np.maximum(sc["channels"], 1))])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    for i, n in enumerate(names):
+        r = ref[n]
+        assert int(sc["n_frames"][i]) == r["n_frames"] and int(sc["sample_rate"][i]) == r["sampling_rate"], n
+        assert bits[i] == r["bits"], n
+        assert sha(ids[fb[i]:fb[i + 1], :6 * r["channels"]]) == r["tables_sha256"], n   # the reference lists 6 ids per channel
+        assert sha(sp[fb[i]:fb[i + 1]].astype(np.int16)) == r["spectra_sha256"], n
+        assert sha(pcm[eb[i]:eb[i + 1]].astype(np.int16)) == r["pcm16_sha256"], n

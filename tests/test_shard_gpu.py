@@ -44,7 +44,8 @@ def test_product_encoded_file_in_ranges(handle, oracle, bitrate):
 
 
 @pytest.mark.parametrize("name", ["stream_reservoir", "stream_vbr_32k_pad", "stream_mono_crc_48k", "stream_ms_stereo",
-                                  "stream_long_alltables", "stream_short_mixed", "stream_is_only_bit"])
+                                  "stream_long_alltables", "stream_short_mixed", "stream_is_only_bit",
+                                  "fuzz_00", "fuzz_02", "fuzz_05", "fuzz_10", "fuzz_13"])
 def test_writer_streams_in_ranges(handle, name):
     """main_data_begin > 0 (the halo must carry the reservoir), variable frame sizes, 21-byte side info, and the streams whose
     granules inherit scalefactors from earlier frames (whole-prefix halo)."""
