@@ -220,3 +220,46 @@ def test_hide_reveal_roundtrip_at_scale(handle, oracle):
         assert r[:min(used, len(b))] == b[:min(used, len(b))]
         if used >= len(b):
             assert oracle.reveal_parse(r) == m
+
+
+def _random_clip(rng, sr):
+    """Tone + noise under a random piecewise envelope: loud stretches, near-silent ones (a few LSB), digital silence and clicks in one
+    clip, so that coded, silent and stale-address granules (A.E6) follow each other within a slot."""
+    n_frames = int(rng.integers(1, 31))
+    n = n_frames * 1152
+    t = np.arange(n) / sr
+    f = rng.uniform(60, 6000, 2)
+    x = np.stack([np.sin(2 * np.pi * f[c] * t) + rng.uniform(0, 0.3) * rng.standard_normal(n) for c in range(2)], axis=1)
+    env = np.zeros(n)
+    pos = 0
+    while pos < n:
+        seg = int(rng.integers(200, 4000))
+        kind = rng.integers(0, 5)
+        env[pos:pos + seg] = (0.0, rng.uniform(1, 8) / 32767, rng.uniform(0.001, 0.02), rng.uniform(0.1, 0.6), 0.99)[kind]
+        pos += seg
+    y = (x * env[:, None] * 32767).astype(np.int16)
+    for _ in range(int(rng.integers(0, 4))):
+        y[int(rng.integers(0, n)), int(rng.integers(0, 2))] = int(rng.integers(-32768, 32768))
+    return y
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_random_clips_vs_oracle(handle, oracle, seed):
+    """Randomised batches: bitrate, sample rate, clip lengths, envelopes and payload lengths (none, ending inside the clip -- the
+    two-, one- and zero-bit variants of the rate loop -- or longer than the capacity), vs the oracle clip by clip, taps included."""
+    rng = np.random.default_rng(seed)
+    sr = int(rng.choice([44100, 44100, 48000, 32000]))
+    bitrate = int(rng.choice([32, 48, 64, 96, 128, 160, 224, 320]))
+    clips = [_random_clip(rng, sr) for _ in range(10)]
+    payloads = []
+    for c in clips:
+        cap = 12 * (c.shape[0] // 1152)
+        k = rng.integers(0, 4)
+        ln = (0, int(rng.integers(1, 12)), int(rng.integers(1, max(2, cap))), 3 * cap + 40)[k]
+        payloads.append("".join(rng.choice(["0", "1"], size=ln)) if ln else "")
+    got = _encode(handle, clips, bitrate, payloads=payloads, sr=sr)
+    for i, (c, p, g) in enumerate(zip(clips, payloads, got)):
+        ref = oracle.encode(c, sr, bitrate, p)
+        _check_taps(g, ref)
+        assert g["hide_str_offset"] == ref["hide_str_offset"], (seed, i)
+        assert g["mp3"] == ref["mp3"], (seed, i)
