@@ -273,9 +273,9 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
 }
 
 // ================================================================================================
-// E2: rate loop, one warp per clip
+// E2: the probe machinery shared by every form of the rate loop, and its sequential form k_enc_rate_chain (one CTA per clip)
 // ================================================================================================
-#define RATE_WARPS 2       // warps per clip: warp w owns granule index gr = w of every frame (see k_enc_rate)
+#define RATE_WARPS 2       // warps per clip of the sequential form: warp w owns granule index gr = w of every frame (see k_enc_rate_chain)
 
 struct RateSmem {
     uint16_t i2i[10000];
@@ -352,7 +352,7 @@ __device__ __forceinline__ int choose_table(const RateSmem &S, int mx, uint32_t 
 // Everything a probe derives from the quantised values WITHOUT looking at the payload bits: run lengths, count1 bits, region
 // bounds and, per region, the maximum and the pooled code-length / sign / escape sums.  The table choice (with the stego swap)
 // and the bit count follow from it in a few scalar steps (probe_tables), which is what lets a mispredicted granule be replayed
-// from its recorded probes instead of re-running them (k_enc_rate).
+// from its recorded probes instead of re-running them (k_enc_rate_chain).
 struct Pooled {
     int c1bits, c1sel, bv, count1, r0, r1, a1, a2, a3;
     uint32_t m0, m1, m2, lo0, hi0, cn0, lo1, hi1, cn1, lo2, hi2, cn2;
