@@ -69,3 +69,26 @@ def test_variants_and_resolve_reproduce_the_chain(model):
     for name, plen in (("tone", 37), ("tone", 8), ("tone", 0), ("clicks", 50), ("hush", 3)):
         r = _run(model, f"{name}_p{plen}", clips[name], 128, bits, payload_len=plen)
         assert r["bad"] == 0, (name, plen, r)
+
+
+def test_probe_bounds_never_decide_wrongly(tmp_path):
+    """Model of the next optimisation of the probe kernel: certified lower / upper bounds on a probe's bit count decide
+    about 3 of the 7 binary-search probes of a granule at 128 kbps without running them -- and never differently from the true count."""
+    exe = str(tmp_path / "probe_bounds_model")
+    subprocess.check_call(["gcc", "-O2", "-w", "-o", exe, os.path.join(ROOT, "tests", "model", "probe_bounds_model.c"), "-lm"])
+    rng = np.random.default_rng(9)
+    n = 12 * 1152
+    clips = dict(tone=synth_wav(4, 60), loud=rng.integers(-32768, 32767, size=(n, 2)).astype(np.int16),
+                 hush=rng.integers(-6, 7, size=(n, 2)).astype(np.int16))
+    decided = {}
+    for name, pcm in clips.items():
+        raw = str(tmp_path / f"{name}.raw")
+        np.ascontiguousarray(pcm, dtype=np.int16).tofile(raw)
+        for br in (64, 128, 320):
+            out = subprocess.run([exe, raw, str(pcm.shape[0] // 1152), str(br)], capture_output=True, text=True, check=True).stdout
+            m = re.search(r"probes\(bin search\) (\d+)  decided by LB (\d+)  by UB (\d+)  violations (\d+)", out)
+            assert m, out
+            probes, lb, ub, viol = map(int, m.groups())
+            assert viol == 0, (name, br, out)
+            decided[(name, br)] = (lb + ub) / max(probes, 1)
+    assert decided[("tone", 128)] > 0.35      # ~3 of 7 probes on the benchmark's kind of clip
