@@ -124,6 +124,36 @@ M3S_API int m3s_decode_frame_pos(m3s_handle_t h, int64_t *frame_pos);
 M3S_API int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t *pcm_off, int16_t *spectra,
                            uint32_t flags);
 
+/* Frame-range decode of one file of the last scan (a long file split across several GPUs): frames
+ * [first_frame, first_frame + frame_count) of file `file_index` into `pcm` (host or device per mem), *rows_out = PCM rows written
+ * (1152 per frame, + 1152 when the range holds the last frame of a file that ends in junk).  The library decodes one warm-up
+ * frame in front of the range (overlap-add tail + synthesis fifo, Frame.py:81-92,150-153) and compacts the <= 9 frames of bit
+ * reservoir it may reach into (Frame.py:306-309,337-356); the ranges of all ranks, concatenated, equal the whole-file decode. */
+M3S_API int m3s_decode_run_range(m3s_handle_t h, int32_t file_index, int64_t first_frame, int64_t frame_count, void *pcm, int mem,
+                                 int64_t *rows_out, uint32_t flags);
+
+/* The batch call: everything above in ONE call that pipelines itself -- MP3Parser.parse_file + write_to_wav's conversion
+ * (MP3_Parser.py:57-91) for n_files files.  The library cuts the batch into waves of whole files and overlaps, on its own
+ * streams, the upload of wave k+1 (host buffers), the scan of wave k+1, the Huffman + synthesis kernels of wave k and the
+ * download of wave k-1 (host buffers); the host thread waits once per wave and the call returns when every output is readable.
+ *   bytes, mem, file_off, audio_start, n_files   as m3s_decode_scan
+ *   pcm            interleaved samples of all files back to back (int16, or float32 with M3S_DEC_PCM_FLOAT); host or device per mem
+ *   pcm_capacity   elements `pcm` can hold; M3S_ERR_CAPACITY if the batch decodes to more (m3s_decode_bound sizes it)
+ *   pcm_off        [n_files+1] host, OUT (may be NULL): element offset of every file in pcm, and the total
+ *   table_ids, reveal_bits   as m3s_decode_reveal (host or device per mem; either may be NULL); frames_capacity = frames they hold
+ *   reveal_len, n_frames, sample_rate, channels, bitrate_bps, status   [n_files] host, OUT, any may be NULL
+ *   flags          M3S_DEC_* */
+M3S_API int m3s_decode(m3s_handle_t h, const uint8_t *bytes, int mem, const int64_t *file_off, const int64_t *audio_start,
+                       int32_t n_files, void *pcm, int64_t pcm_capacity, int64_t *pcm_off, uint8_t *table_ids, uint8_t *reveal_bits,
+                       int64_t frames_capacity, int64_t *reveal_len, int64_t *n_frames, int32_t *sample_rate, int32_t *channels,
+                       int32_t *bitrate_bps, int32_t *status, uint32_t flags);
+/* Host-only sizing aid for m3s_decode with HOST bytes: frames each file can hold according to its first frame header (exact
+ * for constant-bitrate files, which is all the reference's own encoder writes; a VBR file may decode to more and then makes
+ * m3s_decode return M3S_ERR_CAPACITY -- size from m3s_decode_scan's pcm_rows instead).  Returns the PCM elements to reserve
+ * (stereo assumed) and the frame count through *frames_bound; < 0 on bad arguments. */
+M3S_API int64_t m3s_decode_bound(const uint8_t *bytes_host, const int64_t *file_off, const int64_t *audio_start, int32_t n_files,
+                                 int64_t *frames_bound);
+
 /* ------------------------------------------------------------------ encode
  * Replaces MP3Encoder.__init__ + MP3Encoder.encode (MP3_Encoder.py:462-650): analysis filterbank + MDCT
  * (:652-758), rate loop with the stego table swap (:760-1264) and bitstream formatting (:1266-1552),

@@ -151,6 +151,43 @@ struct M3sBuf {
     size_t cap = 0;
 };
 
+// One CTA's run of frames in k_hybrid.
+struct M3sWork {
+    int64_t g_first;   // first frame whose PCM this CTA emits
+    int32_t count;     // frames to emit
+    int32_t warm;      // 1: decode frame g_first-1 first without emitting
+    int64_t pcm_elem;  // element offset of frame g_first's first sample in the PCM buffer
+    int32_t channels;
+    int32_t pad;
+};
+
+// Written by k_layout, one per scan: the wave's totals.
+struct M3sLayout {
+    int64_t total_frames;
+    int64_t s_bytes;        // bytes of the header-stripped stream S the wave needs
+    int64_t irregular;      // frames past the ninth of a file whose bit reservoir is assembled explicitly (see k_sideinfo)
+    int32_t overflow;       // total_frames exceeded the set's capacity: the scan stopped after the walk
+    int32_t pad;
+};
+
+// One wave's scan state: D0 (frame walk, per-frame records, unit records) and D4 (table ids, reveal chars).
+struct M3sScanSet {
+    M3sBuf files, fouts, tmp_pos, fr_pos, fr_P, fr_meta, fr_carry, fr_reveal, fr_file, units, tabids, reveal, layout, irr;
+    // per-file results and the totals reach the host through MAPPED pinned memory (kernel stores), not copy-engine commands: a scan
+    // is then never queued behind a bulk PCM transfer
+    M3sFileOut *fouts_mapped = nullptr, *fouts_mdev = nullptr;
+    M3sLayout *lay_mapped = nullptr, *lay_mdev = nullptr;
+    size_t fouts_cap = 0;
+    int64_t frames_cap = 0;            // frames the per-frame buffers hold
+    int32_t n_files = 0;
+    int64_t total_frames = 0, s_bytes = 0, total_bytes = 0, irregular = 0;
+    const uint8_t *d_bytes = nullptr;  // device pointer to the wave's bytes (caller's or staged)
+    std::vector<M3sFileRec> files_h;
+    std::vector<M3sFileOut> fouts_h;
+    void *pin = nullptr;               // pinned staging of the file records
+    size_t pin_cap = 0;
+};
+
 struct m3s_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -175,22 +212,22 @@ struct m3s_ctx {
     M3sDevTablesD *d_tab_f64 = nullptr;
     int sm_count = 148;
 
-    // ---- decode state (valid between m3s_decode_scan and the next scan)
+    // ---- decode state.  A scan set holds one wave's D0 + D4 results (valid between a scan and the next scan on that set); the pipelined
+    //      batch call m3s_decode alternates between the two sets so that wave k+1 is scanned while wave k is in the big kernels.
+    M3sScanSet ss[2];
+    M3sScanSet *cur = &ss[0];          // the set m3s_decode_reveal / m3s_decode_frame_pos / m3s_decode_run work on
     bool scanned = false;
-    int32_t n_files = 0;
-    int64_t total_frames = 0;
-    int64_t s_bytes = 0;
-    const uint8_t *d_bytes = nullptr;  // device pointer to the batch bytes (caller's or staged)
-    std::vector<M3sFileRec> files;
-    std::vector<M3sFileOut> fouts;
-    // per-file results of the scan kernels land in MAPPED pinned host memory (zero-copy stores): reading them back needs no
-    // copy-engine command, so a scan is never queued behind another handle's bulk PCM transfer
-    M3sFileOut *fouts_mapped = nullptr, *fouts_dev = nullptr;
-    size_t fouts_cap = 0;
-    uint8_t *rev_mapped = nullptr, *rev_dev = nullptr;   // same idea for the reveal outputs (24 bytes per frame), filled by a copy KERNEL
+    double dec_bpf_guess = 0.0;        // bytes per frame seen by earlier scans of device-resident input (sizes the next scan's workspaces)
+    int64_t dec_wave_bytes = 0;        // M3S_DEC_WAVE_BYTES override of the pipelined call's wave size (0 = default)
+    M3sBuf b_stage_in[2], b_pcm_stage[2];
+    M3sBuf b_sf, b_S, b_spec, b_work, b_spec_export;
+    void *work_pin[2] = {nullptr, nullptr};   // pinned staging of the hybrid kernel's work lists
+    size_t work_pin_cap[2] = {0, 0};
+    std::vector<M3sWork> work_h[2];
+    cudaEvent_t ev_d_h2d[2] = {nullptr, nullptr}, ev_d_scan[2] = {nullptr, nullptr}, ev_d_comp[2] = {nullptr, nullptr},
+                ev_d_out[2] = {nullptr, nullptr};
+    uint8_t *rev_mapped = nullptr, *rev_dev = nullptr;   // m3s_decode_reveal to host memory: mapped pinned staging filled by a copy KERNEL
     size_t rev_cap = 0;
-    M3sBuf b_stage_in, b_files, b_tmp_pos, b_fr_pos, b_fr_P, b_fr_meta, b_fr_carry, b_fr_reveal, b_fr_file;
-    M3sBuf b_units, b_sf, b_S, b_spec, b_tabids, b_reveal, b_work, b_pcm_stage, b_spec_export;
     // ---- encode state
     M3sBuf e_clips2, e_mdct2, e_gran2, e_ix2, e_info2, e_scfsi2;   // second set of the buffers the analysis writes ahead
     M3sBuf e_var, e_var2, e_sum, e_sum2;   // per-granule variant records / summaries of the parallel rate loop (k_enc_probe -> k_enc_resolve)
@@ -215,6 +252,14 @@ int m3s_copy_paced(m3s_ctx *h, void *dst, const void *src, size_t bytes, cudaMem
 cudaError_t m3s_copy_bulk(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s);   // in bounded pieces
 cudaError_t m3s_copy_rows(const std::vector<M3sRow> &rows, cudaMemcpyKind kind, cudaStream_t s);
 int m3s_upload_cos36(const float *f, const double *d);  // m3s_decode.cu: constant-memory IMDCT rows of the current device
+
+// launches on `s` are timed on `s` (m3s_time_begin records on launch_stream); restored when the scope ends, error returns included
+struct M3sLaunchOn {
+    m3s_ctx *h;
+    cudaStream_t saved;
+    M3sLaunchOn(m3s_ctx *h_, cudaStream_t s) : h(h_), saved(h_->launch_stream) { h->launch_stream = s; }
+    ~M3sLaunchOn() { h->launch_stream = saved; }
+};
 
 #define M3S_CUDA(h, call)                                                                             \
     do {                                                                                              \

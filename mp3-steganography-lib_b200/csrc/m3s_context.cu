@@ -23,6 +23,11 @@ int m3s_buf_reserve(m3s_ctx *h, M3sBuf &b, size_t bytes)
     if (bytes <= b.cap) return M3S_OK;
     if (b.p) {
         M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->copy_in) {   // the helper streams of the pipelines may still reference the buffer (e.g. after an early error return)
+            M3S_CUDA(h, cudaStreamSynchronize(h->copy_in));
+            M3S_CUDA(h, cudaStreamSynchronize(h->copy_out));
+            M3S_CUDA(h, cudaStreamSynchronize(h->aux));
+        }
         M3S_CUDA(h, cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -228,7 +233,7 @@ static void build_tables(M3sDevTables *T)
 
 static_assert(sizeof(M3S_HUFF_PACKED) / sizeof(uint32_t) == 1410, "packed code book size");
 
-extern "C" int m3s_version(void) { return 100; }
+extern "C" int m3s_version(void) { return 200; }
 
 extern "C" int m3s_create(int device, m3s_handle_t *out)
 {
@@ -256,11 +261,13 @@ extern "C" int m3s_create(int device, m3s_handle_t *out)
     }
     h->stream = h->own_stream;
     if (const char *cb = getenv("M3S_ENC_CHUNK_FRAMES")) h->enc_chunk_budget = atoll(cb);
+    if (const char *cb = getenv("M3S_DEC_WAVE_BYTES")) h->dec_wave_bytes = atoll(cb);
     M3sDevTables *T = new M3sDevTables();
     memset(T, 0, sizeof *T);
     build_tables(T);
     if (build_huff_lut(T) < 0) {
         delete T;
+        cudaStreamDestroy(h->own_stream);
         delete h;
         return M3S_ERR_STATE;
     }
@@ -288,6 +295,8 @@ extern "C" int m3s_create(int device, m3s_handle_t *out)
         if (m3s_upload_cos36(&cf[0][0], &cd[0][0]) != 0) e = cudaErrorUnknown;
     }
     if (e != cudaSuccess) {
+        if (h->d_tab) cudaFree(h->d_tab);
+        if (h->d_tab_f64) cudaFree(h->d_tab_f64);
         cudaStreamDestroy(h->own_stream);
         delete h;
         return M3S_ERR_CUDA;
@@ -389,14 +398,25 @@ extern "C" int m3s_destroy(m3s_handle_t h)
     if (!h) return M3S_ERR_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    M3sBuf *bufs[] = {&h->b_stage_in, &h->b_files, &h->b_tmp_pos, &h->b_fr_pos, &h->b_fr_P, &h->b_fr_meta, &h->b_fr_carry,
-                      &h->b_fr_reveal, &h->b_fr_file, &h->b_units, &h->b_sf, &h->b_S, &h->b_spec, &h->b_tabids,
-                      &h->b_reveal, &h->b_work, &h->b_pcm_stage, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
+    if (h->copy_in) { cudaStreamSynchronize(h->copy_in); cudaStreamSynchronize(h->copy_out); cudaStreamSynchronize(h->aux); }
+    M3sBuf *bufs[] = {&h->b_stage_in[0], &h->b_stage_in[1], &h->b_pcm_stage[0], &h->b_pcm_stage[1],
+                      &h->b_sf, &h->b_S, &h->b_spec,
+                      &h->b_work, &h->b_spec_export, &h->e_pcm, &h->e_clips, &h->e_mdct,
                       &h->e_ix, &h->e_info, &h->e_gran, &h->e_out, &h->e_payload, &h->e_misc, &h->e_pad, &h->e_tabs, &h->e_state,
                       &h->e_lastix, &h->e_scfsi, &h->e_work, &h->e_clips2, &h->e_mdct2, &h->e_gran2, &h->e_ix2, &h->e_info2, &h->e_scfsi2,
                       &h->e_var, &h->e_var2, &h->e_sum, &h->e_sum2};
     for (M3sBuf *b : bufs) free_buf(*b);
-    if (h->fouts_mapped) cudaFreeHost(h->fouts_mapped);
+    for (M3sScanSet &ss : h->ss) {
+        M3sBuf *sb[] = {&ss.files, &ss.fouts, &ss.tmp_pos, &ss.fr_pos, &ss.fr_P, &ss.fr_meta, &ss.fr_carry, &ss.fr_reveal, &ss.fr_file,
+                        &ss.units, &ss.tabids, &ss.reveal, &ss.layout, &ss.irr};
+        for (M3sBuf *b : sb) free_buf(*b);
+        if (ss.fouts_mapped) cudaFreeHost(ss.fouts_mapped);
+        if (ss.pin) cudaFreeHost(ss.pin);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (h->work_pin[i]) cudaFreeHost(h->work_pin[i]);
+        if (h->ev_d_h2d[i]) { cudaEventDestroy(h->ev_d_h2d[i]); cudaEventDestroy(h->ev_d_scan[i]); cudaEventDestroy(h->ev_d_comp[i]); cudaEventDestroy(h->ev_d_out[i]); }
+    }
     if (h->rev_mapped) cudaFreeHost(h->rev_mapped);
     timing_resolve(h);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

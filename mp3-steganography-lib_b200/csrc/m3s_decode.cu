@@ -174,6 +174,61 @@ k_walk(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec 
 }
 
 // ================================================================================================
+// D0a'': the wave's layout, one CTA: exclusive prefix sums over the files of the frame counts (global frame index of each file's
+// first frame) and of the main-data bytes (position of each file's header-stripped stream in S), written into the device file
+// records -- the host does not have to see the walk's result before the per-frame kernels can be launched.  Each file's stream is
+// preceded by M3S_APX_BYTES of assembly slots for its first nine frames (see resv_plan) and 512 zero bytes.
+// ================================================================================================
+#define M3S_APX_SLOTS 9
+#define M3S_APX_SLOT_BYTES 2048
+#define M3S_APX_BYTES (M3S_APX_SLOTS * M3S_APX_SLOT_BYTES)
+#define M3S_META_IRR (1u << 26)           // fr_meta: the frame's main data is assembled explicitly into a slot (k_reservoir_fix)
+
+__global__ void __launch_bounds__(256)
+k_layout(M3sFileRec *__restrict__ files, const M3sFileOut *__restrict__ fouts, int n_files, int64_t frames_cap, M3sLayout *lay)
+{
+    __shared__ int64_t s_fr[256], s_sb[256];
+    __shared__ int64_t carry_fr, carry_sb;
+    const int tid = threadIdx.x;
+    if (tid == 0) { carry_fr = 0; carry_sb = 0; }
+    __syncthreads();
+    for (int base = 0; base < n_files; base += 256) {
+        const int f = base + tid;
+        int64_t nfr = 0, sbytes = 0;
+        if (f < n_files) {
+            nfr = fouts[f].n_frames;
+            sbytes = M3S_APX_BYTES + 512 + ((fouts[f].payload_total + 15) & ~(int64_t)15) + 64;
+        }
+        s_fr[tid] = nfr; s_sb[tid] = sbytes;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            int64_t a = 0, b = 0;
+            if (tid >= d) { a = s_fr[tid - d]; b = s_sb[tid - d]; }
+            __syncthreads();
+            s_fr[tid] += a; s_sb[tid] += b;
+            __syncthreads();
+        }
+        if (f < n_files) {
+            files[f].frame_base = carry_fr + s_fr[tid] - nfr;
+            files[f].s_base = carry_sb + s_sb[tid] - sbytes + M3S_APX_BYTES + 512;
+            files[f].n_frames = (int32_t)nfr;
+            files[f].flags = fouts[f].status;
+            files[f].channels = fouts[f].channels;
+        }
+        __syncthreads();
+        if (tid == 255) { carry_fr += s_fr[255]; carry_sb += s_sb[255]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        lay->total_frames = carry_fr;
+        lay->s_bytes = carry_sb + 64;
+        lay->irregular = 0;
+        lay->overflow = carry_fr > frames_cap ? 1 : 0;
+        lay->pad = 0;
+    }
+}
+
+// ================================================================================================
 // D0a': per-file scans over the frames found by the walk, one warp per file, one frame per lane:
 // payload prefix (position in the header-stripped stream), the carried table_select[2] of window-switched
 // granules (A.D3: FrameSideInformation.py:104-107 parses only two selects, the third keeps its old value)
@@ -192,12 +247,12 @@ __global__ void __launch_bounds__(32 * WALK_WARPS)
 k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec *__restrict__ files, M3sFileOut *fouts,
         int n_files, const uint32_t *__restrict__ tmp_pos, int64_t *__restrict__ fr_pos, uint32_t *__restrict__ fr_P,
         uint32_t *__restrict__ fr_meta, uint32_t *__restrict__ fr_carry, uint32_t *__restrict__ fr_reveal,
-        int32_t *__restrict__ fr_file)
+        int32_t *__restrict__ fr_file, const M3sLayout *__restrict__ lay)
 {
     __shared__ uint32_t s_win[WALK_WARPS][32 * FSCAN_STRIDE + 4];
     const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;
     const int f = blockIdx.x * WALK_WARPS + wip;
-    if (f >= n_files) return;
+    if (f >= n_files || lay->overflow) return;   // overflow: the per-frame arrays are too small, the host grows them and rescans
     const M3sFileRec fr = files[f];
     const int64_t fend = fr.end;
     const int64_t align_fix = (int64_t)((uintptr_t)bytes & 15);
@@ -301,18 +356,108 @@ k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec
 }
 
 // ================================================================================================
+// Bit reservoir, the reference's way (Frame.py:318-363).  A frame's main data is the `main_data_begin` bytes in front of its header,
+// skipping the headers + side infos of the frames in between, then its own payload.  On the header-stripped stream S that is plain
+// addressing (start = sum of earlier payloads - main_data_begin) -- as long as every byte comes out of an earlier frame's payload.
+// The reference does NOT require that; it applies its formula to whatever lies in front of the frame:
+//   * it remembers the sizes of 9 earlier frames, the list starting (A.D9) with a phantom copy of frame 0 in front of the file
+//     (MP3Parser.__init__ calls set_frame_size once more than there are frames), then zeros;
+//   * it takes the CURRENT frame's header + side-info length C for every earlier frame (mono / stereo or CRC changes shift the cut);
+//   * the window search `main_data_begin < bound` may fail within the first 8 frames of a file: main_data then stays what the
+//     PREVIOUS frame assembled (a cut stream whose first frames still point into the missing part);
+//   * bytes "of the phantom frame" are the bytes physically in front of frame 0 (an ID3 tag), with Python's slice rules when the
+//     position is negative.
+// resv_plan() decides which of the three a frame is; the irregular ones get their main data assembled byte by byte into a slot
+// (k_reservoir_fix) and their unit records point there.
+// ================================================================================================
+struct M3sResvPlan {
+    int kind;        // 0: regular (S addressing)   1: assembled from the segments below + own payload   2: stale (no window matched)
+    int nseg;
+    int total;       // bytes of the segments (without the own payload)
+    int64_t lo[10];  // absolute batch positions
+    int len[10];
+};
+
+__device__ __forceinline__ void py_slice(int64_t a, int64_t b, int64_t n, int64_t &lo, int64_t &len)   // list[a:b] of a list of n
+{
+    if (a < 0) { a += n; if (a < 0) a = 0; }
+    if (b < 0) { b += n; if (b < 0) b = 0; }
+    if (a > n) a = n;
+    if (b > n) b = n;
+    lo = a;
+    len = b > a ? b - a : 0;
+}
+
+__device__ __forceinline__ int nominal_frame_size(const uint8_t *bytes, int64_t pos, int64_t fend)
+{
+    M3sHdr h;
+    if (parse_header(ldb(bytes, pos + 1, fend), ldb(bytes, pos + 2, fend), ldb(bytes, pos + 3, fend), h) < 0) return 0;
+    return h.frame_size;
+}
+
+// g: global frame index, n: its index inside the file, mdb > 0
+__device__ __noinline__ void resv_plan(const uint8_t *__restrict__ bytes, const M3sFileRec &fr, const int64_t *__restrict__ fr_pos,
+                                       const uint32_t *fr_meta, int64_t g, int n, int mdb, M3sResvPlan &pl)
+{
+    const int C = (int)((fr_meta[g] >> M3S_META_HDR_SHIFT) & 63u);
+    pl.nseg = 0;
+    pl.total = 0;
+    // ---- regular: every byte comes out of the payload of a real earlier frame with the same C
+    {
+        int acc = 0;
+        const int lim = n < 9 ? n : 9;
+        for (int i = 1; i <= lim; i++) {
+            if ((int)((fr_meta[g - i] >> M3S_META_HDR_SHIFT) & 63u) != C) break;
+            acc += (int)(fr_pos[g - i + 1] - fr_pos[g - i]) - C;
+            if (mdb <= acc) { pl.kind = 0; return; }
+        }
+    }
+    // ---- the reference's search, literally
+    int prev[9];
+    for (int i = 0; i < 9; i++) {
+        if (i < n) prev[i] = (int)(fr_pos[g - i] - fr_pos[g - 1 - i]);
+        else if (i == n) prev[i] = nominal_frame_size(bytes, fr_pos[g - n], fr.end);
+        else prev[i] = 0;
+    }
+    const int64_t curr = fr_pos[g] - fr.begin, flen = fr.end - fr.begin;
+    int bound = 0;
+    for (int frame = 0; frame < 9; frame++) {
+        bound += prev[frame] - C;
+        if (mdb < bound) {
+            int part[9];
+            part[frame] = mdb;
+            for (int i = 0; i < frame; i++) { part[i] = prev[i] - C; part[frame] -= part[i]; }
+            int64_t ptr = (int64_t)mdb + (int64_t)frame * C;
+            for (int i = frame; i >= 0; i--) {
+                const int64_t loc = curr - ptr;
+                int64_t lo, len;
+                py_slice(loc, loc + part[i], flen, lo, len);
+                pl.lo[pl.nseg] = fr.begin + lo;
+                pl.len[pl.nseg] = (int)len;
+                pl.total += (int)len;
+                pl.nseg++;
+                ptr -= part[i] + C;
+            }
+            pl.kind = 1;
+            return;
+        }
+    }
+    pl.kind = 2;
+}
+
+// ================================================================================================
 // D0b + D4: side-info parse, one thread per frame (FrameSideInformation.py:39-137), bit cursors through
 // the reservoir (Frame.py:318-363 restated on the header-stripped stream S), table ids and reveal chars
 // (Frame.py:676-685, util.py:67-81).
 // ================================================================================================
-__global__ void k_sideinfo(const uint8_t *__restrict__ bytes, const M3sFileRec *__restrict__ files, int64_t total_frames,
+__global__ void k_sideinfo(const uint8_t *__restrict__ bytes, const M3sFileRec *__restrict__ files, M3sLayout *lay,
                            const int64_t *__restrict__ fr_pos, const uint32_t *__restrict__ fr_P,
-                           const uint32_t *__restrict__ fr_meta, const uint32_t *__restrict__ fr_carry,
+                           uint32_t *fr_meta, const uint32_t *__restrict__ fr_carry,
                            const uint32_t *__restrict__ fr_reveal, const int32_t *__restrict__ fr_file, M3sUnitRec *units,
-                           uint8_t *tabids, uint8_t *reveal)
+                           uint8_t *tabids, uint8_t *reveal, uint32_t *irr)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_frames) return;
+    if (lay->overflow || g >= lay->total_frames) return;
     int f = fr_file[g];
     const M3sFileRec fr = files[f];
     uint32_t meta = fr_meta[g];
@@ -326,11 +471,49 @@ __global__ void k_sideinfo(const uint8_t *__restrict__ bytes, const M3sFileRec *
     int payload = meta & M3S_META_PAYLOAD_MASK;
     int64_t cur = 8 * (fr.s_base + (int64_t)fr_P[g] - (int64_t)mdb);
     int64_t limit = 8 * (fr.s_base + (int64_t)fr_P[g] + payload);
+    if (mdb) {
+        const int n = (int)(g - fr.frame_base);
+        M3sResvPlan pl;
+        resv_plan(bytes, fr, fr_pos, fr_meta, g, n, (int)mdb, pl);
+        if (pl.kind != 0) {
+            int64_t k = g;          // the frame whose assembled main data this frame reads
+            int kn = n;
+            uint32_t kmdb = mdb;
+            while (pl.kind == 2 && kn > 0) {   // stale: what the previous frame assembled (at most 7 steps, first frames of a file only)
+                k--; kn--;
+                const uint32_t km = fr_meta[k];
+                kmdb = bits_at(bytes, fr_pos[k] + 4 + ((km & M3S_META_CRC) ? 2 : 0), fend, 0, 9);
+                if (kmdb == 0) { pl.kind = 0; break; }
+                resv_plan(bytes, fr, fr_pos, fr_meta, k, kn, (int)kmdb, pl);
+            }
+            const int kpayload = (int)(fr_meta[k] & M3S_META_PAYLOAD_MASK);
+            if (pl.kind == 2) {            // frame 0 found no window either: main_data is still the empty list
+                cur = 8 * fr.s_base;
+                limit = cur;
+            } else if (pl.kind == 0) {
+                cur = 8 * (fr.s_base + (int64_t)fr_P[k] - (int64_t)kmdb);
+                limit = 8 * (fr.s_base + (int64_t)fr_P[k] + kpayload);
+            } else {
+                int64_t slot_addr;
+                if (kn < M3S_APX_SLOTS) {
+                    slot_addr = fr.s_base - 512 - M3S_APX_BYTES + (int64_t)kn * M3S_APX_SLOT_BYTES;
+                    if (k == g) { meta |= M3S_META_IRR; fr_meta[g] = meta; }
+                } else {   // only reached with k == g: the stale chain never leaves the first 8 frames
+                    const unsigned long long slot = atomicAdd((unsigned long long *)&lay->irregular, 1ULL);
+                    irr[slot] = (uint32_t)g;
+                    slot_addr = lay->s_bytes + (int64_t)slot * M3S_APX_SLOT_BYTES;
+                }
+                cur = 8 * slot_addr;
+                limit = 8 * (slot_addr + pl.total + kpayload);
+            }
+        }
+    }
     uint8_t ids[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) ids[i] = 0;
     M3sUnitRec inval;
-    inval.bit_start = 0; inval.limit_bits = 0; inval.a = 0; inval.b = 0; inval.c = 0; inval.frame = (uint32_t)g; inval.pad = 0;
+    inval.bit_start = 0; inval.limit_bits = 0; inval.a = 0; inval.b = 0; inval.frame = (uint32_t)g; inval.pad = 0;
+    inval.c = (meta & M3S_META_FIRST) ? (1u << 18) : 0;   // the backward walks for stale scalefactors stop at a file's first frame
     if (mono) { units[4 * g + 1] = inval; units[4 * g + 3] = inval; }
     for (int gr = 0; gr < 2; gr++)
         for (int ch = 0; ch < (mono ? 1 : 2); ch++) {
@@ -397,12 +580,12 @@ __global__ void k_sideinfo(const uint8_t *__restrict__ bytes, const M3sFileRec *
 // file) to its position in the header-stripped stream S, one warp per frame.
 // ================================================================================================
 __global__ void k_strip(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec *__restrict__ files,
-                        int64_t total_frames, const int64_t *__restrict__ fr_pos, const uint32_t *__restrict__ fr_P,
+                        int64_t g_lo, int64_t g_hi, const int64_t *__restrict__ fr_pos, const uint32_t *__restrict__ fr_P,
                         const uint32_t *__restrict__ fr_meta, const int32_t *__restrict__ fr_file, uint8_t *S)
 {
-    int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t g = g_lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     int lane = threadIdx.x & 31;
-    if (g >= total_frames) return;
+    if (g >= g_hi) return;
     uint32_t meta = fr_meta[g];
     int n = meta & M3S_META_PAYLOAD_MASK;
     int64_t src = fr_pos[g] + ((meta >> M3S_META_HDR_SHIFT) & 63);
@@ -431,6 +614,60 @@ __global__ void k_strip(const uint8_t *__restrict__ bytes, int64_t total_bytes, 
     }
     int tail = n - head - 4 * nwords;
     if (lane < tail) S[dst + head + 4 * nwords + lane] = bytes[src + head + 4 * nwords + lane];
+}
+
+// ================================================================================================
+// Irregular bit reservoirs (see resv_plan): one warp per candidate frame -- the first nine frames of every file (flagged
+// M3S_META_IRR by k_sideinfo) and the frames k_sideinfo listed in `irr` -- copies the segments the reference would assemble,
+// then the frame's own payload, into the frame's slot.
+// ================================================================================================
+__global__ void k_reservoir_fix(const uint8_t *__restrict__ bytes, const M3sFileRec *__restrict__ files, int n_files,
+                                const int64_t *__restrict__ fr_pos, const uint32_t *__restrict__ fr_meta,
+                                const int32_t *__restrict__ fr_file, const uint32_t *__restrict__ irr, int64_t n_irr,
+                                int64_t apx2_base, uint8_t *S)
+{
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    int64_t g, slot_addr;
+    int n;
+    if (w < (int64_t)n_files * M3S_APX_SLOTS) {
+        const int f = (int)(w / M3S_APX_SLOTS);
+        n = (int)(w - (int64_t)f * M3S_APX_SLOTS);
+        if (n >= files[f].n_frames) return;
+        g = files[f].frame_base + n;
+        if (!(fr_meta[g] & M3S_META_IRR)) return;
+        slot_addr = files[f].s_base - 512 - M3S_APX_BYTES + (int64_t)n * M3S_APX_SLOT_BYTES;
+    } else {
+        const int64_t k = w - (int64_t)n_files * M3S_APX_SLOTS;
+        if (k >= n_irr) return;
+        g = irr[k];
+        n = (int)(g - files[fr_file[g]].frame_base);
+        slot_addr = apx2_base + k * M3S_APX_SLOT_BYTES;
+    }
+    const M3sFileRec fr = files[fr_file[g]];
+    const uint32_t meta = fr_meta[g];
+    const int64_t si = fr_pos[g] + 4 + ((meta & M3S_META_CRC) ? 2 : 0);
+    const int mdb = (int)bits_at(bytes, si, fr.end, 0, 9);
+    M3sResvPlan pl;
+    resv_plan(bytes, fr, fr_pos, fr_meta, g, n, mdb, pl);
+    if (pl.kind != 1) return;
+    int64_t dst = slot_addr;
+    for (int sg = 0; sg < pl.nseg; sg++) {
+        for (int i = lane; i < pl.len[sg]; i += 32) S[dst + i] = bytes[pl.lo[sg] + i];
+        dst += pl.len[sg];
+    }
+    const int own = (int)(meta & M3S_META_PAYLOAD_MASK);
+    const int64_t src = fr_pos[g] + ((meta >> M3S_META_HDR_SHIFT) & 63);
+    for (int i = lane; i < own; i += 32) S[dst + i] = bytes[src + i];
+}
+
+// end of a scan: per-file results and the totals -> mapped host memory
+__global__ void k_scan_publish(const M3sFileOut *__restrict__ fouts, int n_files, const M3sLayout *__restrict__ lay,
+                               M3sFileOut *__restrict__ fouts_host, M3sLayout *__restrict__ lay_host)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_files) fouts_host[i] = fouts[i];
+    if (i == 0) *lay_host = *lay;
 }
 
 // ================================================================================================
@@ -502,10 +739,12 @@ __device__ __noinline__ uint32_t fetch_gr0_long_sf(const uint8_t *S, const M3sUn
 {
     for (int64_t u = u_gr0;; u -= 4) {
         const M3sUnitRec d = units[u];
-        uint32_t sl0 = T->slen[M3S_UB_SFC(d.b)][0], sl1 = T->slen[M3S_UB_SFC(d.b)][1];
-        bool is_short = M3S_UA_BT(d.a) == 2 && M3S_UA_WS(d.a);
-        if (!is_short) return read_bits_at(S, d, sfb < 11 ? sfb * sl0 : 11 * sl0 + (sfb - 11) * sl1, sfb < 11 ? sl0 : sl1);
-        if (M3S_UB_MIXED(d.b) && sfb < 8) return read_bits_at(S, d, sfb * sl0, sl0);
+        if (M3S_UC_VALID(d.c)) {   // not the placeholder of a mono frame's second channel: that frame wrote nothing to this slot
+            uint32_t sl0 = T->slen[M3S_UB_SFC(d.b)][0], sl1 = T->slen[M3S_UB_SFC(d.b)][1];
+            bool is_short = M3S_UA_BT(d.a) == 2 && M3S_UA_WS(d.a);
+            if (!is_short) return read_bits_at(S, d, sfb < 11 ? sfb * sl0 : 11 * sl0 + (sfb - 11) * sl1, sfb < 11 ? sl0 : sl1);
+            if (M3S_UB_MIXED(d.b) && sfb < 8) return read_bits_at(S, d, sfb * sl0, sl0);
+        }
         if (M3S_UC_FIRST(d.c)) return 0u;
     }
 }
@@ -528,7 +767,7 @@ __device__ __noinline__ uint32_t fetch_stale_short_sf(const uint8_t *S, const M3
 #define HUFF_THREADS 256
 
 __global__ void __launch_bounds__(HUFF_THREADS)
-k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int64_t n_units,
+k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int64_t u_lo, int64_t u_hi,
        const M3sDevTables *__restrict__ T, uint32_t *__restrict__ spec, uint8_t *__restrict__ sfout)
 {
     __shared__ uint16_t s_lut[8192];
@@ -538,8 +777,8 @@ k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int6
     if (threadIdx.x < 32) { s_desc[threadIdx.x] = T->huff_desc[threadIdx.x]; s_sub[threadIdx.x] = T->huff_sub[threadIdx.x]; }
     if (threadIdx.x < 64) s_c1[threadIdx.x] = T->count1_lut[threadIdx.x];
     __syncthreads();
-    int64_t u = (int64_t)blockIdx.x * HUFF_THREADS + threadIdx.x;
-    if (u >= n_units) return;
+    int64_t u = u_lo + (int64_t)blockIdx.x * HUFF_THREADS + threadIdx.x;
+    if (u >= u_hi) return;
     const M3sUnitRec rec = units[u];
     uint32_t *out = spec + (u >> 2) * (288 * 4) + (u & 3);
     if (!M3S_UC_VALID(rec.c)) {
@@ -683,14 +922,6 @@ __global__ void k_spec_export(const uint32_t *__restrict__ spec, int64_t total_f
 // (Frame.py:157-218 re_quantize, :561-572, :574-602, :604-622, :106-154 imdct, :624-631, :65-103 synth,
 //  :633-640 interleave, MP3_Parser.py:91 int16 conversion)
 // ================================================================================================
-struct M3sWork {
-    int64_t g_first;   // first frame whose PCM this CTA emits
-    int32_t count;     // frames to emit
-    int32_t warm;      // 1: decode frame g_first-1 first without emitting
-    int64_t pcm_elem;  // element offset of frame g_first's first sample in the PCM buffer
-    int32_t channels;
-    int32_t pad;
-};
 
 #define HYB_THREADS 256
 
@@ -1091,6 +1322,207 @@ static inline double now_ms() { return std::chrono::duration<double, std::milli>
 
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+static int sync_all_streams(m3s_ctx *h)
+{
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->copy_in) {
+        M3S_CUDA(h, cudaStreamSynchronize(h->copy_in));
+        M3S_CUDA(h, cudaStreamSynchronize(h->copy_out));
+        M3S_CUDA(h, cudaStreamSynchronize(h->aux));
+    }
+    return M3S_OK;
+}
+
+// grow-only reserve that is safe while other streams of the handle may still use the buffer
+static int reserve_quiet(m3s_ctx *h, M3sBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return M3S_OK;
+    int rc = sync_all_streams(h);
+    if (rc) return rc;
+    return m3s_buf_reserve(h, b, bytes);
+}
+
+// small pinned staging areas (file records, work lists): an asynchronous copy out of PAGEABLE memory would first wait for the
+// stream to drain, i.e. for the previous wave's kernels
+static int pin_reserve(m3s_ctx *h, void *&p, size_t &cap, size_t bytes)
+{
+    if (bytes <= cap) return M3S_OK;
+    int rc = sync_all_streams(h);
+    if (rc) return rc;
+    if (p) M3S_CUDA(h, cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    M3S_CUDA(h, cudaHostAlloc(&p, want, cudaHostAllocDefault));
+    cap = want;
+    return M3S_OK;
+}
+
+// frames a file of `len` audio bytes can hold when its first header says `first4`; <= 0: no usable header
+static int64_t frames_by_first_header(const uint8_t *p, int64_t len)
+{
+    if (len < 4 || p[0] != 0xFF || p[1] < 0xE0) return 0;
+    const uint32_t b1 = p[1], b2 = p[2];
+    if (((b1 >> 3) & 3) != 3 || ((b1 >> 1) & 3) != 1) return 0;
+    const int sri = (b2 >> 2) & 3;
+    int bi = (int)(b2 >> 4);
+    if (sri == 3 || bi == 15) return 0;
+    static const int br_tab[14] = {32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
+    bi = bi == 0 ? 13 : bi - 1;
+    const int sr = sri == 0 ? 44100 : (sri == 1 ? 48000 : 32000);
+    const int fs = 144 * br_tab[bi] * 1000 / sr;
+    return len / fs + 2;
+}
+
+static int scan_reserve_frames(m3s_ctx *h, M3sScanSet &ss, int64_t frames)
+{
+    if (frames <= ss.frames_cap) return M3S_OK;
+    const int64_t nf = frames + frames / 16 + 64;
+    int rc;
+    if ((rc = reserve_quiet(h, ss.fr_pos, sizeof(int64_t) * (nf + 1)))) return rc;
+    if ((rc = reserve_quiet(h, ss.fr_P, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = reserve_quiet(h, ss.fr_meta, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = reserve_quiet(h, ss.fr_carry, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = reserve_quiet(h, ss.fr_reveal, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = reserve_quiet(h, ss.fr_file, sizeof(int32_t) * nf))) return rc;
+    if ((rc = reserve_quiet(h, ss.irr, sizeof(uint32_t) * nf))) return rc;
+    if ((rc = reserve_quiet(h, ss.units, sizeof(M3sUnitRec) * 4 * nf))) return rc;
+    if ((rc = reserve_quiet(h, ss.tabids, 12 * nf))) return rc;
+    if ((rc = reserve_quiet(h, ss.reveal, 12 * nf))) return rc;
+    ss.frames_cap = nf;
+    return M3S_OK;
+}
+
+// Queue the scan of one wave on stream `s` (no host synchronisation): walk -> layout -> per-file scans -> side info -> publish.
+// `hint` (host copy of the wave's bytes, or NULL) sizes the per-frame arrays from every file's first header; device-resident input is
+// sized from the bytes per frame earlier scans saw.  scan_finish() reads the result once `s` has passed this point.
+static int scan_enqueue(m3s_ctx *h, M3sScanSet &ss, cudaStream_t s, const uint8_t *d_bytes, const uint8_t *hint, const int64_t *file_off,
+                        const int64_t *audio_start, int32_t n_files, bool relaunch_only = false)
+{
+    int rc;
+    M3sLaunchOn on(h, s);
+    const int wg = (n_files + WALK_WARPS - 1) / WALK_WARPS;
+    if (!relaunch_only) {
+        const int64_t base = file_off[0];
+        const int64_t total_bytes = file_off[n_files] - base;
+        ss.n_files = n_files;
+        ss.d_bytes = d_bytes;
+        ss.total_bytes = total_bytes;
+        ss.files_h.assign(n_files, M3sFileRec());
+        ss.fouts_h.assign(n_files, M3sFileOut());
+        int64_t tb = 0, est = 0;
+        for (int i = 0; i < n_files; i++) {
+            M3sFileRec &f = ss.files_h[i];
+            f.begin = file_off[i] - base;
+            f.end = file_off[i + 1] - base;
+            f.audio = f.begin + (audio_start ? audio_start[i] : 0);
+            if (f.audio > f.end) f.audio = f.end;
+            f.frame_base = 0; f.s_base = 0; f.pcm_base = 0; f.n_frames = 0; f.flags = 0; f.channels = 0; f.pad = 0;
+            if (f.end - f.begin > 0xFFFFFFFFLL) return m3s_fail(h, M3S_ERR_ARG, "decode: file %d exceeds 4 GiB", i);
+            f.tmp_base = tb;
+            tb += (f.end - f.audio) / 96 + 2;   // the walk's temporary position array is sized by the smallest legal frame (96 bytes)
+            if (hint) est += frames_by_first_header(hint + f.audio, f.end - f.audio);
+            else est += (int64_t)((double)(f.end - f.audio) / (h->dec_bpf_guess > 0 ? h->dec_bpf_guess : 417.0)) + 2;
+        }
+        if ((rc = reserve_quiet(h, ss.files, sizeof(M3sFileRec) * n_files))) return rc;
+        if ((rc = reserve_quiet(h, ss.fouts, sizeof(M3sFileOut) * n_files))) return rc;
+        if ((rc = reserve_quiet(h, ss.layout, sizeof(M3sLayout)))) return rc;
+        if ((rc = reserve_quiet(h, ss.tmp_pos, sizeof(uint32_t) * (size_t)(tb + 32)))) return rc;
+        if ((rc = scan_reserve_frames(h, ss, est + 8))) return rc;
+        if ((size_t)n_files > ss.fouts_cap) {
+            if ((rc = sync_all_streams(h))) return rc;
+            if (ss.fouts_mapped) M3S_CUDA(h, cudaFreeHost(ss.fouts_mapped));
+            ss.fouts_mapped = nullptr;
+            ss.fouts_cap = 0;
+            const size_t cap = (size_t)n_files + 64;
+            M3S_CUDA(h, cudaHostAlloc((void **)&ss.fouts_mapped, sizeof(M3sFileOut) * cap + sizeof(M3sLayout), cudaHostAllocMapped));
+            M3S_CUDA(h, cudaHostGetDevicePointer((void **)&ss.fouts_mdev, ss.fouts_mapped, 0));
+            ss.lay_mapped = (M3sLayout *)(ss.fouts_mapped + cap);
+            ss.lay_mdev = (M3sLayout *)(ss.fouts_mdev + cap);
+            ss.fouts_cap = cap;
+        }
+        if ((rc = pin_reserve(h, ss.pin, ss.pin_cap, sizeof(M3sFileRec) * n_files))) return rc;
+        memcpy(ss.pin, ss.files_h.data(), sizeof(M3sFileRec) * n_files);
+        M3S_CUDA(h, cudaMemcpyAsync(ss.files.p, ss.pin, sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, s));
+        M3S_KBEGIN(h, M3S_K_WALK);
+        k_walk<<<wg, 32 * WALK_WARPS, 0, s>>>(ss.d_bytes, ss.total_bytes, (const M3sFileRec *)ss.files.p, (M3sFileOut *)ss.fouts.p,
+                                               n_files, (uint32_t *)ss.tmp_pos.p);
+        M3S_LAUNCH_CHECK(h);
+    }
+    M3S_KBEGIN(h, M3S_K_FSCAN);
+    k_layout<<<1, 256, 0, s>>>((M3sFileRec *)ss.files.p, (const M3sFileOut *)ss.fouts.p, n_files, ss.frames_cap, (M3sLayout *)ss.layout.p);
+    M3S_LAUNCH_CHECK(h);
+    M3S_KBEGIN(h, M3S_K_FSCAN);
+    k_fscan<<<wg, 32 * WALK_WARPS, 0, s>>>(ss.d_bytes, ss.total_bytes, (const M3sFileRec *)ss.files.p, (M3sFileOut *)ss.fouts.p, n_files,
+                                            (const uint32_t *)ss.tmp_pos.p, (int64_t *)ss.fr_pos.p, (uint32_t *)ss.fr_P.p,
+                                            (uint32_t *)ss.fr_meta.p, (uint32_t *)ss.fr_carry.p, (uint32_t *)ss.fr_reveal.p,
+                                            (int32_t *)ss.fr_file.p, (const M3sLayout *)ss.layout.p);
+    M3S_LAUNCH_CHECK(h);
+    M3S_KBEGIN(h, M3S_K_SIDEINFO);
+    k_sideinfo<<<(unsigned)((ss.frames_cap + 127) / 128), 128, 0, s>>>(
+        ss.d_bytes, (const M3sFileRec *)ss.files.p, (M3sLayout *)ss.layout.p, (const int64_t *)ss.fr_pos.p, (const uint32_t *)ss.fr_P.p,
+        (uint32_t *)ss.fr_meta.p, (const uint32_t *)ss.fr_carry.p, (const uint32_t *)ss.fr_reveal.p, (const int32_t *)ss.fr_file.p,
+        (M3sUnitRec *)ss.units.p, (uint8_t *)ss.tabids.p, (uint8_t *)ss.reveal.p, (uint32_t *)ss.irr.p);
+    M3S_LAUNCH_CHECK(h);
+    M3S_KBEGIN(h, M3S_K_SIDEINFO);
+    k_scan_publish<<<(n_files + 255) / 256, 256, 0, s>>>((const M3sFileOut *)ss.fouts.p, n_files, (const M3sLayout *)ss.layout.p,
+                                                          ss.fouts_mdev, ss.lay_mdev);
+    M3S_LAUNCH_CHECK(h);
+    return M3S_OK;
+}
+
+// After stream `s` has run the scan: read the results; when the per-frame arrays were too small (VBR files, a wrong guess) grow them
+// and run the per-frame part again (synchronously -- the rare slow path).
+static int scan_finish(m3s_ctx *h, M3sScanSet &ss, cudaStream_t s, const int64_t *file_off, const int64_t *audio_start)
+{
+    for (int attempt = 0;; attempt++) {
+        const M3sLayout lay = *ss.lay_mapped;
+        if (!lay.overflow) {
+            memcpy(ss.fouts_h.data(), ss.fouts_mapped, sizeof(M3sFileOut) * ss.n_files);
+            ss.total_frames = lay.total_frames;
+            ss.s_bytes = lay.s_bytes;
+            ss.irregular = lay.irregular;
+            break;
+        }
+        if (attempt > 0) return m3s_fail(h, M3S_ERR_STATE, "decode: scan overflow persists");
+        int rc = scan_reserve_frames(h, ss, lay.total_frames);
+        if (rc) return rc;
+        if ((rc = scan_enqueue(h, ss, s, ss.d_bytes, nullptr, file_off, audio_start, ss.n_files, true))) return rc;
+        M3S_CUDA(h, cudaStreamSynchronize(s));
+    }
+    int64_t fb = 0, sb = 0, audio_bytes = 0;
+    for (int i = 0; i < ss.n_files; i++) {   // the same layout k_layout computed on the device
+        M3sFileRec &f = ss.files_h[i];
+        const M3sFileOut &o = ss.fouts_h[i];
+        f.frame_base = fb;
+        f.n_frames = o.n_frames;
+        f.flags = o.status;
+        f.channels = o.channels;
+        fb += f.n_frames;
+        sb += M3S_APX_BYTES + 512;
+        f.s_base = sb;
+        sb += round_up(o.payload_total, 16) + 64;
+        audio_bytes += f.end - f.audio;
+    }
+    if (fb != ss.total_frames || sb + 64 != ss.s_bytes) return m3s_fail(h, M3S_ERR_STATE, "decode: host and device layouts disagree");
+    if (fb > 0) h->dec_bpf_guess = 0.97 * (double)audio_bytes / (double)fb;
+    return M3S_OK;
+}
+
+static int decode_events_init(m3s_ctx *h)
+{
+    int rc = m3s_pipeline_init(h);
+    if (rc) return rc;
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_d_h2d[i]) continue;
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_d_h2d[i], cudaEventDisableTiming));
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_d_scan[i], cudaEventDisableTiming));
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_d_comp[i], cudaEventDisableTiming));
+        M3S_CUDA(h, cudaEventCreateWithFlags(&h->ev_d_out[i], cudaEventDisableTiming));
+    }
+    return M3S_OK;
+}
+
 extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, const int64_t *file_off,
                                const int64_t *audio_start, int32_t n_files, int64_t *n_frames, int64_t *pcm_rows,
                                int32_t *sample_rate, int32_t *channels, int32_t *bitrate_bps, int32_t *status)
@@ -1100,110 +1532,29 @@ extern "C" int m3s_decode_scan(m3s_handle_t h, const uint8_t *bytes, int mem, co
     if (!bytes || !file_off || n_files <= 0) return m3s_fail(h, M3S_ERR_ARG, "decode_scan: bytes/file_off/n_files");
     M3S_CUDA(h, cudaSetDevice(h->device));
     double tr_t = g_trace ? now_ms() : 0.0;
-    const int64_t total_bytes = file_off[n_files];
     for (int i = 0; i < n_files; i++)
         if (file_off[i + 1] < file_off[i] || (audio_start && (audio_start[i] < 0)))
             return m3s_fail(h, M3S_ERR_ARG, "decode_scan: file_off must be non-decreasing, audio_start >= 0");
+    const int64_t total_bytes = file_off[n_files] - file_off[0];
+    M3sScanSet &ss = h->ss[0];
+    h->cur = &ss;
+    int rc;
+    const uint8_t *d_bytes = bytes + file_off[0];
     // ---- stage the bytes on the device when they are host memory
     if (mem == M3S_MEM_HOST) {
-        int rc = m3s_buf_reserve(h, h->b_stage_in, (size_t)total_bytes + 16);
-        if (rc) return rc;
-        if ((rc = m3s_copy_paced(h, h->b_stage_in.p, bytes, (size_t)total_bytes, cudaMemcpyHostToDevice))) return rc;
-        h->d_bytes = (const uint8_t *)h->b_stage_in.p;
-    } else
-        h->d_bytes = bytes;
+        if ((rc = m3s_buf_reserve(h, h->b_stage_in[0], (size_t)total_bytes + 16))) return rc;
+        if ((rc = m3s_copy_paced(h, h->b_stage_in[0].p, bytes + file_off[0], (size_t)total_bytes, cudaMemcpyHostToDevice))) return rc;
+        d_bytes = (const uint8_t *)h->b_stage_in[0].p;
+    }
     M3S_TRACE_MARK("scan.h2d_submitted");
-    h->n_files = n_files;
-    h->files.assign(n_files, M3sFileRec());
-    h->fouts.assign(n_files, M3sFileOut());
-    for (int i = 0; i < n_files; i++) {
-        M3sFileRec &f = h->files[i];
-        f.begin = file_off[i];
-        f.end = file_off[i + 1];
-        f.audio = file_off[i] + (audio_start ? audio_start[i] : 0);
-        if (f.audio > f.end) f.audio = f.end;
-        f.frame_base = 0; f.s_base = 0; f.pcm_base = 0; f.n_frames = 0; f.flags = 0; f.channels = 0; f.pad = 0; f.tmp_base = 0;
-    }
-    int rc;
-    if ((rc = m3s_buf_reserve(h, h->b_files, sizeof(M3sFileRec) * n_files))) return rc;
-    if ((size_t)n_files > h->fouts_cap) {
-        M3S_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (h->fouts_mapped) M3S_CUDA(h, cudaFreeHost(h->fouts_mapped));
-        h->fouts_mapped = nullptr;
-        h->fouts_cap = 0;
-        const size_t cap = (size_t)n_files + 64;
-        M3S_CUDA(h, cudaHostAlloc((void **)&h->fouts_mapped, sizeof(M3sFileOut) * cap, cudaHostAllocMapped));
-        M3S_CUDA(h, cudaHostGetDevicePointer((void **)&h->fouts_dev, h->fouts_mapped, 0));
-        h->fouts_cap = cap;
-    }
-    M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
-    // ---- walk: positions of every frame (file-relative) into a temporary array sized by the smallest legal frame (96 bytes)
-    {
-        int64_t tb = 0;
-        for (int i = 0; i < n_files; i++) {
-            h->files[i].tmp_base = tb;
-            tb += (h->files[i].end - h->files[i].audio) / 96 + 2;
-        }
-        if ((rc = m3s_buf_reserve(h, h->b_tmp_pos, sizeof(uint32_t) * (size_t)(tb + 32)))) return rc;
-        for (int i = 0; i < n_files; i++)
-            if (h->files[i].end - h->files[i].begin > 0xFFFFFFFFLL) return m3s_fail(h, M3S_ERR_ARG, "decode_scan: file %d exceeds 4 GiB", i);
-    }
-    M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
-    const int wg = (n_files + WALK_WARPS - 1) / WALK_WARPS;
-    M3S_KBEGIN(h, M3S_K_WALK);
-    k_walk<<<wg, 32 * WALK_WARPS, 0, h->stream>>>(h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, h->fouts_dev,
-                                                   n_files, (uint32_t *)h->b_tmp_pos.p);
-    M3S_LAUNCH_CHECK(h);
-    M3S_TRACE_MARK("scan.walk_launched");
+    if ((rc = scan_enqueue(h, ss, h->stream, d_bytes, mem == M3S_MEM_HOST ? bytes + file_off[0] : nullptr, file_off, audio_start, n_files)))
+        return rc;
+    M3S_TRACE_MARK("scan.launched");
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
-    memcpy(h->fouts.data(), h->fouts_mapped, sizeof(M3sFileOut) * n_files);
-    M3S_TRACE_MARK("scan.walk_synced");
-    int64_t fb = 0, sb = 0;
+    if ((rc = scan_finish(h, ss, h->stream, file_off, audio_start))) return rc;
+    M3S_TRACE_MARK("scan.synced");
     for (int i = 0; i < n_files; i++) {
-        M3sFileRec &f = h->files[i];
-        f.frame_base = fb;
-        f.n_frames = h->fouts[i].n_frames;
-        f.flags = h->fouts[i].status;
-        fb += f.n_frames;
-        sb += 512;  // zero pad in front: a main_data_begin that reaches before the first frame reads zeros
-        f.s_base = sb;
-        sb += round_up(h->fouts[i].payload_total, 16) + 64;
-    }
-    h->total_frames = fb;
-    h->s_bytes = sb + 64;
-    const int64_t nf = std::max<int64_t>(fb, 1);
-    if ((rc = m3s_buf_reserve(h, h->b_fr_pos, sizeof(int64_t) * nf))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_fr_P, sizeof(uint32_t) * nf))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_fr_meta, sizeof(uint32_t) * nf))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_fr_carry, sizeof(uint32_t) * nf))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_fr_reveal, sizeof(uint32_t) * nf))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_fr_file, sizeof(int32_t) * nf))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_units, sizeof(M3sUnitRec) * 4 * nf))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_tabids, 12 * nf))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_reveal, 12 * nf))) return rc;
-    M3S_CUDA(h, cudaMemcpyAsync(h->b_files.p, h->files.data(), sizeof(M3sFileRec) * n_files, cudaMemcpyHostToDevice, h->stream));
-    M3S_KBEGIN(h, M3S_K_FSCAN);
-    k_fscan<<<wg, 32 * WALK_WARPS, 0, h->stream>>>(h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, h->fouts_dev,
-                                                    n_files, (const uint32_t *)h->b_tmp_pos.p, (int64_t *)h->b_fr_pos.p,
-                                                    (uint32_t *)h->b_fr_P.p, (uint32_t *)h->b_fr_meta.p, (uint32_t *)h->b_fr_carry.p,
-                                                    (uint32_t *)h->b_fr_reveal.p, (int32_t *)h->b_fr_file.p);
-    M3S_LAUNCH_CHECK(h);
-    if (fb > 0) {
-        M3S_KBEGIN(h, M3S_K_SIDEINFO);
-        k_sideinfo<<<(unsigned)((fb + 127) / 128), 128, 0, h->stream>>>(
-            h->d_bytes, (const M3sFileRec *)h->b_files.p, fb, (const int64_t *)h->b_fr_pos.p, (const uint32_t *)h->b_fr_P.p,
-            (const uint32_t *)h->b_fr_meta.p, (const uint32_t *)h->b_fr_carry.p, (const uint32_t *)h->b_fr_reveal.p,
-            (const int32_t *)h->b_fr_file.p, (M3sUnitRec *)h->b_units.p, (uint8_t *)h->b_tabids.p, (uint8_t *)h->b_reveal.p);
-        M3S_LAUNCH_CHECK(h);
-    }
-    M3S_TRACE_MARK("scan.fscan_launched");
-    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
-    memcpy(h->fouts.data(), h->fouts_mapped, sizeof(M3sFileOut) * n_files);
-    M3S_TRACE_MARK("scan.fscan_synced");
-    for (int i = 0; i < n_files; i++) {
-        const M3sFileOut &o = h->fouts[i];
-        h->files[i].flags = o.status;
-        h->files[i].channels = o.channels;
+        const M3sFileOut &o = ss.fouts_h[i];
         if (n_frames) n_frames[i] = o.n_frames;
         if (pcm_rows) pcm_rows[i] = 1152LL * (o.n_frames + ((o.status & M3S_FILE_TRAILING_JUNK) && o.n_frames > 0 ? 1 : 0));
         if (sample_rate) sample_rate[i] = o.sample_rate;
@@ -1231,13 +1582,14 @@ extern "C" int m3s_decode_reveal(m3s_handle_t h, uint8_t *table_ids, uint8_t *re
     if (!h) return M3S_ERR_ARG;
     if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_reveal: call m3s_decode_scan first");
     M3S_CUDA(h, cudaSetDevice(h->device));
+    M3sScanSet &ss = *h->cur;
     if (reveal_len)
-        for (int i = 0; i < h->n_files; i++) reveal_len[i] = h->fouts[i].reveal_len;
-    const size_t nb = (size_t)12 * (size_t)h->total_frames;   // bytes of each output (a multiple of 4)
+        for (int i = 0; i < ss.n_files; i++) reveal_len[i] = ss.fouts_h[i].reveal_len;
+    const size_t nb = (size_t)12 * (size_t)ss.total_frames;   // bytes of each output (a multiple of 4)
     if (nb == 0 || (!table_ids && !reveal_bits)) return M3S_OK;
     if (mem != M3S_MEM_HOST) {
-        if (table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids, h->b_tabids.p, nb, cudaMemcpyDeviceToDevice, h->stream));
-        if (reveal_bits) M3S_CUDA(h, cudaMemcpyAsync(reveal_bits, h->b_reveal.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+        if (table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids, ss.tabids.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+        if (reveal_bits) M3S_CUDA(h, cudaMemcpyAsync(reveal_bits, ss.reveal.p, nb, cudaMemcpyDeviceToDevice, h->stream));
         M3S_CUDA(h, cudaStreamSynchronize(h->stream));
         return M3S_OK;
     }
@@ -1253,7 +1605,7 @@ extern "C" int m3s_decode_reveal(m3s_handle_t h, uint8_t *table_ids, uint8_t *re
     }
     const int64_t nw = (int64_t)(nb / 4);
     M3S_KBEGIN(h, M3S_K_SIDEINFO);
-    k_words_out<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)h->b_tabids.p, (const uint32_t *)h->b_reveal.p, nw,
+    k_words_out<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)ss.tabids.p, (const uint32_t *)ss.reveal.p, nw,
                                                                        table_ids ? (uint32_t *)h->rev_dev : nullptr,
                                                                        reveal_bits ? (uint32_t *)(h->rev_dev + nb) : nullptr);
     M3S_LAUNCH_CHECK(h);
@@ -1268,12 +1620,13 @@ extern "C" int m3s_decode_frame_pos(m3s_handle_t h, int64_t *frame_pos)
     if (!h) return M3S_ERR_ARG;
     if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_frame_pos: call m3s_decode_scan first");
     if (!frame_pos) return m3s_fail(h, M3S_ERR_ARG, "decode_frame_pos: null output");
-    if (h->total_frames == 0) return M3S_OK;
+    M3sScanSet &ss = *h->cur;
+    if (ss.total_frames == 0) return M3S_OK;
     M3S_CUDA(h, cudaSetDevice(h->device));
-    M3S_CUDA(h, cudaMemcpyAsync(frame_pos, h->b_fr_pos.p, sizeof(int64_t) * (size_t)h->total_frames, cudaMemcpyDeviceToHost, h->stream));
+    M3S_CUDA(h, cudaMemcpyAsync(frame_pos, ss.fr_pos.p, sizeof(int64_t) * (size_t)ss.total_frames, cudaMemcpyDeviceToHost, h->stream));
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < h->n_files; i++)   // absolute batch positions -> file-relative
-        for (int64_t g = h->files[i].frame_base; g < h->files[i].frame_base + h->files[i].n_frames; g++) frame_pos[g] -= h->files[i].begin;
+    for (int i = 0; i < ss.n_files; i++)   // wave positions -> file-relative
+        for (int64_t g = ss.files_h[i].frame_base; g < ss.files_h[i].frame_base + ss.files_h[i].n_frames; g++) frame_pos[g] -= ss.files_h[i].begin;
     return M3S_OK;
 }
 
@@ -1285,73 +1638,86 @@ static int hybrid_run_length(int64_t total_frames, int sm_count)
     return (int)std::max<int64_t>(16, std::min<int64_t>(128, want));
 }
 
-extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t *pcm_off, int16_t *spectra, uint32_t flags)
+// Queue D1-D3 of a scanned wave on the handle's compute stream: main-data compaction (+ irregular reservoirs), Huffman decode,
+// hybrid synthesis into d_pcm.  files_h[].pcm_base must hold each file's element offset inside d_pcm.
+static int run_enqueue(m3s_ctx *h, M3sScanSet &ss, void *d_pcm, int16_t *d_spectra, uint32_t flags, int wb, int range_file = -1,
+                       int64_t range_first = 0, int64_t range_count = 0)
 {
-    if (!h) return M3S_ERR_ARG;
-    if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_run: call m3s_decode_scan first");
-    if (!pcm) return m3s_fail(h, M3S_ERR_ARG, "decode_run: pcm is NULL");
-    M3S_CUDA(h, cudaSetDevice(h->device));
-    const int64_t nf = h->total_frames;
+    std::vector<M3sWork> &work = h->work_h[wb];
+    const int64_t nf = ss.total_frames;
     if (nf == 0) return M3S_OK;
-    double tr_t = g_trace ? now_ms() : 0.0;
+    // frames [g_lo, g_hi) go through Huffman decode + synthesis; [s_lo, g_hi) through the main-data compaction
+    int64_t g_lo = 0, g_hi = nf, s_lo = 0;
     const bool fl = (flags & M3S_DEC_PCM_FLOAT) != 0;
-    const size_t esz = fl ? 4 : 2;
     int rc;
-    // ---- PCM layout
-    int64_t total_elems = 0;
-    std::vector<M3sWork> work;
-    const int run = hybrid_run_length(nf, h->sm_count);
-    for (int i = 0; i < h->n_files; i++) {
-        M3sFileRec &f = h->files[i];
-        const int64_t rows = 1152LL * (f.n_frames + ((f.flags & M3S_FILE_TRAILING_JUNK) && f.n_frames > 0 ? 1 : 0));
-        const int64_t elems = rows * std::max(f.channels, 1);
-        f.pcm_base = pcm_off ? pcm_off[i] : total_elems;
-        if (f.channels == 2 && !fl && (f.pcm_base & 1)) return m3s_fail(h, M3S_ERR_ARG, "decode_run: stereo pcm_off must be even");
-        total_elems = std::max(total_elems, f.pcm_base + elems);
-        for (int64_t k = 0; k < f.n_frames; k += run) {
+    cudaStream_t s = h->stream;
+    work.clear();
+    if (range_file >= 0) {
+        // one file's frames [first, first + count): the frame in front is the warm-up frame (its PCM is dropped; overlap-add tail and
+        // the 15 V vectors of the synthesis fifo, Frame.py:81-92,150-153), and its main data may reach 511 bytes = at most 9 frames
+        // back (Frame.py:306-309); a file whose granules inherit scalefactors from arbitrarily old frames needs its whole prefix in S
+        const M3sFileRec &f = ss.files_h[range_file];
+        const int run = hybrid_run_length(range_count, h->sm_count);
+        g_lo = f.frame_base + std::max<int64_t>(range_first - 1, 0);
+        g_hi = f.frame_base + range_first + range_count;
+        s_lo = (f.flags & M3S_FILE_STATE_CARRY) ? f.frame_base : std::max<int64_t>(g_lo - 9, f.frame_base);
+        for (int64_t k = range_first; k < range_first + range_count; k += run) {
             M3sWork w;
             w.g_first = f.frame_base + k;
-            w.count = (int32_t)std::min<int64_t>(run, f.n_frames - k);
+            w.count = (int32_t)std::min<int64_t>(run, range_first + range_count - k);
             w.warm = k > 0 ? 1 : 0;
-            w.pcm_elem = f.pcm_base + k * 1152 * f.channels;
+            w.pcm_elem = (k - range_first) * 1152 * f.channels;
             w.channels = f.channels;
             w.pad = 0;
             work.push_back(w);
         }
-    }
-    // ---- workspaces
-    if ((rc = m3s_buf_reserve(h, h->b_S, (size_t)h->s_bytes))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_spec, (size_t)nf * 288 * 4 * 4))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_sf, (size_t)nf * 4 * M3S_SF_STRIDE))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->b_work, sizeof(M3sWork) * work.size()))) return rc;
-    void *d_pcm = pcm;
-    if (mem == M3S_MEM_HOST) {
-        if ((rc = m3s_buf_reserve(h, h->b_pcm_stage, (size_t)total_elems * esz))) return rc;
-        d_pcm = h->b_pcm_stage.p;
-    }
-    M3S_CUDA(h, cudaMemcpyAsync(h->b_work.p, work.data(), sizeof(M3sWork) * work.size(), cudaMemcpyHostToDevice, h->stream));
-    M3S_CUDA(h, cudaMemsetAsync(h->b_S.p, 0, (size_t)h->s_bytes, h->stream));
-    int64_t total_bytes = h->files[h->n_files - 1].end;
-    M3S_KBEGIN(h, M3S_K_STRIP);
-        k_strip<<<(unsigned)((nf * 32 + 255) / 256), 256, 0, h->stream>>>(
-        h->d_bytes, total_bytes, (const M3sFileRec *)h->b_files.p, nf, (const int64_t *)h->b_fr_pos.p,
-        (const uint32_t *)h->b_fr_P.p, (const uint32_t *)h->b_fr_meta.p, (const int32_t *)h->b_fr_file.p, (uint8_t *)h->b_S.p);
-    M3S_LAUNCH_CHECK(h);
-    M3S_KBEGIN(h, M3S_K_HUFF);
-        k_huff<<<(unsigned)((4 * nf + HUFF_THREADS - 1) / HUFF_THREADS), HUFF_THREADS, 0, h->stream>>>(
-        (const uint8_t *)h->b_S.p, (const M3sUnitRec *)h->b_units.p, 4 * nf, h->d_tab, (uint32_t *)h->b_spec.p, (uint8_t *)h->b_sf.p);
-    M3S_LAUNCH_CHECK(h);
-    if (spectra) {
-        int16_t *d_sp = spectra;
-        if (mem == M3S_MEM_HOST) {
-            if ((rc = m3s_buf_reserve(h, h->b_spec_export, (size_t)nf * 4 * 576 * 2))) return rc;
-            d_sp = (int16_t *)h->b_spec_export.p;
+    } else {
+        const int run = hybrid_run_length(nf, h->sm_count);
+        for (int i = 0; i < ss.n_files; i++) {
+            const M3sFileRec &f = ss.files_h[i];
+            for (int64_t k = 0; k < f.n_frames; k += run) {
+                M3sWork w;
+                w.g_first = f.frame_base + k;
+                w.count = (int32_t)std::min<int64_t>(run, f.n_frames - k);
+                w.warm = k > 0 ? 1 : 0;
+                w.pcm_elem = f.pcm_base + k * 1152 * f.channels;
+                w.channels = f.channels;
+                w.pad = 0;
+                work.push_back(w);
+            }
         }
-        M3S_KBEGIN(h, M3S_K_SPEC_EXPORT);
-        k_spec_export<<<(unsigned)((nf * 288 * 4 + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)h->b_spec.p, nf, d_sp);
+    }
+    if (work.empty()) return M3S_OK;
+    const int64_t s_total = ss.s_bytes + ss.irregular * M3S_APX_SLOT_BYTES;
+    if ((rc = reserve_quiet(h, h->b_S, (size_t)s_total))) return rc;
+    if ((rc = reserve_quiet(h, h->b_spec, (size_t)nf * 288 * 4 * 4))) return rc;
+    if ((rc = reserve_quiet(h, h->b_sf, (size_t)nf * 4 * M3S_SF_STRIDE))) return rc;
+    if ((rc = reserve_quiet(h, h->b_work, sizeof(M3sWork) * work.size()))) return rc;
+    if ((rc = pin_reserve(h, h->work_pin[wb], h->work_pin_cap[wb], sizeof(M3sWork) * work.size()))) return rc;
+    memcpy(h->work_pin[wb], work.data(), sizeof(M3sWork) * work.size());
+    M3S_CUDA(h, cudaMemcpyAsync(h->b_work.p, h->work_pin[wb], sizeof(M3sWork) * work.size(), cudaMemcpyHostToDevice, s));
+    M3S_CUDA(h, cudaMemsetAsync(h->b_S.p, 0, (size_t)s_total, s));
+    M3S_KBEGIN(h, M3S_K_STRIP);
+    k_strip<<<(unsigned)(((g_hi - s_lo) * 32 + 255) / 256), 256, 0, s>>>(
+        ss.d_bytes, ss.total_bytes, (const M3sFileRec *)ss.files.p, s_lo, g_hi, (const int64_t *)ss.fr_pos.p,
+        (const uint32_t *)ss.fr_P.p, (const uint32_t *)ss.fr_meta.p, (const int32_t *)ss.fr_file.p, (uint8_t *)h->b_S.p);
+    M3S_LAUNCH_CHECK(h);
+    {   // irregular reservoirs: candidates are the first nine frames of every file + the listed frames (a no-op launch for clean input)
+        const int64_t warps = (int64_t)ss.n_files * M3S_APX_SLOTS + ss.irregular;
+        M3S_KBEGIN(h, M3S_K_STRIP);
+        k_reservoir_fix<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(
+            ss.d_bytes, (const M3sFileRec *)ss.files.p, ss.n_files, (const int64_t *)ss.fr_pos.p, (const uint32_t *)ss.fr_meta.p,
+            (const int32_t *)ss.fr_file.p, (const uint32_t *)ss.irr.p, ss.irregular, ss.s_bytes, (uint8_t *)h->b_S.p);
         M3S_LAUNCH_CHECK(h);
-        if (mem == M3S_MEM_HOST)
-            M3S_CUDA(h, m3s_copy_bulk(spectra, d_sp, (size_t)nf * 4 * 576 * 2, cudaMemcpyDeviceToHost, h->stream));
+    }
+    M3S_KBEGIN(h, M3S_K_HUFF);
+    k_huff<<<(unsigned)((4 * (g_hi - g_lo) + HUFF_THREADS - 1) / HUFF_THREADS), HUFF_THREADS, 0, s>>>(
+        (const uint8_t *)h->b_S.p, (const M3sUnitRec *)ss.units.p, 4 * g_lo, 4 * g_hi, h->d_tab, (uint32_t *)h->b_spec.p, (uint8_t *)h->b_sf.p);
+    M3S_LAUNCH_CHECK(h);
+    if (d_spectra) {
+        M3S_KBEGIN(h, M3S_K_SPEC_EXPORT);
+        k_spec_export<<<(unsigned)((nf * 288 * 4 + 255) / 256), 256, 0, s>>>((const uint32_t *)h->b_spec.p, nf, d_spectra);
+        M3S_LAUNCH_CHECK(h);
     }
     const bool exact = (flags & M3S_DEC_EXACT) != 0;
 #define M3S_LAUNCH_HYBRID(R, TAB, FL, tabptr)                                                                              \
@@ -1359,9 +1725,9 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
         const size_t smem = sizeof(HybSmem<R>);                                                                            \
         M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid<R, TAB, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         M3S_KBEGIN(h, M3S_K_HYBRID);                                                                                       \
-        k_hybrid<R, TAB, FL><<<(unsigned)work.size(), HYB_THREADS, smem, h->stream>>>(                                     \
-            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)h->b_units.p, (const uint8_t *)h->b_sf.p,                   \
-            (const uint32_t *)h->b_fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, (tabptr), d_pcm);                    \
+        k_hybrid<R, TAB, FL><<<(unsigned)work.size(), HYB_THREADS, smem, s>>>(                                             \
+            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)ss.units.p, (const uint8_t *)h->b_sf.p,                     \
+            (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, (tabptr), d_pcm);                      \
     } while (0)
     if (exact) {
         if (fl) M3S_LAUNCH_HYBRID(double, M3sDevTablesD, true, h->d_tab_f64);
@@ -1371,11 +1737,253 @@ extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t 
         else M3S_LAUNCH_HYBRID(float, M3sDevTables, false, h->d_tab);
     }
     M3S_LAUNCH_CHECK(h);
+    return M3S_OK;
+}
+
+static inline int64_t file_pcm_elems(const M3sFileRec &f)
+{
+    const int64_t rows = 1152LL * (f.n_frames + ((f.flags & M3S_FILE_TRAILING_JUNK) && f.n_frames > 0 ? 1 : 0));
+    return rows * std::max(f.channels, 1);
+}
+
+extern "C" int m3s_decode_run(m3s_handle_t h, void *pcm, int mem, const int64_t *pcm_off, int16_t *spectra, uint32_t flags)
+{
+    if (!h) return M3S_ERR_ARG;
+    if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_run: call m3s_decode_scan first");
+    if (!pcm) return m3s_fail(h, M3S_ERR_ARG, "decode_run: pcm is NULL");
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    M3sScanSet &ss = *h->cur;
+    const int64_t nf = ss.total_frames;
+    if (nf == 0) return M3S_OK;
+    double tr_t = g_trace ? now_ms() : 0.0;
+    const bool fl = (flags & M3S_DEC_PCM_FLOAT) != 0;
+    const size_t esz = fl ? 4 : 2;
+    int rc;
+    // ---- PCM layout: the caller's offsets, or back to back
+    int64_t total_elems = 0;
+    std::vector<int64_t> user_base(ss.n_files);
+    for (int i = 0; i < ss.n_files; i++) {
+        M3sFileRec &f = ss.files_h[i];
+        const int64_t elems = file_pcm_elems(f);
+        user_base[i] = pcm_off ? pcm_off[i] : total_elems;
+        if (f.channels == 2 && !fl && (user_base[i] & 1)) return m3s_fail(h, M3S_ERR_ARG, "decode_run: stereo pcm_off must be even");
+        // host buffers are staged back to back on the device and copied out file by file (gaps the caller left stay untouched)
+        f.pcm_base = mem == M3S_MEM_HOST ? total_elems + (total_elems & 1) : user_base[i];
+        if (mem == M3S_MEM_HOST) total_elems = f.pcm_base + elems;
+        else total_elems = std::max(total_elems, f.pcm_base + elems);
+    }
+    void *d_pcm = pcm;
+    if (mem == M3S_MEM_HOST) {
+        if ((rc = m3s_buf_reserve(h, h->b_pcm_stage[0], (size_t)total_elems * esz + 16))) return rc;
+        d_pcm = h->b_pcm_stage[0].p;
+    }
+    int16_t *d_sp = spectra;
+    if (spectra && mem == M3S_MEM_HOST) {
+        if ((rc = m3s_buf_reserve(h, h->b_spec_export, (size_t)nf * 4 * 576 * 2))) return rc;
+        d_sp = (int16_t *)h->b_spec_export.p;
+    }
+    if ((rc = run_enqueue(h, ss, d_pcm, d_sp, flags, 0))) return rc;
+    if (spectra && mem == M3S_MEM_HOST)
+        M3S_CUDA(h, m3s_copy_bulk(spectra, d_sp, (size_t)nf * 4 * 576 * 2, cudaMemcpyDeviceToHost, h->stream));
     M3S_TRACE_MARK("run.launched");
     if (g_trace) { cudaStreamSynchronize(h->stream); M3S_TRACE_MARK("run.kernels_done"); }
-    if (mem == M3S_MEM_HOST)
-        if ((rc = m3s_copy_paced(h, pcm, d_pcm, (size_t)total_elems * esz, cudaMemcpyDeviceToHost))) return rc;
+    if (mem == M3S_MEM_HOST) {
+        bool dense = true;   // one paced transfer when the caller's layout is the staging layout
+        for (int i = 0; i < ss.n_files; i++) dense = dense && user_base[i] == ss.files_h[i].pcm_base;
+        if (dense) {
+            if ((rc = m3s_copy_paced(h, pcm, d_pcm, (size_t)total_elems * esz, cudaMemcpyDeviceToHost))) return rc;
+        } else {
+            std::vector<M3sRow> rows;
+            for (int i = 0; i < ss.n_files; i++) {
+                const M3sFileRec &f = ss.files_h[i];
+                rows.push_back(M3sRow{(char *)pcm + user_base[i] * esz, (const char *)d_pcm + f.pcm_base * esz, (size_t)file_pcm_elems(f) * esz});
+            }
+            M3S_CUDA(h, m3s_copy_rows(rows, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     M3S_TRACE_MARK("run.d2h_done");
+    return M3S_OK;
+}
+
+// ================================================================================================
+// m3s_decode: the whole of MP3Parser.parse_file + write_to_wav's conversion (MP3_Parser.py:57-91) for a batch, as ONE call that
+// pipelines itself.  The files are cut into waves; four streams keep both PCIe directions and the SMs busy at once:
+//
+//      copy_in   MP3 bytes of wave k+1            (host buffers only)
+//      aux       scan of wave k+1                 (walk, layout, per-file scans, side info + reveal: latency-bound, tiny)
+//      stream    compaction, Huffman, hybrid of wave k
+//      copy_out  PCM + table ids + reveal chars of wave k-1   (host buffers only)
+//
+// The host waits once per wave, for the scan of the NEXT wave, while the current wave's kernels are already queued; there is no
+// other synchronisation until the end of the call.
+// ================================================================================================
+extern "C" int64_t m3s_decode_bound(const uint8_t *bytes_host, const int64_t *file_off, const int64_t *audio_start, int32_t n_files,
+                                    int64_t *frames_bound)
+{
+    if (!bytes_host || !file_off || n_files <= 0) return -1;
+    int64_t frames = 0;
+    for (int i = 0; i < n_files; i++) {
+        int64_t a = file_off[i] + (audio_start ? audio_start[i] : 0);
+        if (a > file_off[i + 1]) a = file_off[i + 1];
+        frames += frames_by_first_header(bytes_host + a, file_off[i + 1] - a);
+    }
+    if (frames_bound) *frames_bound = frames;
+    return frames * 1152 * 2;
+}
+
+extern "C" int m3s_decode(m3s_handle_t h, const uint8_t *bytes, int mem, const int64_t *file_off, const int64_t *audio_start,
+                          int32_t n_files, void *pcm, int64_t pcm_capacity, int64_t *pcm_off, uint8_t *table_ids, uint8_t *reveal_bits,
+                          int64_t frames_capacity, int64_t *reveal_len, int64_t *n_frames, int32_t *sample_rate, int32_t *channels,
+                          int32_t *bitrate_bps, int32_t *status, uint32_t flags)
+{
+    if (!h) return M3S_ERR_ARG;
+    h->scanned = false;
+    if (!bytes || !file_off || n_files <= 0 || !pcm) return m3s_fail(h, M3S_ERR_ARG, "decode: bytes/file_off/n_files/pcm");
+    for (int i = 0; i < n_files; i++)
+        if (file_off[i + 1] < file_off[i] || (audio_start && (audio_start[i] < 0)))
+            return m3s_fail(h, M3S_ERR_ARG, "decode: file_off must be non-decreasing, audio_start >= 0");
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = decode_events_init(h))) return rc;
+    const bool host = mem == M3S_MEM_HOST;
+    const bool fl = (flags & M3S_DEC_PCM_FLOAT) != 0;
+    const size_t esz = fl ? 4 : 2;
+    // ---- waves of whole files
+    const int64_t wave_bytes = h->dec_wave_bytes > 0 ? h->dec_wave_bytes : ((int64_t)256 << 20);
+    std::vector<int> wave_first;
+    for (int i = 0; i < n_files;) {
+        wave_first.push_back(i);
+        int64_t acc = 0;
+        do { acc += file_off[i + 1] - file_off[i]; i++; } while (i < n_files && acc + (file_off[i + 1] - file_off[i]) <= wave_bytes);
+    }
+    const int W = (int)wave_first.size();
+    wave_first.push_back(n_files);
+    int64_t frames_before = 0, elems_before = 0;
+    int err = M3S_OK;
+    for (int k = 0; k <= W && err == M3S_OK; k++) {
+        // ------------------------------------------------------------ A(k): bytes of wave k up, scan of wave k
+        if (k < W) {
+            const int b = k & 1, f0 = wave_first[k], nfl = wave_first[k + 1] - f0;
+            M3sScanSet &ss = h->ss[b];
+            const int64_t nbytes = file_off[f0 + nfl] - file_off[f0];
+            const uint8_t *d_bytes = bytes + file_off[f0];
+            if (host) {
+                if ((err = reserve_quiet(h, h->b_stage_in[b], (size_t)nbytes + 16))) break;
+                d_bytes = (const uint8_t *)h->b_stage_in[b].p;
+            }
+            if (k >= 2) {   // set b's previous wave (k - 2) must be through the kernels (they read its bytes and records) and copied out
+                M3S_CUDA(h, cudaStreamWaitEvent(h->copy_in, h->ev_d_comp[b], 0));
+                M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_d_comp[b], 0));
+                if (host) M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_d_out[b], 0));
+            }
+            if (host) {
+                M3S_CUDA(h, m3s_copy_bulk((void *)d_bytes, bytes + file_off[f0], (size_t)nbytes, cudaMemcpyHostToDevice, h->copy_in));
+                M3S_CUDA(h, cudaEventRecord(h->ev_d_h2d[b], h->copy_in));
+                M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_d_h2d[b], 0));
+            }
+            if ((err = scan_enqueue(h, ss, h->aux, d_bytes, host ? bytes + file_off[f0] : nullptr, file_off + f0,
+                                    audio_start ? audio_start + f0 : nullptr, nfl)))
+                break;
+            M3S_CUDA(h, cudaEventRecord(h->ev_d_scan[b], h->aux));
+        }
+        // ------------------------------------------------------------ B(k - 1): kernels of wave k - 1, results home
+        if (k >= 1) {
+            const int j = k - 1, b = j & 1, f0 = wave_first[j];
+            M3sScanSet &ss = h->ss[b];
+            M3S_CUDA(h, cudaEventSynchronize(h->ev_d_scan[b]));
+            if ((err = scan_finish(h, ss, h->aux, file_off + f0, audio_start ? audio_start + f0 : nullptr))) break;
+            int64_t wave_elems = 0;
+            for (int i = 0; i < ss.n_files; i++) {
+                M3sFileRec &f = ss.files_h[i];
+                const M3sFileOut &o = ss.fouts_h[i];
+                const int64_t elems = file_pcm_elems(f);
+                f.pcm_base = (host ? 0 : elems_before) + wave_elems;
+                if (pcm_off) pcm_off[f0 + i] = elems_before + wave_elems;
+                wave_elems += elems;
+                if (n_frames) n_frames[f0 + i] = o.n_frames;
+                if (sample_rate) sample_rate[f0 + i] = o.sample_rate;
+                if (channels) channels[f0 + i] = o.channels;
+                if (bitrate_bps) bitrate_bps[f0 + i] = o.bitrate;
+                if (status) status[f0 + i] = o.status;
+                if (reveal_len) reveal_len[f0 + i] = o.reveal_len;
+            }
+            if (elems_before + wave_elems > pcm_capacity) {
+                err = m3s_fail(h, M3S_ERR_CAPACITY, "decode: pcm holds %lld elements, files up to %d need %lld", (long long)pcm_capacity,
+                               f0 + ss.n_files - 1, (long long)(elems_before + wave_elems));
+                break;
+            }
+            if ((table_ids || reveal_bits) && frames_before + ss.total_frames > frames_capacity) {
+                err = m3s_fail(h, M3S_ERR_CAPACITY, "decode: table_ids / reveal_bits hold %lld frames, files up to %d need %lld",
+                               (long long)frames_capacity, f0 + ss.n_files - 1, (long long)(frames_before + ss.total_frames));
+                break;
+            }
+            void *d_pcm = pcm;
+            if (host) {
+                if ((err = reserve_quiet(h, h->b_pcm_stage[b], (size_t)wave_elems * esz + 16))) break;
+                d_pcm = h->b_pcm_stage[b].p;
+                if (j >= 2) M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_d_out[b], 0));   // the staging buffer's previous wave is home
+            }
+            M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_d_scan[b], 0));
+            if ((err = run_enqueue(h, ss, d_pcm, nullptr, flags, b))) break;
+            const size_t nb = (size_t)12 * (size_t)ss.total_frames;
+            if (!host && nb) {
+                if (table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids + 12 * frames_before, ss.tabids.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+                if (reveal_bits) M3S_CUDA(h, cudaMemcpyAsync(reveal_bits + 12 * frames_before, ss.reveal.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+            }
+            M3S_CUDA(h, cudaEventRecord(h->ev_d_comp[b], h->stream));
+            if (host) {
+                // the reveal outputs only need the scan; they go first so that they never wait behind the PCM
+                if (nb && table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids + 12 * frames_before, ss.tabids.p, nb, cudaMemcpyDeviceToHost, h->copy_out));
+                if (nb && reveal_bits) M3S_CUDA(h, cudaMemcpyAsync(reveal_bits + 12 * frames_before, ss.reveal.p, nb, cudaMemcpyDeviceToHost, h->copy_out));
+                M3S_CUDA(h, cudaStreamWaitEvent(h->copy_out, h->ev_d_comp[b], 0));
+                if (wave_elems)
+                    M3S_CUDA(h, m3s_copy_bulk((char *)pcm + elems_before * esz, d_pcm, (size_t)wave_elems * esz, cudaMemcpyDeviceToHost, h->copy_out));
+                M3S_CUDA(h, cudaEventRecord(h->ev_d_out[b], h->copy_out));
+            }
+            frames_before += ss.total_frames;
+            elems_before += wave_elems;
+        }
+    }
+    if (err == M3S_OK && pcm_off) pcm_off[n_files] = elems_before;
+    const std::string keep = h->err;
+    const int rc2 = sync_all_streams(h);
+    if (err != M3S_OK) { h->err = keep; return err; }
+    return rc2;
+}
+
+
+// Frame-range decode of ONE file of the last scan (a long file split across GPUs).  Every rank scans the whole file
+// (the reference never resynchronises: frame positions, bit-reservoir cursors, reveal bits and the carried table ids come from there),
+// then runs Huffman decode + synthesis only on frames [first, first + count) plus ONE warm-up frame in front, and compacts the main
+// data of at most 9 more frames for that frame's bit reservoir -- all cut from the bytes already on the device.
+extern "C" int m3s_decode_run_range(m3s_handle_t h, int32_t file_index, int64_t first_frame, int64_t frame_count, void *pcm, int mem,
+                                    int64_t *rows_out, uint32_t flags)
+{
+    if (!h) return M3S_ERR_ARG;
+    if (!h->scanned) return m3s_fail(h, M3S_ERR_STATE, "decode_run_range: call m3s_decode_scan first");
+    M3sScanSet &ss = *h->cur;
+    if (file_index < 0 || file_index >= ss.n_files) return m3s_fail(h, M3S_ERR_ARG, "decode_run_range: file_index");
+    const M3sFileRec &f = ss.files_h[file_index];
+    if (first_frame < 0 || frame_count < 0 || first_frame + frame_count > f.n_frames) return m3s_fail(h, M3S_ERR_ARG, "decode_run_range: frame range");
+    if (!pcm && frame_count) return m3s_fail(h, M3S_ERR_ARG, "decode_run_range: pcm is NULL");
+    M3S_CUDA(h, cudaSetDevice(h->device));
+    const bool fl = (flags & M3S_DEC_PCM_FLOAT) != 0;
+    const size_t esz = fl ? 4 : 2;
+    const bool last = first_frame + frame_count == f.n_frames;
+    const int64_t rows = 1152LL * (frame_count + (last && frame_count > 0 && (f.flags & M3S_FILE_TRAILING_JUNK) ? 1 : 0));
+    if (rows_out) *rows_out = rows;
+    if (frame_count == 0) return M3S_OK;
+    const int64_t elems = rows * std::max(f.channels, 1);
+    int rc;
+    void *d_pcm = pcm;
+    if (mem == M3S_MEM_HOST) {
+        if ((rc = m3s_buf_reserve(h, h->b_pcm_stage[0], (size_t)elems * esz + 16))) return rc;
+        d_pcm = h->b_pcm_stage[0].p;
+    }
+    if ((rc = run_enqueue(h, ss, d_pcm, nullptr, flags, 0, file_index, first_frame, frame_count))) return rc;
+    if (mem == M3S_MEM_HOST)
+        if ((rc = m3s_copy_paced(h, pcm, d_pcm, (size_t)elems * esz, cudaMemcpyDeviceToHost))) return rc;
+    M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     return M3S_OK;
 }

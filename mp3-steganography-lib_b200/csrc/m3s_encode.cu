@@ -1790,10 +1790,29 @@ static void build_enc_tables(const M3sDevTables *T, EncTables *E)
     }
 }
 
+static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_t *pcm_off, const int64_t *n_samples,
+                       int32_t n_clips, int32_t sample_rate, int32_t bitrate_kbps, const uint8_t *payload_bits,
+                       const int64_t *payload_off, uint8_t *mp3_out, const int64_t *mp3_off, const int64_t *mp3_cap,
+                       int64_t *out_len, int64_t *hide_str_offset_out);
+
 extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int64_t *pcm_off, const int64_t *n_samples,
                           int32_t n_clips, int32_t sample_rate, int32_t bitrate_kbps, const uint8_t *payload_bits,
                           const int64_t *payload_off, uint8_t *mp3_out, const int64_t *mp3_off, const int64_t *mp3_cap,
                           int64_t *out_len, int64_t *hide_str_offset_out)
+{
+    const int rc = encode_impl(h, pcm, mem, pcm_off, n_samples, n_clips, sample_rate, bitrate_kbps, payload_bits, payload_off, mp3_out,
+                               mp3_off, mp3_cap, out_len, hide_str_offset_out);
+    if (rc != M3S_OK && h) {   // an early return may leave work of this call on the helper streams: drain them before the caller reuses buffers
+        cudaStreamSynchronize(h->stream);
+        if (h->copy_in) { cudaStreamSynchronize(h->copy_in); cudaStreamSynchronize(h->copy_out); cudaStreamSynchronize(h->aux); }
+    }
+    return rc;
+}
+
+static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_t *pcm_off, const int64_t *n_samples,
+                       int32_t n_clips, int32_t sample_rate, int32_t bitrate_kbps, const uint8_t *payload_bits,
+                       const int64_t *payload_off, uint8_t *mp3_out, const int64_t *mp3_off, const int64_t *mp3_cap,
+                       int64_t *out_len, int64_t *hide_str_offset_out)
 {
     if (!h) return M3S_ERR_ARG;
     h->enc_taps_ok = false;
@@ -1989,13 +2008,12 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
         // the rate loop of chunk k-1 on the main stream -- also lets that rate loop's CTAs take their SM slots first: the analysis
         // then fills what is left instead of crowding the critical chain out
         if (k >= 2) M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_pack[pb], 0));
-        h->launch_stream = h->aux;
+        M3sLaunchOn on_aux(h, h->aux);   // timing events of this launch go to the aux stream; restored on every return path
         M3S_KBEGIN(h, M3S_K_ENC_ANALYSIS);
         k_enc_analysis<<<(unsigned)nw, ANA_THREADS, 0, h->aux>>>(
             k_pcm, (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips, (const M3sEncWork *)h->e_work.p + work_off[k], h->d_tab,
             (const EncTables *)h->e_tabs.p, sri, 0, (int32_t *)b_mdct[pb]->p, (M3sEncStats *)b_gran[pb]->p);
         M3S_LAUNCH_CHECK(h);
-        h->launch_stream = nullptr;
         M3S_CUDA(h, cudaEventRecord(h->ev_ana[pb], h->aux));
         if (host) {
             M3S_CUDA(h, cudaEventRecord(h->ev_free[pb], h->aux));   // the staging set may be refilled once the analysis has read it

@@ -34,6 +34,12 @@ SYMBOLS = [
     ("m3s_decode_reveal", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p]),
     ("m3s_decode_run", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, ctypes.c_void_p,
                                       ctypes.c_uint32]),
+    ("m3s_decode_run_range", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int,
+                                            _c_i64p, ctypes.c_uint32]),
+    ("m3s_decode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, _c_i64p, ctypes.c_int32, ctypes.c_void_p,
+                                  ctypes.c_int64, _c_i64p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, _c_i64p, _c_i64p, _c_i32p,
+                                  _c_i32p, _c_i32p, _c_i32p, ctypes.c_uint32]),
+    ("m3s_decode_bound", ctypes.c_int64, [ctypes.c_void_p, _c_i64p, _c_i64p, ctypes.c_int32, _c_i64p]),
     ("m3s_encode_bound", ctypes.c_int64, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     ("m3s_encode_size", ctypes.c_int64, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     ("m3s_encode", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _c_i64p, _c_i64p, ctypes.c_int32,
@@ -213,6 +219,71 @@ class Handle:
                                     (M3S_DEC_PCM_FLOAT if as_float else 0) | (M3S_DEC_EXACT if exact else 0))
         self._check(rc, "m3s_decode_run")
         return pcm, sp
+
+    def decode_run_range(self, file_index, first, count, pcm=None, as_float=False, exact=False):
+        """D1-D3 of frames [first, first + count) of one file of the last scan (m3s_decode_run_range).  Returns (pcm, rows)."""
+        ch = max(int(self._scan["channels"][file_index]), 1)
+        if pcm is None:
+            pcm = np.zeros((count + 1) * 1152 * ch, np.float32 if as_float else np.int16)
+        rows = ctypes.c_int64(0)
+        rc = self._L.m3s_decode_run_range(self._h, file_index, first, count, _ptr(pcm), _mem_of(pcm), ctypes.byref(rows),
+                                          (M3S_DEC_PCM_FLOAT if as_float else 0) | (M3S_DEC_EXACT if exact else 0))
+        self._check(rc, "m3s_decode_run_range")
+        return pcm, int(rows.value)
+
+    def decode(self, data, file_off, audio_start=None, pcm=None, table_ids=None, reveal_bits=None, as_float=False, exact=False,
+               frames_bound=None):
+        """m3s_decode: decode + reveal of a whole batch in ONE self-pipelining call (MP3Parser.parse_file + write_to_wav's int16
+        conversion for every file).  `data`: uint8 numpy / torch tensor (host or cuda) of all files end to end.  Output buffers
+        (numpy or torch, same side as `data`) are allocated when None -- for host input sized by m3s_decode_bound, for device
+        input `pcm` / `frames_bound` must be given.  Returns a dict: per-file arrays n_frames, pcm_rows, sample_rate, channels,
+        bitrate, status, reveal_len, pcm_off [n+1] (elements) and the buffers pcm, table_ids, reveal_bits."""
+        n = len(file_off) - 1
+        fo, fo_p = _i64(file_off)
+        au, au_p = (None, None) if audio_start is None else _i64(audio_start)
+        mem = _mem_of(data)
+        if frames_bound is None:
+            if mem == M3S_MEM_DEVICE:
+                raise M3SError("decode: device-resident input needs frames_bound (and pcm)")
+            fb = ctypes.c_int64(0)
+            if self._L.m3s_decode_bound(_ptr(data), fo_p, au_p, n, ctypes.byref(fb)) < 0:
+                raise M3SError("m3s_decode_bound failed")
+            frames_bound = int(fb.value)
+        frames_bound = max(int(frames_bound), 1)
+        if mem == M3S_MEM_DEVICE:
+            import torch
+            mk = lambda cnt, dt: torch.empty(cnt, dtype=dt, device=data.device)   # noqa: E731
+            u8, pdt = torch.uint8, (torch.float32 if as_float else torch.int16)
+        else:
+            mk = lambda cnt, dt: np.empty(cnt, dt)   # noqa: E731
+            u8, pdt = np.uint8, (np.float32 if as_float else np.int16)
+        if pcm is None:
+            pcm = mk(frames_bound * 1152 * 2, pdt)
+        if table_ids is None:
+            table_ids = mk(frames_bound * 12, u8)
+        if reveal_bits is None:
+            reveal_bits = mk(frames_bound * 12, u8)
+        cap = int(pcm.numel() if hasattr(pcm, "numel") else pcm.size)
+        fcap = min(int(t.numel() if hasattr(t, "numel") else t.size) for t in (table_ids, reveal_bits)) // 12
+        out = dict(n_frames=np.zeros(n, np.int64), sample_rate=np.zeros(n, np.int32), channels=np.zeros(n, np.int32),
+                   bitrate=np.zeros(n, np.int32), status=np.zeros(n, np.int32), reveal_len=np.zeros(n, np.int64),
+                   pcm_off=np.zeros(n + 1, np.int64))
+        self._keep = (data, fo, au)
+        rc = self._L.m3s_decode(self._h, _ptr(data), mem, fo_p, au_p, n, _ptr(pcm), cap, out["pcm_off"].ctypes.data_as(_c_i64p),
+                                _ptr(table_ids), _ptr(reveal_bits), fcap, out["reveal_len"].ctypes.data_as(_c_i64p),
+                                out["n_frames"].ctypes.data_as(_c_i64p), out["sample_rate"].ctypes.data_as(_c_i32p),
+                                out["channels"].ctypes.data_as(_c_i32p), out["bitrate"].ctypes.data_as(_c_i32p),
+                                out["status"].ctypes.data_as(_c_i32p), (M3S_DEC_PCM_FLOAT if as_float else 0) | (M3S_DEC_EXACT if exact else 0))
+        self._check(rc, "m3s_decode")
+        out["pcm_rows"] = np.diff(out["pcm_off"]) // np.maximum(out["channels"], 1)
+        out.update(pcm=pcm, table_ids=table_ids, reveal_bits=reveal_bits)
+        return out
+
+    def reveal_strings(self, res):
+        """Per-file reveal bit strings ('0'/'1') of a decode() result with host buffers."""
+        base = np.concatenate([[0], np.cumsum(res["n_frames"])])
+        bits = res["reveal_bits"]
+        return [bytes(bits[12 * base[i]: 12 * base[i] + int(res["reveal_len"][i])]).decode("ascii") for i in range(len(res["n_frames"]))]
 
     # ------------------------------------------------------------------ encode
     def encode(self, pcm, n_samples, sample_rate, bitrate_kbps, payloads=None, pcm_off=None, mp3_out=None, taps=False,

@@ -39,60 +39,49 @@ def frame_ranges(n_frames: int, parts: int) -> List[Dict[str, int]]:
             for k in range(parts) if edges[k + 1] > edges[k]]
 
 
-# frames a range shard decodes in front of its first frame: one warm-up frame (overlap + V history) whose own main data may
-# reach 511 bytes back through the bit reservoir, i.e. through at most 9 frames of the smallest legal payload (60 bytes)
-HALO_FRAMES = 10
-
-
-def plan_frame_shard(n_frames: int, status: int, rank: int, world: int, halo: int = HALO_FRAMES) -> Dict[str, int]:
-    """The frame range rank `rank` of `world` decodes of ONE long file, and how many frames in front of it it has to decode as
-    well (`lead`, PCM discarded): `halo` frames cover the warm-up frame and its bit reservoir; a file whose granules inherit
-    scalefactors from earlier frames (M3S_FILE_STATE_CARRY) needs its whole prefix.  Every rank computes every rank's plan from
-    the same scan result: no communication."""
+def plan_frame_shard(n_frames: int, status: int, rank: int, world: int) -> Dict[str, int]:
+    """The frame range rank `rank` of `world` decodes of ONE long file: dict(first, count, warm, compact_from).  `warm` = 1 when a
+    warm-up frame is decoded in front of the range (PCM discarded); `compact_from` = the first frame whose main data has to be
+    compacted for the range: 9 frames in front of the warm-up frame cover its bit reservoir (511 bytes over the smallest legal
+    payload, Frame.py:306-309), and a file whose granules inherit scalefactors from earlier frames (M3S_FILE_STATE_CARRY) needs
+    its whole prefix.  Informational: m3s_decode_run_range derives the same numbers itself.  Every rank computes every rank's
+    plan from the same scan result: no communication."""
     from . import _lib
     rs = frame_ranges(n_frames, world)
     if rank >= len(rs):
-        return dict(first=n_frames, count=0, lead=0)
+        return dict(first=n_frames, count=0, warm=0, compact_from=n_frames)
     r = rs[rank]
-    lead = r["first"] if status & _lib.M3S_FILE_STATE_CARRY else min(r["first"], max(halo, 1))
-    return dict(first=r["first"], count=r["count"], lead=lead)
+    lo = max(r["first"] - r["warm"], 0)
+    return dict(first=r["first"], count=r["count"], warm=r["warm"],
+                compact_from=0 if status & _lib.M3S_FILE_STATE_CARRY else max(lo - 9, 0))
 
 
 _H0 = frozenset((3, 6, 8, 11, 12, 15, 17, 19, 21, 23, 24, 26, 28, 30))   # tables that reveal a '0' (decoder/util.py:3)
 
 
-def decode_frame_range(handle, blob: bytes, rank: int, world: int, audio_start: int = 0, exact: bool = False,
-                       halo: int = HALO_FRAMES):
+def decode_frame_range(handle, blob, rank: int, world: int, audio_start: int = 0, exact: bool = False, pcm=None):
     """Range-sharded decode+reveal of one long file: rank `rank` of `world` returns the PCM rows and the reveal
     bits of ITS frame range only; the ranges of all ranks, concatenated in rank order, equal the whole-file decode bit for bit.
 
     The frame walk and the side-info scan (D0 + D4: no Huffman decode, ~36 bytes read per frame) run over the WHOLE file on
-    every rank, because the reference never resynchronises: frame positions, the reveal bits and the carried table ids of
-    window-switched granules (A.D3) all come from that scan.  The expensive part (D1-D3) runs on the bytes of the range plus
-    its halo, cut out at frame boundaries and decoded as a file of its own; the halo's PCM is dropped."""
-    data = np.frombuffer(blob, np.uint8)
-    sc = handle.decode_scan(data, [0, len(blob)], [audio_start])
+    every rank, because the reference never resynchronises: frame positions, bit-reservoir cursors, the reveal bits and the
+    carried table ids of window-switched granules (A.D3) all come from that scan.  The expensive part (D1-D3) runs on the
+    range plus one warm-up frame, cut on the device from the bytes already uploaded (m3s_decode_run_range).
+    `blob`: bytes, a uint8 numpy array or a uint8 torch tensor (host or cuda); `pcm`: optional output buffer (same side)."""
+    data = np.frombuffer(blob, np.uint8) if isinstance(blob, (bytes, bytearray)) else blob
+    nbytes = int(data.numel() if hasattr(data, "numel") else data.size)
+    sc = handle.decode_scan(data, [0, nbytes], [audio_start])
     n_frames, status, ch = int(sc["n_frames"][0]), int(sc["status"][0]), max(int(sc["channels"][0]), 1)
     meta = dict(n_frames=n_frames, sample_rate=int(sc["sample_rate"][0]), channels=ch, bitrate=int(sc["bitrate"][0]), status=status)
-    plan = plan_frame_shard(n_frames, status, rank, world, halo)
-    first, count, lead = plan["first"], plan["count"], plan["lead"]
+    plan = plan_frame_shard(n_frames, status, rank, world)
+    first, count = plan["first"], plan["count"]
     if count == 0:
         return dict(meta, first=first, count=0, pcm=np.zeros((0, ch), np.int16), bits="")
     ids, _ = handle.decode_reveal()
     own = ids[first:first + count].reshape(-1)
     bits = "".join("0" if t in _H0 else "1" for t in own.tolist() if t)
-    pos = handle.decode_frame_pos()
-    last = first + count == n_frames
-    lo = int(pos[first - lead])
-    hi = len(blob) if last else int(pos[first + count])     # the last range keeps the file's tail (trailing junk repeats its last frame)
-    sub = data[lo:hi]
-    s2 = handle.decode_scan(sub, [0, len(sub)])
-    if int(s2["n_frames"][0]) != lead + count:
-        raise RuntimeError(f"range shard parsed {int(s2['n_frames'][0])} frames, expected {lead + count}")
-    pcm, _ = handle.decode_run(exact=exact)
-    rows = int(s2["pcm_rows"][0])
-    pcm = pcm[: rows * ch].reshape(rows, ch)[lead * 1152:]
-    return dict(meta, first=first, count=count, pcm=pcm, bits=bits)
+    out, rows = handle.decode_run_range(0, first, count, pcm=pcm, exact=exact)
+    return dict(meta, first=first, count=count, pcm=out[: rows * ch].reshape(rows, ch), bits=bits)
 
 
 def rank_world():

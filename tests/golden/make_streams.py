@@ -340,9 +340,88 @@ def main_fuzz():
     json.dump(digests, open(os.path.join(HERE, "ref_fuzz.json"), "w"), indent=1, sort_keys=True)
 
 
+def frame_table(data, start=0):
+    """(position, size, main_data_begin) of every frame found by the reference's own walk rule (offset += frame_size)."""
+    out, pos = [], start
+    while len(data) > pos + 4 and data[pos] == 0xFF and data[pos + 1] >= 0xE0:
+        b1, b2, b3 = data[pos + 1], data[pos + 2], data[pos + 3]
+        br = BITRATES[b2 >> 4] if b2 >> 4 else 320
+        sr = {0: 44100, 1: 48000, 2: 32000}[(b2 >> 2) & 3]
+        size = 144000 * br // sr + ((b2 >> 1) & 1)
+        si = pos + 4 + (0 if b1 & 1 else 2)
+        mdb = (data[si] << 1) | (data[si + 1] >> 7)
+        out.append((pos, size, mdb))
+        pos += size
+    return out
+
+
+def cut_at(data, k):
+    """The stream from its k-th frame on (what a file cut out of a longer stream looks like)."""
+    return data[frame_table(data)[k][0]:]
+
+
+def id3v2(n):
+    """A syntactically valid ID3v2.3 tag of 10 + n bytes (decoder.py:29-33 honours the synchsafe size)."""
+    body = bytes((37 * i + 11) & 0xFF for i in range(n))
+    return b"ID3\x03\x00\x00" + bytes([(n >> 21) & 0x7F, (n >> 14) & 0x7F, (n >> 7) & 0x7F, n & 0x7F]) + body
+
+
+def edge_cases():
+    """Streams whose first frames point into a bit reservoir that is not there (files cut out of a stream, with and without an
+    ID3v2 tag in front), and streams whose header + side-info length changes under a live reservoir (mono <-> stereo, CRC on /
+    off): the cases in which the reference's main-data assembly (Frame.py:318-363, A.D9) is NOT 'the bytes of the earlier payloads'."""
+    res = make_stream(**STREAMS["reservoir"])
+    ft = frame_table(res)
+    cases = {}
+    ks = [k for k in range(1, len(ft)) if ft[k][2] > 0]
+    for k in ks[:6]:
+        cases["cut%02d" % k] = cut_at(res, k)
+    k = ks[1]
+    cases["cut%02d_id3_small" % k] = id3v2(40) + cut_at(res, k)      # the tag is shorter than the reach: Python negative-index slices
+    cases["cut%02d_id3_large" % k] = id3v2(900) + cut_at(res, k)     # reads tag bytes as main data
+    vbr = make_stream(**STREAMS["vbr_32k_pad"])
+    kv = [k for k, f in enumerate(frame_table(vbr)) if f[2] > 0 and k > 0]
+    for k in kv[:2]:
+        cases["vbrcut%02d" % k] = cut_at(vbr, k)
+    mono = make_stream(seed=21, n_frames=6, sr=44100, bitrate=96, mode=3, reservoir=True, opts=dict(switching=True, max_bv=100))
+    mono_crc = make_stream(seed=22, n_frames=6, sr=44100, bitrate=96, mode=3, crc=True, reservoir=True, opts=dict(switching=True, max_bv=100))
+    st = make_stream(seed=23, n_frames=9, sr=44100, bitrate=160, mode=1, mode_ext=2, reservoir=True,
+                     opts=dict(switching=True, max_bv=110, block_types=[2], mixed=True))
+    st_crc = make_stream(seed=24, n_frames=9, sr=44100, bitrate=160, crc=True, reservoir=True, opts=dict(switching=True, max_bv=110))
+    def first_live(d):
+        return [k for k, f in enumerate(frame_table(d)) if f[2] > 0 and k > 0][0]
+    # (a channel-count change inside one file is outside the reference's domain: MP3Parser.parse_file raises ValueError when it
+    #  stacks PCM rows of different widths, MP3_Parser.py:83 -- so only the CRC flag can change C under a live reservoir)
+    cases["crc_on"] = make_stream(**STREAMS["reservoir"]) + cut_at(st_crc, first_live(st_crc))   # C 36 -> 38
+    cases["crc_off_mono"] = mono_crc + cut_at(mono, first_live(mono))         # C 23 -> 21
+    long_crc = make_stream(seed=25, n_frames=14, sr=44100, bitrate=128, crc=True, reservoir=True, opts=dict(max_bv=100))
+    cases["late_switch"] = long_crc + cut_at(st, first_live(st))             # C 38 -> 36 after frame 9: dynamic assembly slots
+    return cases
+
+
+def main_edge():
+    import hashlib
+    import json
+    digests = {}
+    for name, data in edge_cases().items():
+        d = MG.ref_decode_taps(data)
+        fn = "edge_" + name
+        open(os.path.join(HERE, fn + ".mp3"), "wb").write(data)
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+        ch = int(d["pcm16"].shape[1]) if d["pcm16"].ndim == 2 else 1
+        digests[fn] = dict(n_frames=int(d["n_frames"]), bitrate=int(d["bitrate"]), sampling_rate=int(d["sampling_rate"]), channels=ch,
+                           pcm16_sha256=sha(d["pcm16"].astype(np.int16)), spectra_sha256=sha(d["spectra"].astype(np.int16)),
+                           tables_shape=list(d["tables"].shape), tables_sha256=sha(np.asarray(d["tables"], np.uint8)), bits=d["bits"])
+        print("%-28s bytes %6d frames %3d ch %d |pcm|max %.3g bits %d" % (fn, len(data), d["n_frames"], ch,
+                                                                         np.abs(d["pcm"]).max() if d["pcm"].size else 0, len(d["bits"])))
+    json.dump(digests, open(os.path.join(HERE, "ref_edge.json"), "w"), indent=1, sort_keys=True)
+
+
 def main():
     if "--fuzz" in sys.argv:
         return main_fuzz()
+    if "--edge" in sys.argv:
+        return main_edge()
     for name, kw in STREAMS.items():
         data = make_stream(**kw)
         d = MG.ref_decode_taps(data)

@@ -26,7 +26,7 @@ def test_reveal_batch_needs_no_decode(handle):
     l0 = handle.launches
     got = batch.reveal_batch(handle, [_blob("ref_test_hid.mp3"), _blob("test.mp3"), _blob("ref_test_cleared.mp3")])
     assert got == [fac["reveal_hid"], fac["reveal_test_mp3"], fac["reveal_cleared"]]
-    assert handle.launches - l0 <= 4          # walk, per-file scan, side info, copy-out: no Huffman / synthesis kernels
+    assert handle.launches - l0 <= 6          # walk, layout, per-file scan, side info, publish, copy-out: no Huffman / synthesis kernels
     assert batch.reveal_batch(handle, []) == []
 
 

@@ -36,6 +36,9 @@ def _decode_batch(handle, blobs, audio_start=None, spectra=True, as_float=False)
 
 def _check(got, ref, pcm16=True):
     assert got["n_frames"] == ref["n_frames"]
+    if ref["n_frames"] == 0:
+        assert got["pcm"].size == 0 and got["bits"] == ""
+        return
     if got["spectra"] is not None:
         assert np.array_equal(got["spectra"], ref["spectra"]), "integer spectra differ"
     assert np.array_equal(got["ids"], ref["tables"]), "table ids differ"
@@ -214,3 +217,125 @@ def test_fuzz_corpus_exact_decode_vs_reference_digests(handle):
         assert sha(ids[fb[i]:fb[i + 1], :6 * r["channels"]]) == r["tables_sha256"], n   # the reference lists 6 ids per channel
         assert sha(sp[fb[i]:fb[i + 1]].astype(np.int16)) == r["spectra_sha256"], n
         assert sha(pcm[eb[i]:eb[i + 1]].astype(np.int16)) == r["pcm16_sha256"], n
+
+
+def _edge_blobs():
+    import json
+    ref = json.load(open(golden_path("ref_edge.json")))
+    names = sorted(ref)
+    return names, [open(golden_path(n + ".mp3"), "rb").read() for n in names], ref
+
+
+def test_edge_reservoirs_exact_vs_reference_digests(handle, oracle):
+    """Cut streams (first frames point into a reservoir that is not there, bare or behind an ID3v2 tag) and CRC switches under a
+    live reservoir: the reference assembles the bytes physically in front of the frame or keeps the previous frame's main data
+    (Frame.py:318-363, A.D9).  Float64 instantiation vs the unmodified reference's digests; FP32 vs the oracle within 1 LSB."""
+    import hashlib
+    names, blobs, ref = _edge_blobs()
+    starts = [oracle.id3_offset(b) for b in blobs]
+    data = np.frombuffer(b"".join(blobs), np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])])
+    sc = handle.decode_scan(data, off, starts)
+    ids, bits = handle.decode_reveal()
+    pcm, sp = handle.decode_run(spectra=True, exact=True)
+    fb = np.concatenate([[0], np.cumsum(sc["n_frames"])])
+    eb = np.concatenate([[0], np.cumsum(sc["pcm_rows"] * np.maximum(sc["channels"], 1))])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    for i, n in enumerate(names):
+        r = ref[n]
+        assert int(sc["n_frames"][i]) == r["n_frames"] and int(sc["sample_rate"][i]) == r["sampling_rate"], n
+        assert bits[i] == r["bits"], n
+        assert sha(ids[fb[i]:fb[i + 1], :6 * r["channels"]]) == r["tables_sha256"], n
+        assert sha(sp[fb[i]:fb[i + 1]].astype(np.int16)) == r["spectra_sha256"], n
+        assert sha(pcm[eb[i]:eb[i + 1]].astype(np.int16)) == r["pcm16_sha256"], n
+    for b, s, g in zip(blobs, starts, _decode_batch(handle, blobs, audio_start=starts)):
+        _check(g, oracle.decode(b, s))
+
+
+def _all_golden_blobs():
+    blobs = [open(golden_path("test.mp3"), "rb").read()]
+    blobs += [np.load(p)["mp3"].tobytes() for p in sorted(glob.glob(os.path.join(GOLDEN, "ref_synth_*.npz")))]
+    blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "ref_test_*.mp3")))]
+    blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "stream_*.mp3")))]
+    blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "fuzz_*.mp3")))]
+    blobs += [open(p, "rb").read() for p in sorted(glob.glob(os.path.join(GOLDEN, "edge_*.mp3")))]
+    blobs += [b"RIFFxxxxWAVE" + b"\x00" * 100, b"", blobs[1] + b"TAG" + b"\x00" * 125]
+    return blobs
+
+
+def _split_decode(res, strings, as_float=False):
+    out = []
+    fb = np.concatenate([[0], np.cumsum(res["n_frames"])])
+    for i in range(len(res["n_frames"])):
+        ch = max(int(res["channels"][i]), 1)
+        out.append(dict(n_frames=int(res["n_frames"][i]), status=int(res["status"][i]), bitrate=int(res["bitrate"][i]),
+                        sample_rate=int(res["sample_rate"][i]), channels=int(res["channels"][i]), spectra=None,
+                        ids=np.asarray(res["table_ids"][12 * fb[i]:12 * fb[i + 1]]).reshape(-1, 12), bits=strings[i],
+                        pcm=np.asarray(res["pcm"][res["pcm_off"][i]:res["pcm_off"][i + 1]]).reshape(-1, ch)))
+    return out
+
+
+@pytest.mark.parametrize("wave_bytes", [3000, 40000, 1 << 28])
+def test_pipelined_batch_call_vs_oracle(built, oracle, wave_bytes, monkeypatch):
+    """m3s_decode -- ONE self-pipelining call for the whole batch (waves of files on copy / scan / compute / copy-out streams) --
+    over every golden stream, with wave sizes that put one file per wave, a few files per wave, and everything in one wave:
+    host buffers, int16 and float PCM, vs the oracle."""
+    from mp3stego_b200 import _lib
+    monkeypatch.setenv("M3S_DEC_WAVE_BYTES", str(wave_bytes))
+    h = _lib.Handle(0)
+    blobs = _all_golden_blobs()
+    starts = [oracle.id3_offset(b) for b in blobs]
+    data = np.frombuffer(b"".join(blobs), np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])])
+    refs = [oracle.decode(b, s) for b, s in zip(blobs, starts)]
+    for rep in range(2):   # the second call reuses every workspace
+        res = h.decode(data, off, starts)
+        for g, ref in zip(_split_decode(res, h.reveal_strings(res)), refs):
+            _check(g, ref)
+    resf = h.decode(data, off, starts, as_float=True)
+    for g, ref in zip(_split_decode(resf, h.reveal_strings(resf)), refs):
+        _check(g, ref, pcm16=False)
+    h.close()
+
+
+def test_pipelined_batch_call_device_resident_and_exact(built, oracle, monkeypatch):
+    """m3s_decode with device pointers (nothing crosses PCIe), float64 instantiation: sample-exact vs the oracle's int16 PCM; the
+    first call under-estimates the frame count of device-resident input on purpose (417 bytes / frame guess vs 64 kbps files),
+    which exercises the grow-and-rescan path."""
+    import torch
+    from mp3stego_b200 import _lib
+    monkeypatch.setenv("M3S_DEC_WAVE_BYTES", "30000")
+    h = _lib.Handle(0)
+    blobs = [np.load(golden_path("ref_synth_s13_64_hide.npz"))["mp3"].tobytes()] * 3 + _all_golden_blobs()
+    starts = [oracle.id3_offset(b) for b in blobs]
+    data = torch.from_numpy(np.frombuffer(b"".join(blobs), np.uint8).copy()).cuda()
+    off = np.concatenate([[0], np.cumsum([len(b) for b in blobs])])
+    refs = [oracle.decode(b, s) for b, s in zip(blobs, starts)]
+    nfr = sum(r["n_frames"] for r in refs) + 8
+    pcm = torch.zeros(nfr * 1152 * 2 + 4096, dtype=torch.int16, device="cuda")
+    res = h.decode(data, off, starts, pcm=pcm, frames_bound=nfr, exact=True)
+    res["pcm"] = res["pcm"].cpu().numpy()
+    res["table_ids"] = res["table_ids"].cpu().numpy()
+    res["reveal_bits"] = res["reveal_bits"].cpu().numpy()
+    for g, ref in zip(_split_decode(res, h.reveal_strings(res)), refs):
+        _check(g, ref)
+        assert np.array_equal(g["pcm"], ref["pcm16"].reshape(g["pcm"].shape))
+    with pytest.raises(_lib.M3SError, match="pcm holds"):
+        h.decode(data, off, starts, pcm=pcm[:1152 * 2 * 40], frames_bound=nfr)
+    res2 = h.decode(data, off, starts, pcm=pcm, frames_bound=nfr)     # the handle is usable after the capacity error
+    assert np.array_equal(res2["n_frames"], res["n_frames"])
+    h.close()
+
+
+def test_decode_run_leaves_gaps_alone(handle, oracle):
+    """Host PCM with caller offsets: the bytes between the files are not touched (per-file copies, not one staging-range copy)."""
+    mp3 = np.load(golden_path("ref_synth_s12_320_plain.npz"))["mp3"].tobytes()
+    data = np.frombuffer(mp3 + mp3, np.uint8)
+    sc = handle.decode_scan(data, [0, len(mp3), 2 * len(mp3)])
+    n = int(sc["pcm_rows"][0]) * 2
+    pcm = np.full(2 * n + 3000, 12345, np.int16)
+    handle.decode_run(pcm=pcm, pcm_off=[1000, 1000 + n + 1000])
+    ref = oracle.decode(mp3)["pcm16"].reshape(-1).astype(np.int32)
+    assert (pcm[:1000] == 12345).all() and (pcm[1000 + n:2000 + n] == 12345).all() and (pcm[2000 + 2 * n:] == 12345).all()
+    assert np.abs(pcm[1000:1000 + n].astype(np.int32) - ref).max() <= PCM_TOL_LSB
+    assert np.abs(pcm[2000 + n:2000 + 2 * n].astype(np.int32) - ref).max() <= PCM_TOL_LSB

@@ -52,7 +52,8 @@ def test_frame_shard_plans_agree_and_cover():
             for p in plans:
                 if p["count"]:
                     assert p["first"] == pos
-                    assert p["lead"] == (p["first"] if status & CARRY else min(p["first"], shard.HALO_FRAMES))
+                    assert p["warm"] == (1 if p["first"] > 0 else 0)
+                    assert p["compact_from"] == (0 if status & CARRY else max(p["first"] - p["warm"] - 9, 0))
                     pos += p["count"]
             assert pos == n
 
@@ -132,6 +133,11 @@ class _OracleHandle:
     def decode_run(self, exact=False):
         return self.r["pcm16"].reshape(-1), None
 
+    def decode_run_range(self, file_index, first, count, pcm=None, exact=False):
+        ch = max(self.r["channels"], 1)
+        rows = self.r["pcm16"].shape[0] - first * 1152 if first + count == self.r["n_frames"] else count * 1152
+        return self.r["pcm16"][first * 1152: first * 1152 + rows].reshape(-1), rows
+
 
 def _range_worker(rank, world, port, blob, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -151,7 +157,7 @@ def _range_worker(rank, world, port, blob, q):
 
 
 def test_frame_range_sharded_decode_world2_gloo():
-    """One long file split by frame range over two ranks (each decodes its range + halo as a file of its own): the ranges,
+    """One long file split by frame range over two ranks (each scans the whole file and decodes its range + one warm-up frame): the ranges,
     gathered, are the whole-file decode sample for sample and bit for bit."""
     import torch.multiprocessing as mp
     sys.path.insert(0, ROOT)

@@ -1,5 +1,5 @@
-"""GPU: frame-range sharding of ONE long file through the C ABI.  The ranks' ranges -- each decoded from the
-bytes of the range plus its halo, cut at frame boundaries -- concatenated in rank order must equal the whole-file decode
+"""GPU: frame-range sharding of ONE long file through the C ABI.  The ranks' ranges -- each decoded on the device from the
+whole file's scan plus one warm-up frame (m3s_decode_run_range) -- concatenated in rank order must equal the whole-file decode
 sample for sample and bit for bit, for product-encoded files and for the writer streams (bit reservoir, VBR, CRC, mono,
 short / mixed blocks, trailing junk)."""
 import numpy as np
@@ -19,10 +19,9 @@ def _whole(handle, blob):
     return sc, pcm[: int(sc["pcm_rows"][0]) * ch].reshape(-1, ch), bits[0]
 
 
-def _sharded(handle, blob, world, halo=None):
+def _sharded(handle, blob, world, exact=False):
     from mp3stego_b200 import shard
-    kw = {} if halo is None else dict(halo=halo)
-    parts = [shard.decode_frame_range(handle, blob, r, world, **kw) for r in range(world)]
+    parts = [shard.decode_frame_range(handle, blob, r, world, exact=exact) for r in range(world)]
     assert sum(p["count"] for p in parts) == parts[0]["n_frames"]
     return np.concatenate([p["pcm"] for p in parts]), "".join(p["bits"] for p in parts), parts
 
@@ -36,25 +35,33 @@ def test_product_encoded_file_in_ranges(handle, oracle, bitrate):
     blob = bytes(res["mp3"][: int(res["out_len"][0])])
     sc, pcm, rbits = _whole(handle, blob)
     assert int(sc["n_frames"][0]) == 150 and not int(sc["status"][0])
+    ref = oracle.decode(blob)
     for world in (2, 3, 8):
         p, b, parts = _sharded(handle, blob, world)
-        assert b == rbits
+        assert b == rbits == ref["bits"]
         assert np.array_equal(p, pcm)
+        assert np.abs(p.astype(np.int32) - ref["pcm16"].astype(np.int32)).max() <= 1
     assert oracle.reveal_parse(rbits) == msg
 
 
 @pytest.mark.parametrize("name", ["stream_reservoir", "stream_vbr_32k_pad", "stream_mono_crc_48k", "stream_ms_stereo",
                                   "stream_long_alltables", "stream_short_mixed", "stream_is_only_bit",
-                                  "fuzz_00", "fuzz_02", "fuzz_05", "fuzz_10", "fuzz_13"])
-def test_writer_streams_in_ranges(handle, name):
+                                  "fuzz_00", "fuzz_02", "fuzz_05", "fuzz_10", "fuzz_13", "edge_cut05", "edge_crc_on", "edge_late_switch"])
+def test_writer_streams_in_ranges(handle, oracle, name):
     """main_data_begin > 0 (the halo must carry the reservoir), variable frame sizes, 21-byte side info, and the streams whose
-    granules inherit scalefactors from earlier frames (whole-prefix halo)."""
+    granules inherit scalefactors from earlier frames (whole-prefix halo).  Pinned on the ORACLE's whole-file decode: reveal bits
+    equal, the float64 instantiation sample-exact, FP32 within 1 LSB (modulo the int16 wrap)."""
     blob = open(golden_path(name + ".mp3"), "rb").read()
+    ref = oracle.decode(blob)
     sc, pcm, rbits = _whole(handle, blob)
-    for world in (2, 3):
+    for world in (2, 3, 5):
         p, b, parts = _sharded(handle, blob, world)
-        assert b == rbits, name
+        assert b == rbits == ref["bits"], name
         assert np.array_equal(p, pcm), name
+        d = np.abs(p.astype(np.int32) - ref["pcm16"].reshape(p.shape).astype(np.int32))
+        assert np.minimum(d, 65536 - d).max() <= 1, name
+        pe, be, _ = _sharded(handle, blob, world, exact=True)
+        assert be == ref["bits"] and np.array_equal(pe, ref["pcm16"].reshape(pe.shape)), name
 
 
 def test_state_carry_flag(handle):
@@ -68,8 +75,8 @@ def test_state_carry_flag(handle):
     assert st["stream_short_mixed"] & _lib.M3S_FILE_STATE_CARRY
     assert not st["stream_long_alltables"] & _lib.M3S_FILE_STATE_CARRY
     assert not st["stream_reservoir"] & _lib.M3S_FILE_STATE_CARRY
-    plan = shard.plan_frame_shard(100, _lib.M3S_FILE_STATE_CARRY, 3, 4)
-    assert plan == dict(first=75, count=25, lead=75)
+    assert shard.plan_frame_shard(100, _lib.M3S_FILE_STATE_CARRY, 3, 4) == dict(first=75, count=25, warm=1, compact_from=0)
+    assert shard.plan_frame_shard(100, 0, 3, 4) == dict(first=75, count=25, warm=1, compact_from=65)
 
 
 def test_trailing_junk_goes_to_the_last_range(handle):

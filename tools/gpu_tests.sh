@@ -1,5 +1,7 @@
 #!/bin/bash
-# GPU parity tests only.  usage: tools/gpu_tests.sh [pytest args]
+# GPU parity tests + smoke (usage: tools/gpu_tests.sh [pytest args])
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q "$@" > gpurun_out/tests_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/tests_gpu.log
-tail -60 gpurun_out/tests_gpu.log
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt
+timeout 1500 python -m pytest tests -m gpu -q "$@" > gpurun_out/tests_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/tests_gpu.log
+tail -25 gpurun_out/tests_gpu.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
