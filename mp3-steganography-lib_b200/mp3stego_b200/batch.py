@@ -30,7 +30,12 @@ def reveal_batch(handle: "_lib.Handle", blobs: Sequence[bytes]) -> List[str]:
     if not blobs:
         return []
     data, off, audio = _concat(blobs)
-    handle.decode_scan(data, off, audio)
+    sc = handle.decode_scan(data, off, audio)
+    for i in range(len(blobs)):   # the reference facade exits / raises on these; a batch must not turn them into ''
+        if sc["status"][i] & _lib.M3S_FILE_UNSUPPORTED:
+            raise IndexError(f"file {i}: frame header outside MPEG-1 Layer III (the reference raises while parsing it)")
+        if sc["status"][i] & _lib.M3S_FILE_NO_SYNC:
+            raise ValueError(f"file {i}: no MPEG sync word at the audio start (MP3Parser is not valid, MP3_Parser.py:36-44)")
     _, bits = handle.decode_reveal()
     return [parse_reveal(b) for b in bits]
 
@@ -39,16 +44,28 @@ def _transcode(handle, blobs, payloads) -> Tuple[List[bytes], List[int], List[in
     import torch
     data, off, audio = _concat(blobs)
     dev = torch.device("cuda", handle.device)
-    sc = handle.decode_scan(torch.from_numpy(data.copy()).to(dev), off, audio)
+    L = _lib.load()
+    fb = np.zeros(1, np.int64)
+    au, au_p = _lib._i64(audio)
+    offc = np.ascontiguousarray(off, np.int64)
+    elems = int(L.m3s_decode_bound(_lib._ptr(data), offc.ctypes.data_as(_lib._c_i64p), au_p, len(blobs), fb.ctypes.data_as(_lib._c_i64p)))
+    d_data = torch.from_numpy(data.copy()).to(dev)
+    pcm = torch.empty(max(elems, 2) + 2, dtype=torch.int16, device=dev)
+    try:     # one self-pipelining call: scan of wave k+1 under the float64 synthesis of wave k, nothing leaves the device
+        sc = handle.decode(d_data, off, audio, pcm=pcm, frames_bound=int(fb[0]) + 1, exact=True)
+    except _lib.M3SError as e:
+        if "hold" not in str(e):
+            raise
+        s0 = handle.decode_scan(d_data, off, audio)   # VBR input: size from an exact scan
+        pcm = torch.empty(int((s0["pcm_rows"] * np.maximum(s0["channels"], 1)).sum()) + 2, dtype=torch.int16, device=dev)
+        sc = handle.decode(d_data, off, audio, pcm=pcm, frames_bound=int(s0["n_frames"].sum()) + 1, exact=True)
     for i in range(len(blobs)):
         if sc["status"][i] & (_lib.M3S_FILE_NO_SYNC | _lib.M3S_FILE_UNSUPPORTED) or sc["n_frames"][i] == 0:
             raise ValueError(f"file {i}: not an MPEG-1 Layer III stream the reference can decode")
         if sc["channels"][i] != 2:
             raise IndexError(f"file {i}: the reference encoder only handles stereo input (WAV_Reader / MP3_Encoder.py:611-614)")
     rows = sc["pcm_rows"].astype(np.int64)
-    pcm_off = np.concatenate([[0], np.cumsum(rows * 2)]).astype(np.int64)
-    pcm = torch.empty(int(pcm_off[-1]) + 2, dtype=torch.int16, device=dev)
-    handle.decode_run(pcm=pcm, pcm_off=pcm_off[:-1], exact=True)
+    pcm_off = sc["pcm_off"]
     out: List[bytes] = [b""] * len(blobs)
     hoff = [0] * len(blobs)
     # one encode call per (sample rate, bitrate) group: the encoder takes one rate pair per batch

@@ -57,6 +57,7 @@ def plan_frame_shard(n_frames: int, status: int, rank: int, world: int) -> Dict[
 
 
 _H0 = frozenset((3, 6, 8, 11, 12, 15, 17, 19, 21, 23, 24, 26, 28, 30))   # tables that reveal a '0' (decoder/util.py:3)
+_REVEAL_CHAR = np.array([ord("0") if t in _H0 else ord("1") for t in range(256)], np.uint8)
 
 
 def decode_frame_range(handle, blob, rank: int, world: int, audio_start: int = 0, exact: bool = False, pcm=None):
@@ -79,7 +80,7 @@ def decode_frame_range(handle, blob, rank: int, world: int, audio_start: int = 0
         return dict(meta, first=first, count=0, pcm=np.zeros((0, ch), np.int16), bits="")
     ids, _ = handle.decode_reveal()
     own = ids[first:first + count].reshape(-1)
-    bits = "".join("0" if t in _H0 else "1" for t in own.tolist() if t)
+    bits = _REVEAL_CHAR[own[own != 0]].tobytes().decode("ascii")     # zeros skipped, H0 -> '0' (decoder/util.py:67-81)
     out, rows = handle.decode_run_range(0, first, count, pcm=pcm, exact=exact)
     return dict(meta, first=first, count=count, pcm=out[: rows * ch].reshape(rows, ch), bits=bits)
 
