@@ -972,10 +972,15 @@ template <typename R> __device__ __forceinline__ R cos36c(int row, int k);
 template <> __device__ __forceinline__ float cos36c<float>(int row, int k) { return c_cos36_f[row][k]; }
 template <> __device__ __forceinline__ double cos36c<double>(int row, int k) { return c_cos36_d[row][k]; }
 
+#include "m3s_hybrid_fast.cuh"
+
 int m3s_upload_cos36(const float *f, const double *d)
 {
     if (cudaMemcpyToSymbol(c_cos36_f, f, sizeof(float) * 18 * 18) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_cos36_d, d, sizeof(double) * 18 * 18) != cudaSuccess) return -1;
+    M3sFastConst fc;   // twiddles of the FP32 instantiation's fast transforms
+    m3s_fast_const_build(fc);
+    if (cudaMemcpyToSymbol(c_fast, &fc, sizeof fc) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -1631,10 +1636,10 @@ extern "C" int m3s_decode_frame_pos(m3s_handle_t h, int64_t *frame_pos)
 }
 
 // frames per CTA run of k_hybrid.  Every run pays the CTA's table staging and one warm-up frame (together ~9 % of a 32-frame
-// run), so large batches use long runs; small batches keep runs short enough to fill the SMs (3 CTAs per SM, >= 4 waves of them).
+// run), so large batches use long runs; small batches keep runs short enough to fill the SMs (3 CTAs per SM, >= 8 waves of them).
 static int hybrid_run_length(int64_t total_frames, int sm_count)
 {
-    const int64_t want = total_frames / ((int64_t)sm_count * 3 * 4);
+    const int64_t want = total_frames / ((int64_t)sm_count * 3 * 8);
     return (int)std::max<int64_t>(16, std::min<int64_t>(128, want));
 }
 
@@ -1729,12 +1734,25 @@ static int run_enqueue(m3s_ctx *h, M3sScanSet &ss, void *d_pcm, int16_t *d_spect
             (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)ss.units.p, (const uint8_t *)h->b_sf.p,                     \
             (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, (tabptr), d_pcm);                      \
     } while (0)
+#define M3S_LAUNCH_HYBRID_FAST(OUT, FL)                                                                                    \
+    do {                                                                                                                   \
+        const size_t smem = sizeof(HybFastSmem<OUT>);                                                                      \
+        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid_fast<OUT, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        M3S_KBEGIN(h, M3S_K_HYBRID);                                                                                       \
+        k_hybrid_fast<OUT, FL><<<(unsigned)work.size(), HF_THREADS, smem, s>>>(                                            \
+            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)ss.units.p, (const uint8_t *)h->b_sf.p,                     \
+            (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, d_pcm);                                \
+    } while (0)
+    static const bool direct_f32 = getenv("M3S_HYBRID_DIRECT") != nullptr;   // A/B: the direct-form FP32 kernel of round 1
     if (exact) {
         if (fl) M3S_LAUNCH_HYBRID(double, M3sDevTablesD, true, h->d_tab_f64);
         else M3S_LAUNCH_HYBRID(double, M3sDevTablesD, false, h->d_tab_f64);
-    } else {
+    } else if (direct_f32) {
         if (fl) M3S_LAUNCH_HYBRID(float, M3sDevTables, true, h->d_tab);
         else M3S_LAUNCH_HYBRID(float, M3sDevTables, false, h->d_tab);
+    } else {
+        if (fl) M3S_LAUNCH_HYBRID_FAST(float, true);
+        else M3S_LAUNCH_HYBRID_FAST(int16_t, false);
     }
     M3S_LAUNCH_CHECK(h);
     return M3S_OK;
@@ -1850,7 +1868,9 @@ extern "C" int m3s_decode(m3s_handle_t h, const uint8_t *bytes, int mem, const i
     const bool fl = (flags & M3S_DEC_PCM_FLOAT) != 0;
     const size_t esz = fl ? 4 : 2;
     // ---- waves of whole files
-    const int64_t wave_bytes = h->dec_wave_bytes > 0 ? h->dec_wave_bytes : ((int64_t)256 << 20);
+    // host buffers: waves small enough that the pipeline fills / drains in a few percent of the call; device-resident input: waves
+    // large enough that the tail of each wave's last CTAs (the kernels of consecutive waves do not overlap) stays small
+    const int64_t wave_bytes = h->dec_wave_bytes > 0 ? h->dec_wave_bytes : (host ? ((int64_t)256 << 20) : ((int64_t)1 << 30));
     std::vector<int> wave_first;
     for (int i = 0; i < n_files;) {
         wave_first.push_back(i);
@@ -1860,6 +1880,11 @@ extern "C" int m3s_decode(m3s_handle_t h, const uint8_t *bytes, int mem, const i
     const int W = (int)wave_first.size();
     wave_first.push_back(n_files);
     int64_t frames_before = 0, elems_before = 0;
+    // M3S_TRACE=1: a timeline of the call (timing events on every stream; printed at the end, relative to the first upload)
+    struct WaveEv { cudaEvent_t h2d0, h2d1, scan1, comp0, comp1, out0, out1; double host_scan_wait_ms; };
+    std::vector<WaveEv> tev;
+    auto mark = [&](cudaEvent_t &e, cudaStream_t st) { if (g_trace) { cudaEventCreate(&e); cudaEventRecord(e, st); } };
+    if (g_trace) { tev.assign(W, WaveEv()); }
     int err = M3S_OK;
     for (int k = 0; k <= W && err == M3S_OK; k++) {
         // ------------------------------------------------------------ A(k): bytes of wave k up, scan of wave k
@@ -1878,20 +1903,25 @@ extern "C" int m3s_decode(m3s_handle_t h, const uint8_t *bytes, int mem, const i
                 if (host) M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_d_out[b], 0));
             }
             if (host) {
-                M3S_CUDA(h, m3s_copy_bulk((void *)d_bytes, bytes + file_off[f0], (size_t)nbytes, cudaMemcpyHostToDevice, h->copy_in));
+                if (g_trace) mark(tev[k].h2d0, h->copy_in);
+                M3S_CUDA(h, cudaMemcpyAsync((void *)d_bytes, bytes + file_off[f0], (size_t)nbytes, cudaMemcpyHostToDevice, h->copy_in));
+                if (g_trace) mark(tev[k].h2d1, h->copy_in);
                 M3S_CUDA(h, cudaEventRecord(h->ev_d_h2d[b], h->copy_in));
                 M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_d_h2d[b], 0));
             }
             if ((err = scan_enqueue(h, ss, h->aux, d_bytes, host ? bytes + file_off[f0] : nullptr, file_off + f0,
                                     audio_start ? audio_start + f0 : nullptr, nfl)))
                 break;
+            if (g_trace) mark(tev[k].scan1, h->aux);
             M3S_CUDA(h, cudaEventRecord(h->ev_d_scan[b], h->aux));
         }
         // ------------------------------------------------------------ B(k - 1): kernels of wave k - 1, results home
         if (k >= 1) {
             const int j = k - 1, b = j & 1, f0 = wave_first[j];
             M3sScanSet &ss = h->ss[b];
+            const double tw0 = g_trace ? now_ms() : 0.0;
             M3S_CUDA(h, cudaEventSynchronize(h->ev_d_scan[b]));
+            if (g_trace) tev[j].host_scan_wait_ms = now_ms() - tw0;
             if ((err = scan_finish(h, ss, h->aux, file_off + f0, audio_start ? audio_start + f0 : nullptr))) break;
             int64_t wave_elems = 0;
             for (int i = 0; i < ss.n_files; i++) {
@@ -1925,7 +1955,9 @@ extern "C" int m3s_decode(m3s_handle_t h, const uint8_t *bytes, int mem, const i
                 if (j >= 2) M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_d_out[b], 0));   // the staging buffer's previous wave is home
             }
             M3S_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_d_scan[b], 0));
+            if (g_trace) mark(tev[j].comp0, h->stream);
             if ((err = run_enqueue(h, ss, d_pcm, nullptr, flags, b))) break;
+            if (g_trace) mark(tev[j].comp1, h->stream);
             const size_t nb = (size_t)12 * (size_t)ss.total_frames;
             if (!host && nb) {
                 if (table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids + 12 * frames_before, ss.tabids.p, nb, cudaMemcpyDeviceToDevice, h->stream));
@@ -1937,8 +1969,10 @@ extern "C" int m3s_decode(m3s_handle_t h, const uint8_t *bytes, int mem, const i
                 if (nb && table_ids) M3S_CUDA(h, cudaMemcpyAsync(table_ids + 12 * frames_before, ss.tabids.p, nb, cudaMemcpyDeviceToHost, h->copy_out));
                 if (nb && reveal_bits) M3S_CUDA(h, cudaMemcpyAsync(reveal_bits + 12 * frames_before, ss.reveal.p, nb, cudaMemcpyDeviceToHost, h->copy_out));
                 M3S_CUDA(h, cudaStreamWaitEvent(h->copy_out, h->ev_d_comp[b], 0));
+                if (g_trace) mark(tev[j].out0, h->copy_out);
                 if (wave_elems)
-                    M3S_CUDA(h, m3s_copy_bulk((char *)pcm + elems_before * esz, d_pcm, (size_t)wave_elems * esz, cudaMemcpyDeviceToHost, h->copy_out));
+                    M3S_CUDA(h, cudaMemcpyAsync((char *)pcm + elems_before * esz, d_pcm, (size_t)wave_elems * esz, cudaMemcpyDeviceToHost, h->copy_out));
+                if (g_trace) mark(tev[j].out1, h->copy_out);
                 M3S_CUDA(h, cudaEventRecord(h->ev_d_out[b], h->copy_out));
             }
             frames_before += ss.total_frames;
@@ -1948,6 +1982,16 @@ extern "C" int m3s_decode(m3s_handle_t h, const uint8_t *bytes, int mem, const i
     if (err == M3S_OK && pcm_off) pcm_off[n_files] = elems_before;
     const std::string keep = h->err;
     const int rc2 = sync_all_streams(h);
+    if (g_trace && err == M3S_OK && host && W > 0) {
+        auto rel = [&](cudaEvent_t e) { float ms = 0.f; if (e) cudaEventElapsedTime(&ms, tev[0].h2d0, e); return ms; };
+        fprintf(stderr, "[m3s_decode] %d waves; per wave (ms since the first upload): h2d [start end] scan_end comp [start end] d2h [start end] | host wait for the scan\n", W);
+        for (int k = 0; k < W; k++)
+            fprintf(stderr, "  wave %3d  h2d %7.2f %7.2f  scan %7.2f  comp %7.2f %7.2f  d2h %7.2f %7.2f | %.2f\n", k, rel(tev[k].h2d0), rel(tev[k].h2d1),
+                    rel(tev[k].scan1), rel(tev[k].comp0), rel(tev[k].comp1), rel(tev[k].out0), rel(tev[k].out1), tev[k].host_scan_wait_ms);
+        for (auto &w : tev)
+            for (cudaEvent_t e : {w.h2d0, w.h2d1, w.scan1, w.comp0, w.comp1, w.out0, w.out1})
+                if (e) cudaEventDestroy(e);
+    }
     if (err != M3S_OK) { h->err = keep; return err; }
     return rc2;
 }

@@ -1,0 +1,372 @@
+// m3s_hybrid_fast.cuh -- D2 + D3 of the decoder, FP32 instantiation (the default path; M3S_DEC_EXACT keeps k_hybrid<double>):
+// requantize -> MS stereo -> reorder / alias -> IMDCT + window + overlap -> frequency inversion -> polyphase synthesis -> int16.
+// (Frame.py:157-218 re_quantize, :561-572, :574-602, :604-622, :106-154 imdct, :624-631, :65-103 synth_filter_bank,
+//  :633-640 interleave, MP3_Parser.py:91 int16 conversion)
+//
+// One CTA (8 warps) walks a run of consecutive frames of one file; a run that does not start its file first decodes one warm-up
+// frame whose PCM is dropped.  A frame costs three CTA barriers; within a phase the warps take different roles:
+//
+//   phase A   warps 0-1  IMDCT of frame f: lane = subband, warp = channel, both granules in turn -- the overlap (second half of the
+//                        previous granule) never leaves the thread's registers; alias butterflies are applied while the 18 inputs
+//                        are loaded (each output depends on one neighbour value, read from the still unmodified spectrum); the
+//                        36-point IMDCT is an 18-point DCT-IV in registers (m3s_fast_transforms.cuh)
+//             warps 2-7  requantize + MS + reorder of frame f + 1 into the other half of the double-buffered spectrum
+//             all        slide the V history, store the PCM of frame f - 1 from its staging tile (32-bit L/R words, coalesced)
+//   phase B   warps 0-2  matrixing: one THREAD per (granule, channel, slot) runs a 32-point Lee DCT in registers on its row
+//             warps 3-7  fetch frame f + 2: integer spectra by cp.async, per-band requantisation factors, block types
+//   phase C   warps 0-7  windowing: warp = (granule, channel, slot parity), lane = output sample; the nine slots of one parity
+//                        share their V rows, so 32 loads feed 144 multiply-adds; results go to the PCM staging tile as int16
+//
+// Shared-memory rows are padded (19 floats per subband, 36 per 32-wide row) so that thread-per-row accesses are conflict-free.
+#pragma once
+#include "m3s_fast_transforms.cuh"
+
+#define HF_THREADS 256
+#define HF_XS 608   // floats per (granule, channel) spectrum: 32 subbands x 19
+#define HF_ROW 36   // floats per 32-wide row of tt / v
+
+template <typename OUT>
+struct HybFastSmem {
+    uint4 spec[288];                   // integer spectra of ONE frame: [pair] = (x, y) int16 of slots 0..3 (slot = 2 gr + ch)
+    float xr[2][2][2][HF_XS];          // [buffer][gr][ch]: requantised spectrum, sample s at s + s / 18
+    float tt[2][2][18][HF_ROW];        // [gr][ch][slot][subband]: IMDCT output = matrixing input
+    float v[2][51][HF_ROW];            // [ch][row]: per slot the 32 distinct matrixing outputs; 15 rows of history + 2 x 18 new
+    OUT stage[1152 * 2];               // PCM of one frame, interleaved
+    float wcoef[16][32];               // windowing: per lane its 8 + 8 signed window coefficients (see the kernel)
+    float pow43[256];
+    float scale[4][64];                // per slot: 2^(e4/4) of long sfb 0..21 | short (sfb * 3 + window) at 22..60
+    float sine[4][36];
+    float cos12[12][8];
+    float cs[8], ca[8];
+    float quarter[4];
+    uint32_t info[4][4];               // ring over frames (g & 3) x slot: block_type [0:2) | mixed [2]
+    uint16_t reorder[576];             // short-block scatter: padded destination | 0x8000 = store zero
+    uint8_t long_sfb2[288];            // pair -> long sfb
+    uint8_t short_sfw2[288];           // pair -> 22 + sfb * 3 + window
+    uint8_t pretab[24];
+    int sr_loaded;
+};
+
+__device__ __forceinline__ float hf_pow2i(int e)
+{
+    e = e < -126 ? -126 : (e > 127 ? 127 : e);
+    return __int_as_float((e + 127) << 23);
+}
+
+// x[i] of the 36-point IMDCT from the 18 DCT-IV values (the index folds once the caller's loop is unrolled)
+__device__ __forceinline__ float hf_imdct_at(const float (&c)[18], int i)
+{
+    return i < 9 ? c[i + 9] : (i <= 26 ? -c[26 - i] : -c[i - 27]);
+}
+
+template <typename OUT, bool FLOAT_OUT>
+__global__ void __launch_bounds__(HF_THREADS, 3)
+k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
+              const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
+              void *__restrict__ pcm_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HybFastSmem<OUT> &sm = *reinterpret_cast<HybFastSmem<OUT> *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const M3sWork wk = work[blockIdx.x];
+    const int nch = wk.channels;
+    const int64_t g_begin = wk.g_first - (wk.warm ? 1 : 0);
+    const int64_t g_end = wk.g_first + wk.count;
+    const uint4 *spec4 = (const uint4 *)spec;
+
+    // ---- one-time table staging
+    for (int i = tid; i < 12 * 8; i += HF_THREADS) (&sm.cos12[0][0])[i] = (&T->imdct_cos12[0][0])[i];
+    for (int i = tid; i < 4 * 36; i += HF_THREADS) (&sm.sine[0][0])[i] = (&T->sine_block[0][0])[i];
+    for (int i = tid; i < 256; i += HF_THREADS) sm.pow43[i] = T->pow43[i];
+    if (tid < 8) { sm.cs[tid] = T->alias_cs[tid]; sm.ca[tid] = T->alias_ca[tid]; }
+    if (tid < 4) sm.quarter[tid] = T->quarter[tid];
+    if (tid < 22) sm.pretab[tid] = T->pretab[tid];
+    if (tid == 0) sm.sr_loaded = -1;
+    for (int i = tid; i < 2 * 51 * HF_ROW; i += HF_THREADS) (&sm.v[0][0][0])[i] = 0.f;
+    // windowing (Frame.py:89-101): pcm[32 t + i] = sum_m V_{t-2m}[i] D[64 m + i] + V_{t-2m-1}[32 + i] D[64 m + 32 + i].  A V row holds the 32
+    // distinct values W[l] = D[16 + l] (l < 16), W[l] = D[l - 16] (l >= 16) of the slot's 32-point DCT D; lane i reads
+    // V[i] = +W[i] | 0 | -W[32 - i] and V[32 + i] = -W[0] | -W[32 - i] | -W[i]; the signs are folded into its 16 window coefficients.
+    for (int e = tid; e < 16 * 32; e += HF_THREADS) {
+        const int m = e >> 5, i = e & 31;
+        const float sA = i < 16 ? 1.f : (i == 16 ? 0.f : -1.f);
+        sm.wcoef[m][i] = m < 8 ? sA * T->synth_d[64 * m + i] : -T->synth_d[64 * (m - 8) + 32 + i];
+    }
+    float ovl[18];   // IMDCT warps: windowed second half of the previous granule of (channel = warp, subband = lane)
+#pragma unroll
+    for (int i = 0; i < 18; i++) ovl[i] = 0.f;
+
+    // ---- per-frame staging: spectra, requantisation factors and block types of frame g, by threads [t0, t0 + nt)
+    auto fetch_frame = [&](int64_t g, int t0, int nt) {
+        const int tr = tid - t0;
+        if (tr < 0 || tr >= nt) return;
+        for (int p = tr; p < 288; p += nt) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.spec[p]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(spec4 + g * 288 + p) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int sr = (int)((fr_meta[g] >> M3S_META_SR_SHIFT) & 3u);
+        if (sm.sr_loaded != sr) {   // uniform over the fetching threads: sr_loaded only changes behind a barrier
+            for (int i = tr; i < 576; i += nt) {
+                const uint32_t d = T->reorder_dst[sr][i];
+                const uint32_t dd = d & 0x3FFu;
+                sm.reorder[i] = (uint16_t)((dd + dd / 18u) | (d & 0x8000u));
+            }
+            for (int p = tr; p < 288; p += nt) {
+                sm.long_sfb2[p] = T->long_sfb_of[sr][2 * p];
+                sm.short_sfw2[p] = (uint8_t)(22 + T->short_sfw_of[sr][2 * p]);
+            }
+        }
+        for (int e = tr; e < 256; e += nt) {
+            const int slot = e >> 6, idx = e & 63;
+            const M3sUnitRec *r = units + 4 * g + slot;
+            const uint32_t a = r->a, b = r->b, c = r->c;
+            const uint8_t *sf = sfin + (4 * g + slot) * M3S_SF_STRIDE;
+            const int gg = M3S_UA_GG(a), mult4 = M3S_UB_SFSCALE(b) ? 4 : 2;
+            int e4 = 0;
+            if (idx < 22) e4 = gg - 210 - mult4 * ((int)sf[idx] + (int)M3S_UB_PREFLAG(b) * (int)sm.pretab[idx]);
+            else if (idx < 61) {
+                const int q = idx - 22, sfb = q / 3, wnd = q - 3 * sfb;
+                e4 = gg - 210 - 8 * (int)M3S_UC_SBG(c, wnd) - mult4 * (int)sf[M3S_SF_SHORT + 13 * wnd + sfb];
+            }
+            sm.scale[slot][idx] = sm.quarter[e4 & 3] * hf_pow2i(e4 >> 2);
+            if (idx == 63) sm.info[g & 3][slot] = M3S_UA_BT(a) | (M3S_UB_MIXED(b) << 2);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    };
+    // (sr_loaded is updated by one thread after the barrier that follows a fetch)
+
+    // ---- requantize + MS + reorder of frame g into xr[buf], by threads [t0, t0 + nt)   (Frame.py:157-218, :561-572, :574-602)
+    auto requant_frame = [&](int64_t g, int buf, int t0, int nt) {
+        const int tr = tid - t0;
+        if (tr < 0 || tr >= nt) return;
+        const bool ms = (fr_meta[g] & M3S_META_MS) != 0 && nch == 2;
+        for (int item = tr; item < 576; item += nt) {
+            const int gr = item >= 288, p = item - 288 * gr;
+            const uint2 w2 = ((const uint2 *)&sm.spec[p])[gr];
+            float val[2][2];
+            uint32_t inf[2];
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch >= nch) { val[ch][0] = val[ch][1] = 0.f; inf[ch] = 0; continue; }
+                const int slot = 2 * gr + ch;
+                const uint32_t wv = ch ? w2.y : w2.x;
+                inf[ch] = sm.info[g & 3][slot];
+                const bool shortp = (inf[ch] & 3u) == 2u;
+                const float sc = sm.scale[slot][shortp ? sm.short_sfw2[p] : sm.long_sfb2[p]];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int x = (int)(int16_t)(h ? (wv >> 16) : (wv & 0xFFFFu));
+                    const int ax = x < 0 ? -x : x;
+                    const float m = (ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax)) * sc;
+                    val[ch][h] = x < 0 ? -m : m;
+                }
+            }
+            if (ms) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float mm = val[0][h], ss = val[1][h];
+                    val[0][h] = (mm + ss) * 0.70710678118654752f;   // (M + S) / SQRT2, Frame.py:568-572
+                    val[1][h] = (mm - ss) * 0.70710678118654752f;
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch >= nch) continue;
+                float *X = sm.xr[buf][gr][ch];
+                if ((inf[ch] & 3u) == 2u || (inf[ch] & 4u)) {
+                    const uint32_t d01 = ((const uint32_t *)sm.reorder)[p];
+                    const uint32_t d0 = d01 & 0xFFFFu, d1 = d01 >> 16;
+                    X[d0 & 0x3FFu] = (d0 & 0x8000u) ? 0.f : val[ch][0];
+                    X[d1 & 0x3FFu] = (d1 & 0x8000u) ? 0.f : val[ch][1];
+                } else {
+                    const int s = 2 * p, pos = s + s / 18;   // 2 p and 2 p + 1 lie in the same subband
+                    X[pos] = val[ch][0];
+                    X[pos + 1] = val[ch][1];
+                }
+            }
+        }
+    };
+
+    // ---- prologue: frame g_begin requantised, frame g_begin + 1 fetched
+    __syncthreads();
+    fetch_frame(g_begin, 0, HF_THREADS);
+    __syncthreads();
+    if (tid == 0) sm.sr_loaded = (int)((fr_meta[g_begin] >> M3S_META_SR_SHIFT) & 3u);
+    requant_frame(g_begin, 0, 0, HF_THREADS);
+    __syncthreads();
+    if (g_begin + 1 < g_end) fetch_frame(g_begin + 1, 0, HF_THREADS);
+    __syncthreads();
+    if (tid == 0 && g_begin + 1 < g_end) sm.sr_loaded = (int)((fr_meta[g_begin + 1] >> M3S_META_SR_SHIFT) & 3u);
+
+    int staged = -1;            // >= 0: the staging tile holds emitted frame number `staged` of the run, still to be stored
+    auto store_staged = [&]() {
+        if (staged < 0) return;
+        const int n_el = 1152 * nch;
+        const M3sWork *w = work + blockIdx.x;   // re-read here rather than held in registers across the frame loop
+        const int reps = (fr_meta[w->g_first + staged] & M3S_META_DUP) ? 2 : 1;
+        for (int rep = 0; rep < reps; rep++) {
+            OUT *dst = (OUT *)pcm_out + w->pcm_elem + (int64_t)(staged + rep) * n_el;
+            if (((uintptr_t)dst & 3) == 0 && ((n_el * (int)sizeof(OUT)) & 3) == 0) {
+                const int nw = n_el * (int)sizeof(OUT) / 4;
+                const uint32_t *s32 = (const uint32_t *)sm.stage;
+                uint32_t *d32 = (uint32_t *)dst;
+                for (int i = tid; i < nw; i += HF_THREADS) d32[i] = s32[i];
+            } else {
+                for (int i = tid; i < n_el; i += HF_THREADS) dst[i] = sm.stage[i];
+            }
+        }
+        staged = -1;
+    };
+
+    const int n_run = (int)(g_end - g_begin), warm = wk.warm ? 1 : 0;
+    for (int f = 0; f < n_run; f++) {
+        const int64_t g = g_begin + f;
+        const int buf = f & 1;
+        const bool emit = f >= warm;
+        // ================================================================ phase A
+        if (g > g_begin) {   // slide the V history: rows 36..50 -> 0..14 (nobody reads or writes V in this phase)
+            for (int idx = tid; idx < nch * 15 * HF_ROW; idx += HF_THREADS) {
+                const int ch = idx >= 15 * HF_ROW, r_ = idx - ch * 15 * HF_ROW;
+                (&sm.v[ch][0][0])[r_] = (&sm.v[ch][36][0])[r_];
+            }
+        }
+        store_staged();
+        if (warp < 2) {
+            const int ch = warp, sb = lane;
+            if (ch < nch) {
+#pragma unroll 1
+                for (int gr = 0; gr < 2; gr++) {
+                    const uint32_t inf = sm.info[g & 3][2 * gr + ch];
+                    const int bt = (int)(inf & 3u);
+                    const float *X = sm.xr[buf][gr][ch];
+                    float *ttc = &sm.tt[gr][ch][0][sb];
+                    float x[18];
+#pragma unroll
+                    for (int k = 0; k < 18; k++) x[k] = X[19 * sb + k];
+                    if (bt != 2) {
+                        if (!(inf & 4u)) {   // alias reduction (Frame.py:604-622): skipped for short and mixed granules
+                            if (sb >= 1) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) x[i] = x[i] * sm.cs[i] + X[19 * (sb - 1) + 17 - i] * sm.ca[i];
+                            }
+                            if (sb <= 30) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) x[17 - i] = x[17 - i] * sm.cs[i] - X[19 * (sb + 1) + i] * sm.ca[i];
+                            }
+                        }
+                        float c[18];
+                        dct4_18(x, c);
+                        const float *w = sm.sine[bt];
+#pragma unroll
+                        for (int i = 0; i < 18; i++) {
+                            float o = fmaf(hf_imdct_at(c, i), w[i], ovl[i]);
+                            if ((i & 1) && (sb & 1)) o = -o;       // frequency inversion (Frame.py:624-631)
+                            ttc[HF_ROW * i] = o;
+                            ovl[i] = hf_imdct_at(c, 18 + i) * w[18 + i];
+                        }
+                    } else {
+                        // three 12-point IMDCTs, windowed and placed at 6 / 12 / 18 with overlap (Frame.py:135-148)
+#pragma unroll
+                        for (int i = 0; i < 18; i++) {
+                            float acc = 0.f;
+                            if (i >= 6) {
+                                const int w_hi = (i - 6) / 6, i_hi = i - 6 - 6 * w_hi;
+                                if (w_hi < 3) {
+                                    float a2 = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < 6; k++) a2 = fmaf(x[6 * w_hi + k], sm.cos12[i_hi][k], a2);
+                                    acc += a2 * sm.sine[2][i_hi];
+                                }
+                                const int w_lo = w_hi - 1;
+                                if (w_lo >= 0) {
+                                    float a2 = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < 6; k++) a2 = fmaf(x[6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
+                                    acc += a2 * sm.sine[2][i_hi + 6];
+                                }
+                            }
+                            float o = acc + ovl[i];
+                            if ((i & 1) && (sb & 1)) o = -o;
+                            ttc[HF_ROW * i] = o;
+                        }
+                        // second half -> the next granule's overlap (every ovl[i] was consumed above)
+#pragma unroll
+                        for (int i = 18; i < 36; i++) {
+                            float acc = 0.f;
+                            if (i < 30) {
+                                const int w_hi = (i - 6) / 6, i_hi = i - 6 - 6 * w_hi;
+                                if (w_hi < 3) {
+                                    float a2 = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < 6; k++) a2 = fmaf(x[6 * w_hi + k], sm.cos12[i_hi][k], a2);
+                                    acc += a2 * sm.sine[2][i_hi];
+                                }
+                                const int w_lo = w_hi - 1;
+                                float a2 = 0.f;
+#pragma unroll
+                                for (int k = 0; k < 6; k++) a2 = fmaf(x[6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
+                                acc += a2 * sm.sine[2][i_hi + 6];
+                            }
+                            ovl[i - 18] = acc;
+                        }
+                    }
+                }
+            }
+        } else if (g + 1 < g_end) {
+            requant_frame(g + 1, buf ^ 1, 64, HF_THREADS - 64);
+        }
+        __syncthreads();
+        // ================================================================ phase B
+        if (tid < nch * 36) {   // matrixing: thread = (granule, channel, slot), a 32-point DCT-II in registers (Frame.py:81-87)
+            const int t = tid % 18, gc = tid / 18, ch = gc % nch, gr = gc / nch;
+            float S[32];
+            const float4 *row = (const float4 *)sm.tt[gr][ch][t];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 q = row[j];
+                S[4 * j] = q.x; S[4 * j + 1] = q.y; S[4 * j + 2] = q.z; S[4 * j + 3] = q.w;
+            }
+            dct2_lee<32>(S);
+            float4 *vo = (float4 *)sm.v[ch][15 + 18 * gr + t];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                vo[j] = make_float4(S[16 + 4 * j], S[17 + 4 * j], S[18 + 4 * j], S[19 + 4 * j]);
+                vo[4 + j] = make_float4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]);
+            }
+        } else if (warp >= 3 && g + 2 < g_end) {
+            fetch_frame(g + 2, 96, HF_THREADS - 96);
+        }
+        __syncthreads();
+        if (tid == 0 && g + 2 < g_end) sm.sr_loaded = (int)((fr_meta[g + 2] >> M3S_META_SR_SHIFT) & 3u);
+        // ================================================================ phase C
+        if (emit) {   // windowing: warp = (granule, channel, slot parity), lane = sample of the slot
+            const int gr = warp >> 2, ch = (warp >> 1) & 1, par = warp & 1;
+            if (ch < nch) {
+                const int idxA = lane < 16 ? lane : (lane == 16 ? 0 : 32 - lane);
+                const int idxB = lane == 0 ? 0 : (lane < 16 ? 32 - lane : lane);
+                const float *va = &sm.v[ch][1 + 18 * gr + par][idxA], *vb = &sm.v[ch][18 * gr + par][idxB];
+                float a[16], b[16], dA[8], dB[8];
+#pragma unroll
+                for (int m = 0; m < 8; m++) { dA[m] = sm.wcoef[m][lane]; dB[m] = sm.wcoef[8 + m][lane]; }
+#pragma unroll
+                for (int d = 0; d < 16; d++) { a[d] = va[2 * HF_ROW * d]; b[d] = vb[2 * HF_ROW * d]; }
+#pragma unroll
+                for (int q = 0; q < 9; q++) {
+                    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        acc0 = fmaf(a[q - m + 7], dA[m], acc0);
+                        acc1 = fmaf(b[q - m + 7], dB[m], acc1);
+                    }
+                    const float o = acc0 + acc1;
+                    const int row = gr * 576 + 32 * (par + 2 * q) + lane;
+                    if (FLOAT_OUT) sm.stage[row * nch + ch] = (OUT)o;
+                    else sm.stage[row * nch + ch] = (OUT)(int16_t)(__float2int_rz(o * 32767.f) & 0xFFFF);   // truncate, keep the low 16 bits (A.D8)
+                }
+            }
+            staged = f - warm;
+        }
+        __syncthreads();
+    }
+    store_staged();
+}

@@ -49,7 +49,9 @@ def _check(got, ref, pcm16=True):
         assert d.max() <= PCM_TOL_LSB, f"PCM off by {d.max()} LSB"
     else:
         assert got["pcm"].shape == ref["pcm"].shape
-        assert np.abs(got["pcm"].astype(np.float64) - ref["pcm"]).max() <= PCM_TOL_FLOAT
+        # 1e-5 of full scale: streams that run (far) past full scale -- the loud / wrap-around cases, |pcm| up to ~30 -- scale with it
+        tol = PCM_TOL_FLOAT * max(1.0, float(np.abs(ref["pcm"]).max()))
+        assert np.abs(got["pcm"].astype(np.float64) - ref["pcm"]).max() <= tol
 
 
 def test_test_mp3_vs_reference_golden(handle):
