@@ -54,6 +54,10 @@ enum {
     M3S_FILE_NO_SYNC = 1,        /* first audio bytes are not 0xFF 0xEx: MP3Parser.__valid False (MP3_Parser.py:36-44) */
     M3S_FILE_UNSUPPORTED = 2,    /* a frame header outside MPEG-1 Layer III / reserved sample rate or bitrate index 15 */
     M3S_FILE_TRAILING_JUNK = 4,  /* parsing stopped at a bad sync word; the last frame's PCM is repeated once (MP3_Parser.py:68-79) */
+    M3S_FILE_CHANNEL_SWITCH = 16,/* mono and stereo frames in one file: MP3Parser.parse_file raises ValueError when it stacks PCM rows of
+                                    different widths (MP3_Parser.py:83); the PCM this library writes for such a file is unspecified */
+    M3S_FILE_BAD_SIDEINFO = 32,  /* a granule with big_values > 288 or region0_count + region1_count + 2 > 22: the reference raises
+                                    IndexError (Frame.py:461-478); this library clamps and flags the file */
     M3S_FILE_STATE_CARRY = 8     /* some granule takes scalefactors from EARLIER frames through the reference's persistent arrays: a mixed
                                     block (scale_fac_s[..][0..2], Frame.py:387-403 vs :198) or scfsi over a short-block granule 0
                                     (Frame.py:419-437).  A frame-range shard of such a file needs the whole prefix as its halo. */

@@ -261,6 +261,7 @@ k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec
     uint32_t carry_in = 0;   // 5 bits per (gr, ch) slot
     uint32_t P_in = 0, reveal_in = 0;
     bool state_carry = false;   // a granule inherits scalefactors from earlier frames (M3S_FILE_STATE_CARRY)
+    uint32_t seen_mono = 0, seen_stereo = 0;
     for (int n0 = 0; n0 < fr.n_frames; n0 += 32) {
         const int n = n0 + lane;
         const bool valid = n < fr.n_frames;
@@ -314,6 +315,8 @@ k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec
                 }
             nzfix = h.mono ? 0x5u : 0xFu;  // slots that exist in this frame
         }
+        seen_mono |= __ballot_sync(0xFFFFFFFFu, valid && (meta & M3S_META_MONO));
+        seen_stereo |= __ballot_sync(0xFFFFFFFFu, valid && !(meta & M3S_META_MONO));
         // ---- carry scan: carry after frame k, slot s = t2 of the latest frame <= k that parsed slot s without window switching
         uint32_t carry = 0;
         uint32_t nz = nz01;
@@ -352,6 +355,7 @@ k_fscan(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec
     if (lane == 0) {
         fouts[f].reveal_len = (int32_t)reveal_in;
         if (state_carry) fouts[f].status |= M3S_FILE_STATE_CARRY;
+        if (seen_mono && seen_stereo) fouts[f].status |= M3S_FILE_CHANNEL_SWITCH;
     }
 }
 
@@ -454,7 +458,7 @@ __global__ void k_sideinfo(const uint8_t *__restrict__ bytes, const M3sFileRec *
                            const int64_t *__restrict__ fr_pos, const uint32_t *__restrict__ fr_P,
                            uint32_t *fr_meta, const uint32_t *__restrict__ fr_carry,
                            const uint32_t *__restrict__ fr_reveal, const int32_t *__restrict__ fr_file, M3sUnitRec *units,
-                           uint8_t *tabids, uint8_t *reveal, uint32_t *irr)
+                           uint8_t *tabids, uint8_t *reveal, uint32_t *irr, M3sFileOut *fouts)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lay->overflow || g >= lay->total_frames) return;
@@ -551,6 +555,7 @@ __global__ void k_sideinfo(const uint8_t *__restrict__ bytes, const M3sFileRec *
             u.a = p23 | (bv << 12) | (gg << 21) | (ws << 29) | (bt << 30);
             // region1 of a window-switched granule (12 or 13) does not fit 3 bits: store region0+region1+2 capped to 22 instead
             uint32_t r01 = r0 + r1 + 2;
+            if (bv > 288 || r01 > 22) atomicOr(&fouts[f].status, M3S_FILE_BAD_SIDEINFO);   // the reference raises IndexError here; k_huff clamps
             if (r01 > 22) r01 = 22;
             u.b = sfc | (mixed << 4) | (t0 << 5) | (t1 << 10) | (t2 << 15) | (r0 << 20) | ((uint32_t)(meta & M3S_META_MS ? 1 : 0) << 30) |
                   ((uint32_t)mono << 31) | (pre << 27) | (sfs << 28) | (c1 << 29);
@@ -766,6 +771,55 @@ __device__ __noinline__ uint32_t fetch_stale_short_sf(const uint8_t *S, const M3
 
 #define HUFF_THREADS 256
 
+// Bit reader of the Huffman loops: a 64-bit window whose top bit is the next unread bit, refilled 32 bits at a time from words that
+// were loaded two refills earlier (a lane streams through its own granule; the latency of its loads hides under the pairs decoded in
+// between).  After every consume() the window holds more than 32 valid bits, so one peek serves a whole code (<= 19 bits) plus
+// both sign bits, or both linbits fields + signs (<= 28).  (A queue of 128-bit loads halved the load stalls but cost 47 % more
+// instructions for its bookkeeping and was slower: the kernel is bound by instruction issue.)
+struct BitWindow {
+    const uint32_t *w;   // word-aligned base in S
+    int lim;             // bits readable relative to w (reads at or beyond read as zero, util.get_bits, util.py:41-43)
+    int pos;             // bits consumed relative to w
+    int have;            // valid bits in win
+    int nextw;           // index of the word held in n1
+    uint64_t win;
+    uint32_t n1, n2;     // words nextw and nextw + 1
+    __device__ __forceinline__ uint32_t load(int wi) const
+    {
+        if (wi < (lim >> 5)) return __byte_perm(__ldg(w + wi), 0, 0x0123);
+        const int b = wi * 32;
+        if (b >= lim) return 0u;
+        const uint32_t v = __byte_perm(__ldg(w + wi), 0, 0x0123);
+        return v & ~(0xFFFFFFFFu >> (lim - b));
+    }
+    __device__ __forceinline__ void init(const BitReader &r)   // continue where the scalefactor reader stopped
+    {
+        w = r.w; lim = r.lim; pos = r.pos;
+        const int wi = pos >> 5, sh = pos & 31;
+        win = (((uint64_t)load(wi) << 32) | (uint64_t)load(wi + 1)) << sh;
+        have = 64 - sh;
+        nextw = wi + 2;
+        n1 = load(nextw);
+        n2 = load(nextw + 1);
+    }
+    __device__ __forceinline__ uint32_t peek() const { return (uint32_t)(win >> 32); }
+    __device__ __forceinline__ void consume(int n)   // n <= 32
+    {
+        win <<= n;
+        have -= n;
+        pos += n;
+        if (have <= 32) {
+            win |= (uint64_t)n1 << (32 - have);
+            have += 32;
+            nextw++;
+            n1 = n2;
+            n2 = load(nextw + 1);
+        }
+    }
+};
+
+// One thread per granule-channel.  The three parts of a granule's spectrum -- big-value pairs, count1 quads, zeros -- run as three
+// loops, so that the lanes of a warp (whose granules have different big_values) stay on the same code path within each loop.
 __global__ void __launch_bounds__(HUFF_THREADS)
 k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int64_t u_lo, int64_t u_hi,
        const M3sDevTables *__restrict__ T, uint32_t *__restrict__ spec, uint8_t *__restrict__ sfout)
@@ -773,6 +827,7 @@ k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int6
     __shared__ uint16_t s_lut[8192];
     __shared__ uint32_t s_desc[32], s_sub[32];
     __shared__ uint8_t s_c1[64];
+    __shared__ uint32_t s_sf[HUFF_THREADS][17];   // this thread's 64 scalefactor bytes (17-word rows: conflict-free); dynamically indexed
     for (int i = threadIdx.x; i < 4096; i += HUFF_THREADS) ((uint32_t *)s_lut)[i] = ((const uint32_t *)T->huff_lut)[i];
     if (threadIdx.x < 32) { s_desc[threadIdx.x] = T->huff_desc[threadIdx.x]; s_sub[threadIdx.x] = T->huff_sub[threadIdx.x]; }
     if (threadIdx.x < 64) s_c1[threadIdx.x] = T->count1_lut[threadIdx.x];
@@ -792,10 +847,10 @@ k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int6
     br.init(S, rec.bit_start, rec.limit_bits);
     const int pos0 = br.pos;
     // ---------------------------------------------------------------- scalefactors (Frame.py:365-441)
-    uint32_t sfw[16];
+    uint32_t *sfw = s_sf[threadIdx.x];
 #pragma unroll
     for (int i = 0; i < 16; i++) sfw[i] = 0;
-    uint8_t *sfb8 = (uint8_t *)sfw;  // local byte view
+    uint8_t *sfb8 = (uint8_t *)sfw;
     {
         const int sl0 = T->slen[M3S_UB_SFC(b)][0], sl1 = T->slen[M3S_UB_SFC(b)][1];
         if (is_short) {
@@ -833,8 +888,7 @@ k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int6
         so[2] = make_uint4(sfw[8], sfw[9], sfw[10], sfw[11]);
         so[3] = make_uint4(sfw[12], sfw[13], sfw[14], sfw[15]);
     }
-    // ---------------------------------------------------------------- big values + count1 (Frame.py:443-559)
-    const int max_pos = pos0 + (int)M3S_UA_P23(a);
+    // ---------------------------------------------------------------- big values (Frame.py:443-519)
     int bv = M3S_UA_BV(a);
     if (bv > 288) bv = 288;  // the reference raises IndexError beyond 576 samples
     int r0p, r1p;
@@ -845,58 +899,66 @@ k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int6
     }
     const uint32_t d0 = s_desc[M3S_UB_TS(b, 0)], d1 = s_desc[M3S_UB_TS(b, 1)], d2 = s_desc[M3S_UB_TS(b, 2)];
     const uint32_t sb0 = s_sub[M3S_UB_TS(b, 0)], sb1 = s_sub[M3S_UB_TS(b, 1)], sb2 = s_sub[M3S_UB_TS(b, 2)];
-    const bool c1b = M3S_UB_C1SEL(b);
-    bool c1_active = true, pending = false;
-    uint32_t pend = 0;
-    for (int k = 0; k < 288; k++) {
+    BitWindow bw;
+    bw.init(br);
+    int k = 0;
+    for (; k < bv; k++) {
+        const uint32_t desc = k < r0p ? d0 : (k < r1p ? d1 : d2);
+        const uint32_t sub = k < r0p ? sb0 : (k < r1p ? sb1 : sb2);
+        const int l1b = (desc >> 13) & 15;
         uint32_t o = 0;
-        if (k < bv) {
-            uint32_t desc = k < r0p ? d0 : (k < r1p ? d1 : d2);
-            uint32_t sub = k < r0p ? sb0 : (k < r1p ? sb1 : sb2);
-            int l1b = (desc >> 13) & 15;
-            if (l1b) {  // tables 0, 4 and 14 carry no codes: zeros, no bits consumed (A.D6)
-                uint32_t wv = br.peek();
-                uint32_t e = s_lut[(desc & 0x1FFF) + (wv >> (32 - l1b))];
-                if (e & 0x8000u) {
-                    int nb = (e >> 11) & 15;
-                    e = s_lut[sub + ((e & 0x7FFu) << 1) + ((wv << l1b) >> (32 - nb))];
-                }
-                br.skip((e >> 8) & 31);
-                int x = (e >> 4) & 15, y = e & 15;
-                int lb = (desc >> 17) & 15;
-                wv = br.peek();
-                int used = 0;
-                if (lb && x == 15) { x += wv >> (32 - lb); wv <<= lb; used += lb; }
-                if (x) { if (wv >> 31) x = -x; wv <<= 1; used++; }
-                if (lb && y == 15) { y += wv >> (32 - lb); wv <<= lb; used += lb; }
-                if (y) { if (wv >> 31) y = -y; used++; }
-                br.skip(used);
-                o = ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16);
+        if (l1b) {  // tables 0, 4 and 14 carry no codes: zeros, no bits consumed (A.D6)
+            uint32_t wv = bw.peek();
+            uint32_t e = s_lut[(desc & 0x1FFF) + (wv >> (32 - l1b))];
+            if (e & 0x8000u) {
+                const int nb = (e >> 11) & 15;
+                e = s_lut[sub + ((e & 0x7FFu) << 1) + ((wv << l1b) >> (32 - nb))];
             }
-        } else if (pending) {
-            o = pend;
-            pending = false;
-        } else if (c1_active) {
-            if (br.pos < max_pos && 2 * k + 4 < 576) {
-                uint32_t wv = br.peek();
-                uint32_t q;  // v w x y in bits 3..0
-                int used;
-                if (c1b) { q = (~wv >> 28) & 15u; used = 4; }
-                else { uint32_t e = s_c1[wv >> 26]; q = e & 15u; used = e >> 4; }
-                wv <<= used;
-                int v0 = (q >> 3) & 1, v1 = (q >> 2) & 1, v2 = (q >> 1) & 1, v3 = q & 1;
-                if (v0) { if (wv >> 31) v0 = -1; wv <<= 1; used++; }
-                if (v1) { if (wv >> 31) v1 = -1; wv <<= 1; used++; }
-                if (v2) { if (wv >> 31) v2 = -1; wv <<= 1; used++; }
-                if (v3) { if (wv >> 31) v3 = -1; used++; }
-                br.skip(used);
-                o = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
-                pend = ((uint32_t)v2 & 0xFFFFu) | ((uint32_t)v3 << 16);
-                pending = true;
-            } else c1_active = false;
+            const int len = (e >> 8) & 31;
+            int x = (e >> 4) & 15, y = e & 15;
+            const int lb = (desc >> 17) & 15;
+            int used;
+            if (lb) {   // escape tables: code, then per value [linbits if 15] [sign if non-zero] (Frame.py:503-513)
+                bw.consume(len);
+                wv = bw.peek();
+                used = 0;
+                if (x == 15) { x += wv >> (32 - lb); wv <<= lb; used += lb; }
+                if (x) { if (wv >> 31) x = -x; wv <<= 1; used++; }
+                if (y == 15) { y += wv >> (32 - lb); wv <<= lb; used += lb; }
+                if (y) { if (wv >> 31) y = -y; used++; }
+            } else {
+                wv <<= len;
+                used = len;
+                if (x) { if (wv >> 31) x = -x; wv <<= 1; used++; }
+                if (y) { if (wv >> 31) y = -y; used++; }
+            }
+            bw.consume(used);
+            o = ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16);
         }
         out[4 * k] = o;
     }
+    // ---------------------------------------------------------------- count1 quads (Frame.py:521-559): `while bit < max_bit and sample + 4 < 576`
+    const bool c1b = M3S_UB_C1SEL(b);
+    const int max_pos = pos0 + (int)M3S_UA_P23(a);
+    while (bw.pos < max_pos && 2 * k + 4 < 576) {
+        uint32_t wv = bw.peek();
+        uint32_t q;  // v w x y in bits 3..0
+        int used;
+        if (c1b) { q = (~wv >> 28) & 15u; used = 4; }
+        else { const uint32_t e = s_c1[wv >> 26]; q = e & 15u; used = e >> 4; }
+        wv <<= used;
+        int v0 = (q >> 3) & 1, v1 = (q >> 2) & 1, v2 = (q >> 1) & 1, v3 = q & 1;
+        if (v0) { if (wv >> 31) v0 = -1; wv <<= 1; used++; }
+        if (v1) { if (wv >> 31) v1 = -1; wv <<= 1; used++; }
+        if (v2) { if (wv >> 31) v2 = -1; wv <<= 1; used++; }
+        if (v3) { if (wv >> 31) v3 = -1; used++; }
+        bw.consume(used);
+        out[4 * k] = ((uint32_t)v0 & 0xFFFFu) | ((uint32_t)v1 << 16);
+        out[4 * k + 4] = ((uint32_t)v2 & 0xFFFFu) | ((uint32_t)v3 << 16);
+        k += 2;
+    }
+    // ---------------------------------------------------------------- the rest is zero
+    for (; k < 288; k++) out[4 * k] = 0u;
 }
 
 // int16 [frame][gr][ch][576] parity tap from the pair-major spectra layout
@@ -1467,7 +1529,7 @@ static int scan_enqueue(m3s_ctx *h, M3sScanSet &ss, cudaStream_t s, const uint8_
     k_sideinfo<<<(unsigned)((ss.frames_cap + 127) / 128), 128, 0, s>>>(
         ss.d_bytes, (const M3sFileRec *)ss.files.p, (M3sLayout *)ss.layout.p, (const int64_t *)ss.fr_pos.p, (const uint32_t *)ss.fr_P.p,
         (uint32_t *)ss.fr_meta.p, (const uint32_t *)ss.fr_carry.p, (const uint32_t *)ss.fr_reveal.p, (const int32_t *)ss.fr_file.p,
-        (M3sUnitRec *)ss.units.p, (uint8_t *)ss.tabids.p, (uint8_t *)ss.reveal.p, (uint32_t *)ss.irr.p);
+        (M3sUnitRec *)ss.units.p, (uint8_t *)ss.tabids.p, (uint8_t *)ss.reveal.p, (uint32_t *)ss.irr.p, (M3sFileOut *)ss.fouts.p);
     M3S_LAUNCH_CHECK(h);
     M3S_KBEGIN(h, M3S_K_SIDEINFO);
     k_scan_publish<<<(n_files + 255) / 256, 256, 0, s>>>((const M3sFileOut *)ss.fouts.p, n_files, (const M3sLayout *)ss.layout.p,

@@ -31,7 +31,7 @@ struct HybFastSmem {
     float xr[2][2][2][HF_XS];          // [buffer][gr][ch]: requantised spectrum, sample s at s + s / 18
     float tt[2][2][18][HF_ROW];        // [gr][ch][slot][subband]: IMDCT output = matrixing input
     float v[2][51][HF_ROW];            // [ch][row]: per slot the 32 distinct matrixing outputs; 15 rows of history + 2 x 18 new
-    OUT stage[1152 * 2];               // PCM of one frame, interleaved
+    OUT stage[2][1152];                // PCM of one frame, channel-major (interleaved when it is stored)
     float wcoef[16][32];               // windowing: per lane its 8 + 8 signed window coefficients (see the kernel)
     float pow43[256];
     float scale[4][64];                // per slot: 2^(e4/4) of long sfb 0..21 | short (sfb * 3 + window) at 22..60
@@ -41,8 +41,7 @@ struct HybFastSmem {
     float quarter[4];
     uint32_t info[4][4];               // ring over frames (g & 3) x slot: block_type [0:2) | mixed [2]
     uint16_t reorder[576];             // short-block scatter: padded destination | 0x8000 = store zero
-    uint8_t long_sfb2[288];            // pair -> long sfb
-    uint8_t short_sfw2[288];           // pair -> 22 + sfb * 3 + window
+    uint8_t band2[2][288];             // pair -> scale index: [0] long sfb, [1] 22 + short sfb * 3 + window
     uint8_t pretab[24];
     int sr_loaded;
 };
@@ -70,8 +69,9 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const M3sWork wk = work[blockIdx.x];
     const int nch = wk.channels;
-    const int64_t g_begin = wk.g_first - (wk.warm ? 1 : 0);
-    const int64_t g_end = wk.g_first + wk.count;
+    // (frame indices are wave-relative and fit 32 bits: they stay `int` to keep the loop-carried state small)
+    const int g_begin = (int)wk.g_first - (wk.warm ? 1 : 0);
+    const int g_end = (int)wk.g_first + wk.count;
     const uint4 *spec4 = (const uint4 *)spec;
 
     // ---- one-time table staging
@@ -89,19 +89,21 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
     for (int e = tid; e < 16 * 32; e += HF_THREADS) {
         const int m = e >> 5, i = e & 31;
         const float sA = i < 16 ? 1.f : (i == 16 ? 0.f : -1.f);
-        sm.wcoef[m][i] = m < 8 ? sA * T->synth_d[64 * m + i] : -T->synth_d[64 * (m - 8) + 32 + i];
+        // (the int16 path folds MP3Parser.write_to_wav's factor 32767 into the coefficients: one multiply per sample less)
+        const float k16 = FLOAT_OUT ? 1.f : 32767.f;
+        sm.wcoef[m][i] = k16 * (m < 8 ? sA * T->synth_d[64 * m + i] : -T->synth_d[64 * (m - 8) + 32 + i]);
     }
     float ovl[18];   // IMDCT warps: windowed second half of the previous granule of (channel = warp, subband = lane)
 #pragma unroll
     for (int i = 0; i < 18; i++) ovl[i] = 0.f;
 
     // ---- per-frame staging: spectra, requantisation factors and block types of frame g, by threads [t0, t0 + nt)
-    auto fetch_frame = [&](int64_t g, int t0, int nt) {
+    auto fetch_frame = [&](int g, int t0, int nt) {
         const int tr = tid - t0;
         if (tr < 0 || tr >= nt) return;
         for (int p = tr; p < 288; p += nt) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.spec[p]);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(spec4 + g * 288 + p) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(spec4 + (int64_t)g * 288 + p) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         const int sr = (int)((fr_meta[g] >> M3S_META_SR_SHIFT) & 3u);
@@ -112,78 +114,86 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                 sm.reorder[i] = (uint16_t)((dd + dd / 18u) | (d & 0x8000u));
             }
             for (int p = tr; p < 288; p += nt) {
-                sm.long_sfb2[p] = T->long_sfb_of[sr][2 * p];
-                sm.short_sfw2[p] = (uint8_t)(22 + T->short_sfw_of[sr][2 * p]);
+                sm.band2[0][p] = T->long_sfb_of[sr][2 * p];
+                sm.band2[1][p] = (uint8_t)(22 + T->short_sfw_of[sr][2 * p]);
             }
         }
-        for (int e = tr; e < 256; e += nt) {
-            const int slot = e >> 6, idx = e & 63;
-            const M3sUnitRec *r = units + 4 * g + slot;
+        // requantisation factors: the four slots go to the first four warps of the fetching threads (nt >= 128), two band entries per
+        // lane; the unit-record fields are warp-uniform loads
+        if (tr < 128) {
+            const int slot = tr >> 5;
+            const M3sUnitRec *r = units + 4 * (int64_t)g + slot;
             const uint32_t a = r->a, b = r->b, c = r->c;
-            const uint8_t *sf = sfin + (4 * g + slot) * M3S_SF_STRIDE;
-            const int gg = M3S_UA_GG(a), mult4 = M3S_UB_SFSCALE(b) ? 4 : 2;
-            int e4 = 0;
-            if (idx < 22) e4 = gg - 210 - mult4 * ((int)sf[idx] + (int)M3S_UB_PREFLAG(b) * (int)sm.pretab[idx]);
-            else if (idx < 61) {
-                const int q = idx - 22, sfb = q / 3, wnd = q - 3 * sfb;
-                e4 = gg - 210 - 8 * (int)M3S_UC_SBG(c, wnd) - mult4 * (int)sf[M3S_SF_SHORT + 13 * wnd + sfb];
+            const uint8_t *sf = sfin + (4 * (int64_t)g + slot) * M3S_SF_STRIDE;
+            const int gg = M3S_UA_GG(a), mult4 = M3S_UB_SFSCALE(b) ? 4 : 2, pre = (int)M3S_UB_PREFLAG(b);
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int idx = (tr & 31) + 32 * it;
+                int e4 = 0;
+                if (idx < 22) e4 = gg - 210 - mult4 * ((int)sf[idx] + pre * (int)sm.pretab[idx]);
+                else if (idx < 61) {
+                    const int q = idx - 22, sfb = q / 3, wnd = q - 3 * sfb;
+                    e4 = gg - 210 - 8 * (int)M3S_UC_SBG(c, wnd) - mult4 * (int)sf[M3S_SF_SHORT + 13 * wnd + sfb];
+                }
+                sm.scale[slot][idx] = sm.quarter[e4 & 3] * hf_pow2i(e4 >> 2);
             }
-            sm.scale[slot][idx] = sm.quarter[e4 & 3] * hf_pow2i(e4 >> 2);
-            if (idx == 63) sm.info[g & 3][slot] = M3S_UA_BT(a) | (M3S_UB_MIXED(b) << 2);
+            if ((tr & 31) == 0) sm.info[g & 3][slot] = M3S_UA_BT(a) | (M3S_UB_MIXED(b) << 2);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     };
     // (sr_loaded is updated by one thread after the barrier that follows a fetch)
 
-    // ---- requantize + MS + reorder of frame g into xr[buf], by threads [t0, t0 + nt)   (Frame.py:157-218, :561-572, :574-602)
-    auto requant_frame = [&](int64_t g, int buf, int t0, int nt) {
+    // ---- requantize + MS + reorder of frame g into xr[buf] (Frame.py:157-218, :561-572, :574-602) by the 192 threads [t0, t0 + 192):
+    //      96 threads per granule, three pairs each; everything that depends on the granule only is hoisted out of the pair loop
+    auto requant_pair = [&](uint32_t wv, float sc, float &vx, float &vy) {
+        const int x = (int)(int16_t)(wv & 0xFFFFu), y = (int)wv >> 16;
+        const int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y;
+        float mx, my;
+        if ((ax | ay) < 256) { mx = sm.pow43[ax]; my = sm.pow43[ay]; }
+        else {
+            mx = ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax);
+            my = ay < 256 ? sm.pow43[ay] : (float)ay * cbrtf((float)ay);
+        }
+        vx = __int_as_float(__float_as_int(mx * sc) | (x & 0x80000000));   // sign(x) |x|^(4/3) 2^(e4/4): the product is >= 0, OR in the sign
+        vy = __int_as_float(__float_as_int(my * sc) | (y & 0x80000000));
+    };
+    auto requant_store = [&](float *X, bool reord, int p, float v0, float v1) {
+        if (reord) {
+            const uint32_t d01 = ((const uint32_t *)sm.reorder)[p];
+            const uint32_t d0 = d01 & 0xFFFFu, d1 = d01 >> 16;
+            X[d0 & 0x3FFu] = (d0 & 0x8000u) ? 0.f : v0;
+            X[d1 & 0x3FFu] = (d1 & 0x8000u) ? 0.f : v1;
+        } else {
+            const int pos = 2 * p + p / 9;   // samples 2 p and 2 p + 1 lie in the same subband; 19 floats per subband
+            X[pos] = v0;
+            X[pos + 1] = v1;
+        }
+    };
+    auto requant_frame = [&](int g, int buf, int t0) {
         const int tr = tid - t0;
-        if (tr < 0 || tr >= nt) return;
+        if (tr < 0 || tr >= 192) return;
+        const int gr = tr >= 96, t = tr - 96 * gr;
         const bool ms = (fr_meta[g] & M3S_META_MS) != 0 && nch == 2;
-        for (int item = tr; item < 576; item += nt) {
-            const int gr = item >= 288, p = item - 288 * gr;
+        const uint32_t inf0 = sm.info[g & 3][2 * gr], inf1 = sm.info[g & 3][2 * gr + 1];
+        const bool sh0 = (inf0 & 3u) == 2u, sh1 = (inf1 & 3u) == 2u;
+        const bool re0 = sh0 || (inf0 & 4u), re1 = sh1 || (inf1 & 4u);
+        const uint8_t *band0 = sm.band2[sh0], *band1 = sm.band2[sh1];
+        const float *sc0 = sm.scale[2 * gr], *sc1 = sm.scale[2 * gr + 1];
+        float *X0 = sm.xr[buf][gr][0], *X1 = sm.xr[buf][gr][1];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const int p = t + 96 * j;
             const uint2 w2 = ((const uint2 *)&sm.spec[p])[gr];
-            float val[2][2];
-            uint32_t inf[2];
-#pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch >= nch) { val[ch][0] = val[ch][1] = 0.f; inf[ch] = 0; continue; }
-                const int slot = 2 * gr + ch;
-                const uint32_t wv = ch ? w2.y : w2.x;
-                inf[ch] = sm.info[g & 3][slot];
-                const bool shortp = (inf[ch] & 3u) == 2u;
-                const float sc = sm.scale[slot][shortp ? sm.short_sfw2[p] : sm.long_sfb2[p]];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int x = (int)(int16_t)(h ? (wv >> 16) : (wv & 0xFFFFu));
-                    const int ax = x < 0 ? -x : x;
-                    const float m = (ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax)) * sc;
-                    val[ch][h] = x < 0 ? -m : m;
-                }
+            float a0, a1, b0 = 0.f, b1 = 0.f;
+            requant_pair(w2.x, sc0[band0[p]], a0, a1);
+            if (nch == 2) requant_pair(w2.y, sc1[band1[p]], b0, b1);
+            if (ms) {   // (M + S) / SQRT2, (M - S) / SQRT2 (Frame.py:568-572)
+                const float m0 = a0, m1 = a1;
+                a0 = (m0 + b0) * 0.70710678118654752f; b0 = (m0 - b0) * 0.70710678118654752f;
+                a1 = (m1 + b1) * 0.70710678118654752f; b1 = (m1 - b1) * 0.70710678118654752f;
             }
-            if (ms) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float mm = val[0][h], ss = val[1][h];
-                    val[0][h] = (mm + ss) * 0.70710678118654752f;   // (M + S) / SQRT2, Frame.py:568-572
-                    val[1][h] = (mm - ss) * 0.70710678118654752f;
-                }
-            }
-#pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch >= nch) continue;
-                float *X = sm.xr[buf][gr][ch];
-                if ((inf[ch] & 3u) == 2u || (inf[ch] & 4u)) {
-                    const uint32_t d01 = ((const uint32_t *)sm.reorder)[p];
-                    const uint32_t d0 = d01 & 0xFFFFu, d1 = d01 >> 16;
-                    X[d0 & 0x3FFu] = (d0 & 0x8000u) ? 0.f : val[ch][0];
-                    X[d1 & 0x3FFu] = (d1 & 0x8000u) ? 0.f : val[ch][1];
-                } else {
-                    const int s = 2 * p, pos = s + s / 18;   // 2 p and 2 p + 1 lie in the same subband
-                    X[pos] = val[ch][0];
-                    X[pos + 1] = val[ch][1];
-                }
-            }
+            requant_store(X0, re0, p, a0, a1);
+            if (nch == 2) requant_store(X1, re1, p, b0, b1);
         }
     };
 
@@ -192,45 +202,56 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
     fetch_frame(g_begin, 0, HF_THREADS);
     __syncthreads();
     if (tid == 0) sm.sr_loaded = (int)((fr_meta[g_begin] >> M3S_META_SR_SHIFT) & 3u);
-    requant_frame(g_begin, 0, 0, HF_THREADS);
+    requant_frame(g_begin, 0, 0);
     __syncthreads();
     if (g_begin + 1 < g_end) fetch_frame(g_begin + 1, 0, HF_THREADS);
     __syncthreads();
     if (tid == 0 && g_begin + 1 < g_end) sm.sr_loaded = (int)((fr_meta[g_begin + 1] >> M3S_META_SR_SHIFT) & 3u);
 
     int staged = -1;            // >= 0: the staging tile holds emitted frame number `staged` of the run, still to be stored
-    auto store_staged = [&]() {
+    auto store_staged = [&](int t0, int nt) {   // by threads [t0, t0 + nt); every thread keeps `staged` in step
         if (staged < 0) return;
+        const int tr = tid - t0;
+        if (tr < 0 || tr >= nt) { staged = -1; return; }
         const int n_el = 1152 * nch;
         const M3sWork *w = work + blockIdx.x;   // re-read here rather than held in registers across the frame loop
         const int reps = (fr_meta[w->g_first + staged] & M3S_META_DUP) ? 2 : 1;
         for (int rep = 0; rep < reps; rep++) {
             OUT *dst = (OUT *)pcm_out + w->pcm_elem + (int64_t)(staged + rep) * n_el;
-            if (((uintptr_t)dst & 3) == 0 && ((n_el * (int)sizeof(OUT)) & 3) == 0) {
-                const int nw = n_el * (int)sizeof(OUT) / 4;
-                const uint32_t *s32 = (const uint32_t *)sm.stage;
-                uint32_t *d32 = (uint32_t *)dst;
-                for (int i = tid; i < nw; i += HF_THREADS) d32[i] = s32[i];
+            if (nch == 2) {   // interleave L / R on the way out: every thread stores whole 32-bit (int16) or 64-bit (float) L/R words
+                if constexpr (FLOAT_OUT) {
+                    float2 *d2 = (float2 *)dst;    // stereo offsets are even: 8-byte aligned
+                    for (int i = tr; i < 1152; i += nt) d2[i] = make_float2((float)sm.stage[0][i], (float)sm.stage[1][i]);
+                } else {
+                    const uint32_t *sl = (const uint32_t *)sm.stage[0], *sr_ = (const uint32_t *)sm.stage[1];
+                    const bool al8 = ((uintptr_t)dst & 7) == 0;
+                    for (int i = tr; i < 576; i += nt) {   // samples 2 i and 2 i + 1
+                        const uint32_t l2 = sl[i], r2 = sr_[i];
+                        const uint32_t w0 = __byte_perm(l2, r2, 0x5410), w1 = __byte_perm(l2, r2, 0x7632);
+                        if (al8) ((uint2 *)dst)[i] = make_uint2(w0, w1);
+                        else { ((uint32_t *)dst)[2 * i] = w0; ((uint32_t *)dst)[2 * i + 1] = w1; }
+                    }
+                }
             } else {
-                for (int i = tid; i < n_el; i += HF_THREADS) dst[i] = sm.stage[i];
+                for (int i = tr; i < 1152; i += nt) dst[i] = sm.stage[0][i];
             }
         }
         staged = -1;
     };
 
-    const int n_run = (int)(g_end - g_begin), warm = wk.warm ? 1 : 0;
+    const int n_run = g_end - g_begin, warm = wk.warm ? 1 : 0;
     for (int f = 0; f < n_run; f++) {
-        const int64_t g = g_begin + f;
+        const int g = g_begin + f;
         const int buf = f & 1;
         const bool emit = f >= warm;
         // ================================================================ phase A
-        if (g > g_begin) {   // slide the V history: rows 36..50 -> 0..14 (nobody reads or writes V in this phase)
-            for (int idx = tid; idx < nch * 15 * HF_ROW; idx += HF_THREADS) {
-                const int ch = idx >= 15 * HF_ROW, r_ = idx - ch * 15 * HF_ROW;
-                (&sm.v[ch][0][0])[r_] = (&sm.v[ch][36][0])[r_];
+        if (g > g_begin && tid >= 64) {   // slide the V history: rows 36..50 -> 0..14 (nobody else touches V in this phase; the IMDCT
+                                          // warps, the phase's critical path, are left out of it)
+            for (int idx = tid - 64; idx < nch * (15 * HF_ROW / 4); idx += HF_THREADS - 64) {
+                const int ch = idx >= 15 * HF_ROW / 4, r_ = idx - ch * (15 * HF_ROW / 4);
+                ((float4 *)&sm.v[ch][0][0])[r_] = ((const float4 *)&sm.v[ch][36][0])[r_];
             }
         }
-        store_staged();
         if (warp < 2) {
             const int ch = warp, sb = lane;
             if (ch < nch) {
@@ -313,7 +334,7 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                 }
             }
         } else if (g + 1 < g_end) {
-            requant_frame(g + 1, buf ^ 1, 64, HF_THREADS - 64);
+            requant_frame(g + 1, buf ^ 1, 64);
         }
         __syncthreads();
         // ================================================================ phase B
@@ -333,9 +354,11 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                 vo[j] = make_float4(S[16 + 4 * j], S[17 + 4 * j], S[18 + 4 * j], S[19 + 4 * j]);
                 vo[4 + j] = make_float4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]);
             }
-        } else if (warp >= 3 && g + 2 < g_end) {
-            fetch_frame(g + 2, 96, HF_THREADS - 96);
         }
+        if (warp >= 3) {   // frame f - 1's PCM goes out of its staging tile, frame f + 2 comes in
+            if (g + 2 < g_end) fetch_frame(g + 2, 96, HF_THREADS - 96);
+        }
+        store_staged(96, HF_THREADS - 96);
         __syncthreads();
         if (tid == 0 && g + 2 < g_end) sm.sr_loaded = (int)((fr_meta[g + 2] >> M3S_META_SR_SHIFT) & 3u);
         // ================================================================ phase C
@@ -359,14 +382,14 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                         acc1 = fmaf(b[q - m + 7], dB[m], acc1);
                     }
                     const float o = acc0 + acc1;
-                    const int row = gr * 576 + 32 * (par + 2 * q) + lane;
-                    if (FLOAT_OUT) sm.stage[row * nch + ch] = (OUT)o;
-                    else sm.stage[row * nch + ch] = (OUT)(int16_t)(__float2int_rz(o * 32767.f) & 0xFFFF);   // truncate, keep the low 16 bits (A.D8)
+                    OUT *so = &sm.stage[ch][gr * 576 + 32 * par + lane];
+                    if (FLOAT_OUT) so[64 * q] = (OUT)o;
+                    else so[64 * q] = (OUT)(int16_t)__float2int_rz(o);   // (pcm * 32767).astype(int16): truncate, keep the low 16 bits (A.D8)
                 }
             }
             staged = f - warm;
         }
         __syncthreads();
     }
-    store_staged();
+    store_staged(0, HF_THREADS);
 }

@@ -13,6 +13,19 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmp3stego_b200.so")
 
 M3S_MEM_HOST, M3S_MEM_DEVICE = 0, 1
 M3S_FILE_NO_SYNC, M3S_FILE_UNSUPPORTED, M3S_FILE_TRAILING_JUNK, M3S_FILE_STATE_CARRY = 1, 2, 4, 8
+M3S_FILE_CHANNEL_SWITCH, M3S_FILE_BAD_SIDEINFO = 16, 32
+
+
+def raise_for_status(status: int, what: str = "file"):
+    """Re-raise what the reference raises for a file the scan flagged (MP3Parser / Frame): IndexError for headers or side info
+    outside its tables, ValueError for a channel-count change inside one file.  NO_SYNC is the caller's business (the reference
+    parser is then merely 'not valid' and parses nothing)."""
+    if status & M3S_FILE_UNSUPPORTED:
+        raise IndexError(f"{what}: frame header outside MPEG-1 Layer III (the reference raises while parsing it)")
+    if status & M3S_FILE_BAD_SIDEINFO:
+        raise IndexError(f"{what}: big_values / region counts outside the band tables (Frame.py:461-478 raises IndexError)")
+    if status & M3S_FILE_CHANNEL_SWITCH:
+        raise ValueError(f"{what}: mono and stereo frames in one file (MP3_Parser.py:83: setting an array element with a sequence)")
 M3S_DEC_PCM_FLOAT = 1
 M3S_DEC_EXACT = 2
 

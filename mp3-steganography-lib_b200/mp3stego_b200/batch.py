@@ -32,8 +32,7 @@ def reveal_batch(handle: "_lib.Handle", blobs: Sequence[bytes]) -> List[str]:
     data, off, audio = _concat(blobs)
     sc = handle.decode_scan(data, off, audio)
     for i in range(len(blobs)):   # the reference facade exits / raises on these; a batch must not turn them into ''
-        if sc["status"][i] & _lib.M3S_FILE_UNSUPPORTED:
-            raise IndexError(f"file {i}: frame header outside MPEG-1 Layer III (the reference raises while parsing it)")
+        _lib.raise_for_status(int(sc["status"][i]), f"file {i}")
         if sc["status"][i] & _lib.M3S_FILE_NO_SYNC:
             raise ValueError(f"file {i}: no MPEG sync word at the audio start (MP3Parser is not valid, MP3_Parser.py:36-44)")
     _, bits = handle.decode_reveal()
@@ -60,7 +59,8 @@ def _transcode(handle, blobs, payloads) -> Tuple[List[bytes], List[int], List[in
         pcm = torch.empty(int((s0["pcm_rows"] * np.maximum(s0["channels"], 1)).sum()) + 2, dtype=torch.int16, device=dev)
         sc = handle.decode(d_data, off, audio, pcm=pcm, frames_bound=int(s0["n_frames"].sum()) + 1, exact=True)
     for i in range(len(blobs)):
-        if sc["status"][i] & (_lib.M3S_FILE_NO_SYNC | _lib.M3S_FILE_UNSUPPORTED) or sc["n_frames"][i] == 0:
+        _lib.raise_for_status(int(sc["status"][i]), f"file {i}")
+        if sc["status"][i] & _lib.M3S_FILE_NO_SYNC or sc["n_frames"][i] == 0:
             raise ValueError(f"file {i}: not an MPEG-1 Layer III stream the reference can decode")
         if sc["channels"][i] != 2:
             raise IndexError(f"file {i}: the reference encoder only handles stereo input (WAV_Reader / MP3_Encoder.py:611-614)")

@@ -1,6 +1,7 @@
 """Decoder-side mirror of the reference's Python surface (decoder/decoder.py, decoder/MP3_Parser.py,
-decoder/ID3_Parser.py): same class names, arguments, return values, side effects and failure messages, with the
-frame loop of MP3Parser.parse_file replaced by one call into the CUDA library (include/mp3stego_b200.h)."""
+decoder/ID3_Parser.py): same class names, arguments, return values, temp-WAV / reveal-text side effects and failure messages, with
+the frame loop of MP3Parser.parse_file replaced by one call into the CUDA library (include/mp3stego_b200.h).  Not mirrored: the
+ID3 frame listing the reference writes to ./METADATA.txt when quiet=False (decoder.py:38-57; host-only text)."""
 import os
 import sys
 import time
@@ -15,12 +16,13 @@ def id3_offset(data) -> int:
     """Audio start as Decoder.__init__ computes it (decoder.py:29-33): the ID3v2 tag is honoured only when the four
     low flag bits are clear (ID3_Parser.py:129-135); offset = synchsafe size + 10 (+10 more with a footer, :121-125)."""
     if len(data) >= 10 and data[0] == 0x49 and data[1] == 0x44 and data[2] == 0x33:
-        if data[5] & 0x0F:
+        flags = int(data[5])                     # int(): `data` may be a numpy uint8 array, whose arithmetic wraps at 256
+        if flags & 0x0F:
             return 0
         size = 0
         for i in range(4):
-            size = (size << 7) + data[6 + i]   # util.char_to_int (decoder/util.py:6-19)
-        return size + (20 if data[5] & 0x10 else 10)
+            size = (size << 7) + int(data[6 + i])   # util.char_to_int (decoder/util.py:6-19)
+        return size + (20 if flags & 0x10 else 10)
     return 0
 
 
@@ -63,8 +65,7 @@ class MP3Parser:
             return 0
         h = _lib.default_handle(self.__device)
         sc = h.decode_scan(self.__file_data, [0, len(self.__file_data)], [self.__offset])
-        if sc["status"][0] & _lib.M3S_FILE_UNSUPPORTED:
-            raise IndexError("frame header outside MPEG-1 Layer III (the reference raises while parsing it)")
+        _lib.raise_for_status(int(sc["status"][0]))
         _, bits = h.decode_reveal()
         self.output_bits = bits[0]
         pcm, _ = h.decode_run(exact=self.__exact)

@@ -79,8 +79,7 @@ def decode_files(handle: "_lib.Handle", mp3_paths: Sequence[str], wav_paths: Opt
         out = []
         for i in range(n):
             st = int(res["status"][i])
-            if st & _lib.M3S_FILE_UNSUPPORTED:
-                raise IndexError(f"{mp3_paths[i]}: frame header outside MPEG-1 Layer III (the reference raises while parsing it)")
+            _lib.raise_for_status(st, mp3_paths[i])
             out.append(dict(n_frames=int(res["n_frames"][i]), bitrate=int(res["bitrate"][i]) // 1000, sample_rate=int(res["sample_rate"][i]),
                             channels=int(res["channels"][i]), status=st, message=parse_reveal(strings[i]) if reveal else None))
 

@@ -20,7 +20,8 @@ def main():
     sys.path.insert(0, REF)
     md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     blocks = re.findall(r"```python\n(.*?)```", md, flags=re.S)
-    stub_src = next(b for b in blocks if "mp3stego/_b200.py" in b.splitlines()[0])
+    stub_src = next(b for b in blocks if "mp3stego/_b200.py" in b.splitlines()[0] and "continued" not in b.splitlines()[0])
+    batch_src = next(b for b in blocks if "mp3stego/_b200.py (continued)" in b.splitlines()[0])
     sites_src = next(b for b in blocks if "mp3stego/decoder/MP3_Parser.py" in b.splitlines()[0])
     import numpy as np
     import tqdm
@@ -72,6 +73,15 @@ def main():
     out["cleared_sha256"] = sha("tests/cleared.mp3")
     s.reveal_massage("tests/hid.mp3", "tests/r.txt")
     out["reveal_hid"] = open("tests/r.txt").read()
+    # the batch binding of INTEGRATION.md (m3s_decode: one pipelined call for N files) against the single-file stub
+    exec(compile(batch_src, "INTEGRATION.md:_b200_batch", "exec"), stub.__dict__)
+    blobs = [open(p, "rb").read() for p in ("tests/test.mp3", "tests/hid.mp3", "tests/cleared.mp3")]
+    many = stub.parse_files(blobs, [0, 0, 0])
+    same = True
+    for b, m in zip(blobs, many):
+        one = stub.parse_file(b, 0)
+        same = same and one[0] == m[0] and np.array_equal(one[1], m[1]) and one[2:] == m[2:]
+    out["batch_binding_equals_single"] = bool(same)
     os.chdir(ROOT)
     shutil.rmtree(work, ignore_errors=True)
     print("RESULT " + json.dumps(out))

@@ -65,3 +65,46 @@ def test_mixed_bitrate_batch_vs_oracle_chain(handle, oracle):
     for m, tl, r in zip(msgs, too_long, revealed):
         if not tl:
             assert r == m
+
+
+def _stereo_writer_corpus(oracle):
+    """Every stereo writer / fuzz / edge stream (BASELINE configs[3]: short / mixed / start / stop blocks, MS stereo, scalefactors,
+    reservoir, CRC, VBR, 32 / 48 kHz, loud spectra with int16 wrap), with its oracle decode."""
+    import glob
+    import os
+    from conftest import GOLDEN
+    out = []
+    for p in sorted(glob.glob(os.path.join(GOLDEN, "stream_*.mp3")) + glob.glob(os.path.join(GOLDEN, "fuzz_*.mp3")) +
+                    glob.glob(os.path.join(GOLDEN, "edge_*.mp3"))):
+        blob = open(p, "rb").read()
+        dec = oracle.decode(blob, oracle.id3_offset(blob), taps=False)
+        if dec["channels"] == 2 and dec["n_frames"] > 0:
+            out.append((os.path.basename(p), blob, dec))
+    return out
+
+
+def test_clean_and_hide_on_the_mixed_block_corpus_vs_oracle_chain(handle, oracle):
+    """BASELINE configs[3] 'decode / reveal / clean': clear_file and hide_message (steganography.py:137-182) over the stereo writer
+    streams in ONE batch call each -- different sample rates and bitrates, so several encode groups -- equal, byte for byte, the
+    oracle chained the way the facade chains the reference: oracle.encode(oracle.decode(x).pcm16, bitrate of the LAST frame)."""
+    from mp3stego_b200 import batch
+    from mp3stego_b200.steganography import str_to_binary_str
+    corpus = _stereo_writer_corpus(oracle)
+    assert len(corpus) >= 20
+    blobs = [b for _, b, _ in corpus]
+    cleared = batch.clear_batch(handle, blobs)
+    msgs = ["clean me %d" % i if i % 3 else "x" * 300 for i in range(len(corpus))]
+    hid, too_long = batch.hide_batch(handle, blobs, msgs)
+    for (name, blob, dec), c, hm, tl, m in zip(corpus, cleared, hid, too_long, msgs):
+        pcm = np.asarray(dec["pcm16"], np.int16).reshape(-1, 2)
+        ref = oracle.encode(pcm, dec["sampling_rate"], dec["bit_rate"] // 1000, "", taps=False)
+        assert c == ref["mp3"], name
+        bits = str_to_binary_str(str(len(m)) + "#" + m)
+        refh = oracle.encode(pcm, dec["sampling_rate"], dec["bit_rate"] // 1000, bits, taps=False)
+        assert hm == refh["mp3"], name
+        assert tl == (refh["hide_str_offset"] < len(bits) - 1), name
+    # reveal of the results = what the oracle reveals from the same bytes (the reference's own hide -> reveal round trip is not
+    # an identity on every input: e.g. a 32 kHz file whose stale region addresses carry bits the decoder never reads back, A.E6)
+    assert batch.reveal_batch(handle, cleared) == [oracle.reveal_parse(oracle.decode(c, 0, taps=False)["bits"]) for c in cleared]
+    assert batch.reveal_batch(handle, hid) == [oracle.reveal_parse(oracle.decode(c, 0, taps=False)["bits"]) for c in hid]
+    assert sum(r == m for m, tl, r in zip(msgs, too_long, batch.reveal_batch(handle, hid)) if not tl) >= 5   # and some do round-trip

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import golden_path, load_npz
+from conftest import ROOT, golden_path, load_npz
 
 
 def test_write_wav_matches_reference_bytes(tmp_path, built):
@@ -51,6 +51,9 @@ def test_id3_offset_rule(built, oracle):
     assert id3_offset(b"ID3\x04\x00\x01\x00\x00\x01\x48" + body) == 0   # protected low flag bit set: tag ignored
     assert id3_offset(b"\xff\xfb\x90\x00" + body) == 0
     assert id3_offset(b"ID") == 0
+    # numpy uint8 input (what Decoder / files.py / batch.py hand in): no wrap-around at 256
+    big = np.frombuffer(b"ID3\x03\x00\x00\x00\x00\x07\x04", np.uint8)
+    assert id3_offset(big) == 910 == oracle.id3_offset(bytes(big) + bytes(900)) and isinstance(id3_offset(big), int)
 
 
 def test_reveal_parse_matches_reference_rule(built, oracle):
@@ -85,3 +88,16 @@ def test_facade_path_checks(tmp_path, built):
     m.write_bytes(open(golden_path("test.mp3"), "rb").read())
     with pytest.raises(SystemExit, match="txt_file_path must be txt file"):
         s.reveal_massage(str(m), str(tmp_path / "o.bin"))
+
+
+def test_fast_transforms_match_the_direct_formulas(tmp_path):
+    """The FP32 hybrid kernel's in-register transforms (csrc/m3s_fast_transforms.cuh: 18-point DCT-IV for the 36-point IMDCT, 32-point
+    Lee DCT-II for the 64 x 32 matrixing, with their index / sign maps), compiled for the host, against the reference's direct
+    formulas (Frame.py:81-87,119-133) in double."""
+    import subprocess
+    exe = str(tmp_path / "ftc")
+    src = os.path.join(ROOT, "tests", "model", "fast_transforms_check.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "imdct36 via dct4_18" in out.stdout and "dct2_lee<32>" in out.stdout

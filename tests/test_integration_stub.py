@@ -35,3 +35,4 @@ def test_reference_classes_over_the_stub(built):
     for k in ("out_wav_sha256", "enc320_sha256", "enc128_sha256", "hid_sha256", "cleared_sha256"):
         assert out[k] == fac[k], k
     assert out["hide_ddd_returns"] == fac["hide_ddd_returns"] and out["reveal_hid"] == fac["reveal_hid"]
+    assert out["batch_binding_equals_single"]      # INTEGRATION.md's m3s_decode binding: N files in one call == N single-file calls

@@ -341,3 +341,33 @@ def test_decode_run_leaves_gaps_alone(handle, oracle):
     assert (pcm[:1000] == 12345).all() and (pcm[1000 + n:2000 + n] == 12345).all() and (pcm[2000 + 2 * n:] == 12345).all()
     assert np.abs(pcm[1000:1000 + n].astype(np.int32) - ref).max() <= PCM_TOL_LSB
     assert np.abs(pcm[2000 + n:2000 + 2 * n].astype(np.int32) - ref).max() <= PCM_TOL_LSB
+
+
+def test_files_the_reference_raises_on_are_flagged(handle):
+    """A channel-count change inside one file makes MP3Parser.parse_file raise ValueError (rows of different widths, MP3_Parser.py:83);
+    big_values > 288 makes Frame.__unpack_samples raise IndexError (Frame.py:461-478).  The scan flags both (the kernels clamp and
+    stay inside their buffers) and the Python mirror re-raises."""
+    from mp3stego_b200 import _lib
+    from mp3stego_b200.decoder import MP3Parser
+    mono = open(golden_path("stream_mono_crc_48k.mp3"), "rb").read()
+    stereo = open(golden_path("stream_short_mixed.mp3"), "rb").read()
+    for blob in (mono + stereo, stereo + mono):
+        data = np.frombuffer(blob, np.uint8)
+        sc = handle.decode_scan(data, [0, len(blob)])
+        assert int(sc["status"][0]) & _lib.M3S_FILE_CHANNEL_SWITCH and int(sc["n_frames"][0]) == 18
+        handle.decode_run()          # memory-safe: completes, output unspecified
+        with pytest.raises(ValueError):
+            MP3Parser(data, 0, "/dev/null").parse_file()
+    bad = bytearray(open(golden_path("stream_long_alltables.mp3"), "rb").read())
+    # side info starts at byte 4: main_data_begin 9 + private 3 + scfsi 8 = 20 bits, then part2_3_length 12, then big_values 9 bits
+    bitpos = 8 * 4 + 20 + 12
+    for k in range(9):            # big_values = 511
+        bad[(bitpos + k) >> 3] |= 0x80 >> ((bitpos + k) & 7)
+    data = np.frombuffer(bytes(bad), np.uint8)
+    sc = handle.decode_scan(data, [0, len(bad)])
+    assert int(sc["status"][0]) & _lib.M3S_FILE_BAD_SIDEINFO
+    handle.decode_run()
+    with pytest.raises(IndexError):
+        MP3Parser(data, 0, "/dev/null").parse_file()
+    ok = handle.decode_scan(np.frombuffer(stereo, np.uint8), [0, len(stereo)])
+    assert not int(ok["status"][0]) & (_lib.M3S_FILE_CHANNEL_SWITCH | _lib.M3S_FILE_BAD_SIDEINFO)
