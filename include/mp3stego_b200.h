@@ -14,6 +14,9 @@
  *     memory; the library stages through the device inside the call) or M3S_MEM_DEVICE (device
  *     pointers, e.g. torch tensors' data_ptr(); nothing crosses PCIe).
  *     Small per-file descriptor arrays (offsets, counts, status) are ALWAYS host memory.
+ *     Device buffers must be READY when a call starts -- the library works on its own streams (or the one given to
+ *     m3s_set_stream) and is not ordered with whatever else the caller has queued, e.g. the kernel that produced an
+ *     input or the fill of a freshly allocated output; results are complete when the call returns.
  *   - A handle owns one CUDA stream (or borrows one via m3s_set_stream) and grow-only device
  *     workspaces; calls on one handle are serialised and block until their results are readable,
  *     except where a function says it is asynchronous.  Handles are not thread-safe.

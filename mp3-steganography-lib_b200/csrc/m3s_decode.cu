@@ -1763,7 +1763,9 @@ static int run_enqueue(m3s_ctx *h, M3sScanSet &ss, void *d_pcm, int16_t *d_spect
     if ((rc = pin_reserve(h, h->work_pin[wb], h->work_pin_cap[wb], sizeof(M3sWork) * work.size()))) return rc;
     memcpy(h->work_pin[wb], work.data(), sizeof(M3sWork) * work.size());
     M3S_CUDA(h, cudaMemcpyAsync(h->b_work.p, h->work_pin[wb], sizeof(M3sWork) * work.size(), cudaMemcpyHostToDevice, s));
-    M3S_CUDA(h, cudaMemsetAsync(h->b_S.p, 0, (size_t)s_total, s));
+    // (S needs no clearing: every reader is confined to [start, limit) of a frame's assembled main data -- regular frames start at or
+    //  after their file's first payload byte by construction of resv_plan, irregular ones read a slot that k_reservoir_fix has written
+    //  in full, and BitReader / BitWindow return zeros at or beyond the limit without touching memory)
     M3S_KBEGIN(h, M3S_K_STRIP);
     k_strip<<<(unsigned)(((g_hi - s_lo) * 32 + 255) / 256), 256, 0, s>>>(
         ss.d_bytes, ss.total_bytes, (const M3sFileRec *)ss.files.p, s_lo, g_hi, (const int64_t *)ss.fr_pos.p,

@@ -58,17 +58,16 @@ __device__ __forceinline__ float hf_imdct_at(const float (&c)[18], int i)
     return i < 9 ? c[i + 9] : (i <= 26 ? -c[26 - i] : -c[i - 27]);
 }
 
-template <typename OUT, bool FLOAT_OUT>
-__global__ void __launch_bounds__(HF_THREADS, 3)
-k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
-              const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
-              void *__restrict__ pcm_out)
+template <typename OUT, bool FLOAT_OUT, int nch>
+__device__ __forceinline__ void hybrid_fast_body(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units,
+                                                 const uint8_t *__restrict__ sfin, const uint32_t *__restrict__ fr_meta,
+                                                 const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
+                                                 void *__restrict__ pcm_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HybFastSmem<OUT> &sm = *reinterpret_cast<HybFastSmem<OUT> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const M3sWork wk = work[blockIdx.x];
-    const int nch = wk.channels;
     // (frame indices are wave-relative and fit 32 bits: they stay `int` to keep the loop-carried state small)
     const int g_begin = (int)wk.g_first - (wk.warm ? 1 : 0);
     const int g_end = (int)wk.g_first + wk.count;
@@ -392,4 +391,15 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
         __syncthreads();
     }
     store_staged(0, HF_THREADS);
+}
+
+// the channel count is a compile-time constant of the body (one branch per CTA): no register for it, no per-sample tests
+template <typename OUT, bool FLOAT_OUT>
+__global__ void __launch_bounds__(HF_THREADS, 3)
+k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
+              const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
+              void *__restrict__ pcm_out)
+{
+    if (work[blockIdx.x].channels == 2) hybrid_fast_body<OUT, FLOAT_OUT, 2>(spec, units, sfin, fr_meta, work, T, pcm_out);
+    else hybrid_fast_body<OUT, FLOAT_OUT, 1>(spec, units, sfin, fr_meta, work, T, pcm_out);
 }

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libmp3stego_b200.so")
+LIB_PATH = os.environ.get("M3S_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libmp3stego_b200.so")   # (override: A/B builds)
 
 M3S_MEM_HOST, M3S_MEM_DEVICE = 0, 1
 M3S_FILE_NO_SYNC, M3S_FILE_UNSUPPORTED, M3S_FILE_TRAILING_JUNK, M3S_FILE_STATE_CARRY = 1, 2, 4, 8
@@ -108,6 +108,18 @@ def _ptr(x):
     raise TypeError(type(x))
 
 
+def _ready(*xs):
+    """The library works on its own CUDA stream and does not know the caller's: make sure whatever torch queued on ITS current
+    stream for these device tensors (the kernel that produced an input, the fill of a freshly allocated output) has finished
+    before the library touches them.  Host arrays and None pass through."""
+    done = set()
+    for x in xs:
+        if x is not None and getattr(x, "is_cuda", False) and x.device not in done:
+            import torch
+            torch.cuda.current_stream(x.device).synchronize()
+            done.add(x.device)
+
+
 def _mem_of(x):
     if hasattr(x, "is_cuda"):
         return M3S_MEM_DEVICE if x.is_cuda else M3S_MEM_HOST
@@ -177,6 +189,7 @@ class Handle:
         out = dict(n_frames=np.zeros(n, np.int64), pcm_rows=np.zeros(n, np.int64), sample_rate=np.zeros(n, np.int32),
                    channels=np.zeros(n, np.int32), bitrate=np.zeros(n, np.int32), status=np.zeros(n, np.int32))
         self._keep = (data, fo, au)
+        _ready(data)
         rc = self._L.m3s_decode_scan(self._h, _ptr(data), _mem_of(data), fo_p, au_p, n,
                                      out["n_frames"].ctypes.data_as(_c_i64p), out["pcm_rows"].ctypes.data_as(_c_i64p),
                                      out["sample_rate"].ctypes.data_as(_c_i32p), out["channels"].ctypes.data_as(_c_i32p),
@@ -210,6 +223,7 @@ class Handle:
         Returns the per-file reveal string lengths; file i's chars start at 12 * (frames of files < i)."""
         ln = np.zeros(len(self._scan["n_frames"]), np.int64)
         mem = _mem_of(table_ids if table_ids is not None else reveal_bits)
+        _ready(table_ids, reveal_bits)
         rc = self._L.m3s_decode_reveal(self._h, _ptr(table_ids), _ptr(reveal_bits), mem, ln.ctypes.data_as(_c_i64p))
         self._check(rc, "m3s_decode_reveal")
         return ln
@@ -228,6 +242,7 @@ class Handle:
             sp = np.zeros((max(total_frames, 1), 2, 2, 576), np.int16)
         elif spectra is not False and spectra is not None:
             sp = spectra
+        _ready(pcm, sp)
         rc = self._L.m3s_decode_run(self._h, _ptr(pcm), _mem_of(pcm), po_p, _ptr(sp),
                                     (M3S_DEC_PCM_FLOAT if as_float else 0) | (M3S_DEC_EXACT if exact else 0))
         self._check(rc, "m3s_decode_run")
@@ -239,6 +254,7 @@ class Handle:
         if pcm is None:
             pcm = np.zeros((count + 1) * 1152 * ch, np.float32 if as_float else np.int16)
         rows = ctypes.c_int64(0)
+        _ready(pcm)
         rc = self._L.m3s_decode_run_range(self._h, file_index, first, count, _ptr(pcm), _mem_of(pcm), ctypes.byref(rows),
                                           (M3S_DEC_PCM_FLOAT if as_float else 0) | (M3S_DEC_EXACT if exact else 0))
         self._check(rc, "m3s_decode_run_range")
@@ -282,6 +298,7 @@ class Handle:
                    bitrate=np.zeros(n, np.int32), status=np.zeros(n, np.int32), reveal_len=np.zeros(n, np.int64),
                    pcm_off=np.zeros(n + 1, np.int64))
         self._keep = (data, fo, au)
+        _ready(data, pcm, table_ids, reveal_bits)
         rc = self._L.m3s_decode(self._h, _ptr(data), mem, fo_p, au_p, n, _ptr(pcm), cap, out["pcm_off"].ctypes.data_as(_c_i64p),
                                 _ptr(table_ids), _ptr(reveal_bits), fcap, out["reveal_len"].ctypes.data_as(_c_i64p),
                                 out["n_frames"].ctypes.data_as(_c_i64p), out["sample_rate"].ctypes.data_as(_c_i32p),
@@ -321,7 +338,7 @@ class Handle:
         if mp3_out is None:
             if mem == M3S_MEM_DEVICE:
                 import torch
-                mp3_out = torch.zeros(int(bounds.sum()) + 16, dtype=torch.uint8, device=pcm.device)
+                mp3_out = torch.zeros(int(bounds.sum()) + 16, dtype=torch.uint8, device=pcm.device)   # (its fill is awaited below)
             else:
                 mp3_out = np.zeros(int(bounds.sum()) + 16, np.uint8)
         if payload_packed is not None:
@@ -336,6 +353,7 @@ class Handle:
             pl, ploff, ploff_p, pl_p = None, None, None, None
         out_len = np.zeros(n, np.int64)
         hoff = np.zeros(n, np.int64)
+        _ready(pcm, mp3_out)
         rc = L.m3s_encode(self._h, _ptr(pcm), mem, po_p, ns_p, n, sample_rate, bitrate_kbps, pl_p, ploff_p, _ptr(mp3_out),
                           mo_p, mc_p, out_len.ctypes.data_as(_c_i64p), hoff.ctypes.data_as(_c_i64p))
         self._check(rc, "m3s_encode")
