@@ -1755,6 +1755,7 @@ static int run_enqueue(m3s_ctx *h, M3sScanSet &ss, void *d_pcm, int16_t *d_spect
         }
     }
     if (work.empty()) return M3S_OK;
+    const size_t n_stereo = (size_t)(std::stable_partition(work.begin(), work.end(), [](const M3sWork &w) { return w.channels == 2; }) - work.begin());
     const int64_t s_total = ss.s_bytes + ss.irregular * M3S_APX_SLOT_BYTES;
     if ((rc = reserve_quiet(h, h->b_S, (size_t)s_total))) return rc;
     if ((rc = reserve_quiet(h, h->b_spec, (size_t)nf * 288 * 4 * 4))) return rc;
@@ -1798,27 +1799,35 @@ static int run_enqueue(m3s_ctx *h, M3sScanSet &ss, void *d_pcm, int16_t *d_spect
             (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)ss.units.p, (const uint8_t *)h->b_sf.p,                     \
             (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, (tabptr), d_pcm);                      \
     } while (0)
-#define M3S_LAUNCH_HYBRID_FAST(OUT, FL)                                                                                    \
-    do {                                                                                                                   \
-        const size_t smem = sizeof(HybFastSmem<OUT>);                                                                      \
-        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid_fast<OUT, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        M3S_KBEGIN(h, M3S_K_HYBRID);                                                                                       \
-        k_hybrid_fast<OUT, FL><<<(unsigned)work.size(), HF_THREADS, smem, s>>>(                                            \
-            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)ss.units.p, (const uint8_t *)h->b_sf.p,                     \
-            (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, d_pcm);                                \
+#define M3S_LAUNCH_HYBRID_FAST1(OUT, FL, NCH, first, count)                                                                  \
+    do {                                                                                                                      \
+        const size_t smem = sizeof(HybFastSmem<OUT>);                                                                         \
+        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid_fast<OUT, FL, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        M3S_KBEGIN(h, M3S_K_HYBRID);                                                                                          \
+        k_hybrid_fast<OUT, FL, NCH><<<(unsigned)(count), HF_THREADS, smem, s>>>(                                              \
+            (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)ss.units.p, (const uint8_t *)h->b_sf.p,                        \
+            (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p + (first), h->d_tab, d_pcm);                         \
+        M3S_LAUNCH_CHECK(h);                                                                                                  \
+    } while (0)
+    // the work list holds the stereo runs first, then the mono ones (see above): one launch per channel count that occurs
+#define M3S_LAUNCH_HYBRID_FAST(OUT, FL)                                                                                       \
+    do {                                                                                                                      \
+        if (n_stereo > 0) M3S_LAUNCH_HYBRID_FAST1(OUT, FL, 2, 0, n_stereo);                                                   \
+        if (work.size() > n_stereo) M3S_LAUNCH_HYBRID_FAST1(OUT, FL, 1, n_stereo, work.size() - n_stereo);                    \
     } while (0)
     static const bool direct_f32 = getenv("M3S_HYBRID_DIRECT") != nullptr;   // A/B: the direct-form FP32 kernel of round 1
     if (exact) {
         if (fl) M3S_LAUNCH_HYBRID(double, M3sDevTablesD, true, h->d_tab_f64);
         else M3S_LAUNCH_HYBRID(double, M3sDevTablesD, false, h->d_tab_f64);
+        M3S_LAUNCH_CHECK(h);
     } else if (direct_f32) {
         if (fl) M3S_LAUNCH_HYBRID(float, M3sDevTables, true, h->d_tab);
         else M3S_LAUNCH_HYBRID(float, M3sDevTables, false, h->d_tab);
+        M3S_LAUNCH_CHECK(h);
     } else {
         if (fl) M3S_LAUNCH_HYBRID_FAST(float, true);
         else M3S_LAUNCH_HYBRID_FAST(int16_t, false);
     }
-    M3S_LAUNCH_CHECK(h);
     return M3S_OK;
 }
 

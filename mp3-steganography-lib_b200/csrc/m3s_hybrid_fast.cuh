@@ -58,11 +58,13 @@ __device__ __forceinline__ float hf_imdct_at(const float (&c)[18], int i)
     return i < 9 ? c[i + 9] : (i <= 26 ? -c[26 - i] : -c[i - 27]);
 }
 
+// The channel count is a template parameter (the host launches the stereo and the mono runs of a wave separately): no register
+// for it, no per-sample tests.
 template <typename OUT, bool FLOAT_OUT, int nch>
-__device__ __forceinline__ void hybrid_fast_body(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units,
-                                                 const uint8_t *__restrict__ sfin, const uint32_t *__restrict__ fr_meta,
-                                                 const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
-                                                 void *__restrict__ pcm_out)
+__global__ void __launch_bounds__(HF_THREADS, 3)
+k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
+              const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
+              void *__restrict__ pcm_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HybFastSmem<OUT> &sm = *reinterpret_cast<HybFastSmem<OUT> *>(smem_raw);
@@ -391,15 +393,4 @@ __device__ __forceinline__ void hybrid_fast_body(const uint32_t *__restrict__ sp
         __syncthreads();
     }
     store_staged(0, HF_THREADS);
-}
-
-// the channel count is a compile-time constant of the body (one branch per CTA): no register for it, no per-sample tests
-template <typename OUT, bool FLOAT_OUT>
-__global__ void __launch_bounds__(HF_THREADS, 3)
-k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
-              const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
-              void *__restrict__ pcm_out)
-{
-    if (work[blockIdx.x].channels == 2) hybrid_fast_body<OUT, FLOAT_OUT, 2>(spec, units, sfin, fr_meta, work, T, pcm_out);
-    else hybrid_fast_body<OUT, FLOAT_OUT, 1>(spec, units, sfin, fr_meta, work, T, pcm_out);
 }

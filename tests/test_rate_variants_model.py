@@ -72,8 +72,9 @@ def test_variants_and_resolve_reproduce_the_chain(model):
 
 
 def test_probe_bounds_never_decide_wrongly(tmp_path):
-    """Model of the next optimisation of the probe kernel: certified lower / upper bounds on a probe's bit count decide
-    about 3 of the 7 binary-search probes of a granule at 128 kbps without running them -- and never differently from the true count."""
+    """Model of k_enc_probe's "light" probes (csrc/m3s_encode.cu: probe_row): certified lower / upper bounds on a probe's bit count
+    decide about 3 of the 7 binary-search probes of a granule at 128 kbps without running them -- and never differently from the
+    true count, with no payload and with random payloads at random offsets (every swap variant meets every probe)."""
     exe = str(tmp_path / "probe_bounds_model")
     subprocess.check_call(["gcc", "-O2", "-w", "-o", exe, os.path.join(ROOT, "tests", "model", "probe_bounds_model.c"), "-lm"])
     rng = np.random.default_rng(9)
@@ -85,10 +86,12 @@ def test_probe_bounds_never_decide_wrongly(tmp_path):
         raw = str(tmp_path / f"{name}.raw")
         np.ascontiguousarray(pcm, dtype=np.int16).tofile(raw)
         for br in (64, 128, 320):
-            out = subprocess.run([exe, raw, str(pcm.shape[0] // 1152), str(br)], capture_output=True, text=True, check=True).stdout
-            m = re.search(r"probes\(bin search\) (\d+)  decided by LB (\d+)  by UB (\d+)  violations (\d+)", out)
-            assert m, out
-            probes, lb, ub, viol = map(int, m.groups())
-            assert viol == 0, (name, br, out)
-            decided[(name, br)] = (lb + ub) / max(probes, 1)
+            for seed in ((), ("1",), ("2",), ("3",)):      # no payload, then three random payloads
+                out = subprocess.run([exe, raw, str(pcm.shape[0] // 1152), str(br), *seed], capture_output=True, text=True, check=True).stdout
+                m = re.search(r"probes\(bin search\) (\d+)  decided by LB (\d+)  by UB (\d+)  violations (\d+)", out)
+                assert m, out
+                probes, lb, ub, viol = map(int, m.groups())
+                assert viol == 0, (name, br, seed, out)
+                if not seed:
+                    decided[(name, br)] = (lb + ub) / max(probes, 1)
     assert decided[("tone", 128)] > 0.35      # ~3 of 7 probes on the benchmark's kind of clip
