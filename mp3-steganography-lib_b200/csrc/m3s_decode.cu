@@ -136,8 +136,51 @@ k_walk(const uint8_t *__restrict__ bytes, int64_t total_bytes, const M3sFileRec 
         __syncwarp();
         // ---- resolve up to 32 frames (uniform control flow)
         uint32_t mypos = 0;
-        int got = 0;
-        for (int k = 0; k < 32; k++) {
+        int got = 0, k0 = 0;
+        // Fast path for runs of frames that repeat the batch's first header up to the padding bit (every constant-bitrate file): frame k
+        // then starts at off + k * fs + (padding bits of frames 0 .. k-1), i.e. at one of k + 1 positions of lane k's window.  Each lane
+        // tests ITS candidates in parallel (match mask, padding mask); the serial part of the chain shrinks to a shuffle, two bit
+        // tests and a few adds per frame.  The first frame that does not match falls back to the general step below.
+        {
+            const int d0 = (int)(off - __shfl_sync(0xFFFFFFFFu, wbase, 0));
+            M3sHdr hr;
+            uint32_t r1 = 0, r2 = 0, r3 = 0;
+            bool fast = fend > off + 4 && d0 >= 0 && d0 + 4 <= WALK_WIN;
+            if (fast) {
+                const uint8_t *q = winb + d0;
+                r1 = q[1]; r2 = q[2]; r3 = q[3];
+                fast = q[0] == 0xFF && r1 >= 0xE0 && parse_header(r1, r2, r3, hr) == 0 && (144 * hr.bitrate) / hr.sr == fs_guess;
+            }
+            if (fast) {
+                const int fs0 = fs_guess, dmin = (int)(want - wbase);   // candidate c of lane k sits at window byte dmin + c, c <= k
+                uint32_t mm = 0, pm = 0;
+                const uint32_t *ww = win + lane * WALK_STRIDE;
+                for (int c = 0; c <= lane; c++) {
+                    const int d = dmin + c;
+                    const uint32_t v = __funnelshift_r(ww[d >> 2], ww[(d >> 2) + 1], 8 * (d & 3));   // bytes d .. d + 3, little-endian
+                    const bool ok = (v & 0xC0FCFFFFu) == (0xFFu | r1 << 8 | (r2 & 0xFCu) << 16 | (r3 & 0xC0u) << 24);
+                    mm |= (uint32_t)ok << c;
+                    pm |= ((v >> 17) & 1u) << c;
+                }
+                int c = 0;
+                for (; k0 < 32; k0++) {
+                    if (!(fend > off + 4)) { done = true; break; }
+                    const uint32_t m = __shfl_sync(0xFFFFFFFFu, mm, k0), pbits = __shfl_sync(0xFFFFFFFFu, pm, k0);
+                    if (!((m >> c) & 1u)) break;
+                    const int pad = (int)((pbits >> c) & 1u), fs = fs0 + pad;
+                    const int64_t avail = fend - off;
+                    int payload = (fs < avail ? fs : (int)avail) - hr.hdrlen;
+                    if (payload < 0) payload = 0;
+                    if (lane == k0) mypos = (uint32_t)(off - fr.begin);
+                    got++;
+                    P += payload;
+                    off += fs;
+                    c += pad;
+                }
+                if (got) { o.sample_rate = hr.sr; o.channels = hr.mono ? 1 : 2; o.bitrate = hr.bitrate; }
+            }
+        }
+        for (int k = k0; k < 32 && !done; k++) {
             if (!(fend > off + 4)) { done = true; break; }
             const int64_t kbase = __shfl_sync(0xFFFFFFFFu, wbase, k);
             uint32_t b0, b1, b2, b3;
@@ -1516,6 +1559,8 @@ static int scan_enqueue(m3s_ctx *h, M3sScanSet &ss, cudaStream_t s, const uint8_
                                                n_files, (uint32_t *)ss.tmp_pos.p);
         M3S_LAUNCH_CHECK(h);
     }
+    // the reveal chars of a file fill only the first reveal_len bytes of its 12-bytes-per-frame area: clear the rest, it is copied out too
+    M3S_CUDA(h, cudaMemsetAsync(ss.reveal.p, 0, (size_t)12 * (size_t)ss.frames_cap, s));
     M3S_KBEGIN(h, M3S_K_FSCAN);
     k_layout<<<1, 256, 0, s>>>((M3sFileRec *)ss.files.p, (const M3sFileOut *)ss.fouts.p, n_files, ss.frames_cap, (M3sLayout *)ss.layout.p);
     M3S_LAUNCH_CHECK(h);

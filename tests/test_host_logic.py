@@ -101,3 +101,25 @@ def test_fast_transforms_match_the_direct_formulas(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "imdct36 via dct4_18" in out.stdout and "dct2_lee<32>" in out.stdout
+
+
+def test_host_affinity_helpers(tmp_path, monkeypatch):
+    """hostaffinity: cpulist parsing, PCI bus-id normalisation, and the no-op on single-node hosts (the GPU pool's VMs)."""
+    from mp3stego_b200 import hostaffinity as ha
+    assert ha._parse_cpulist("0-3,8,10-11") == [0, 1, 2, 3, 8, 10, 11]
+    assert ha._parse_cpulist("") == []
+    assert ha.gpu_numa_node("00000000:ZZ:00.0") == -1            # unknown device: the platform "does not say"
+    info = ha.bind_to_device("0000:00:00.0")
+    assert set(info) >= {"numa_nodes", "gpu_node", "bound", "cpus"}
+    if info["numa_nodes"] <= 1:
+        assert info["bound"] is False and "nothing to bind" in info["note"]
+    # two nodes, device without a node: ranks are spread round-robin and the process is bound to CPUs it is allowed to use
+    cpus = sorted(os.sched_getaffinity(0))
+    half = max(1, len(cpus) // 2)
+    monkeypatch.setattr(ha, "numa_nodes", lambda: {0: cpus[:half], 1: cpus[half:] or cpus[:half]})
+    monkeypatch.setattr(ha, "gpu_numa_node", lambda bdf: -1)
+    try:
+        info = ha.bind_to_device("0000:00:00.0", local_rank=1, local_world=2)
+        assert info["bound"] and info["node"] == 1 and os.sched_getaffinity(0) == set(cpus[half:] or cpus[:half])
+    finally:
+        os.sched_setaffinity(0, cpus)
