@@ -168,6 +168,7 @@ class CpuPort:
     def __init__(self, n_frames, procs, n_clips):
         from oracle import oracle as O
         O.build()
+        O.lib()       # loaded in the parent too (the workers inherit it at fork; the driver's record of loaded libraries sees it here)
         self.n_frames, self.procs, self.n = n_frames, procs, n_clips
         _CPU_INPUTS["pcm"] = [synth_pcm_host(n_frames, 4242 + i) for i in range(n_clips)]
         packed, off = random_payload_bits(n_clips, PAYLOAD_BITS_PER_FRAME * n_frames, 7)

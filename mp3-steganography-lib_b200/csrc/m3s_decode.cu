@@ -662,6 +662,10 @@ __global__ void k_strip(const uint8_t *__restrict__ bytes, int64_t total_bytes, 
     }
     int tail = n - head - 4 * nwords;
     if (lane < tail) S[dst + head + 4 * nwords + lane] = bytes[src + head + 4 * nwords + lane];
+    // the readers fetch whole 32-bit words and mask what lies beyond a frame's limit: give the word after a file's last payload byte
+    // defined contents (S is not cleared)
+    const M3sFileRec &fl = files[fr_file[g]];
+    if (g == fl.frame_base + fl.n_frames - 1 && lane < 8) S[dst + n + lane] = 0;
 }
 
 // ================================================================================================
@@ -707,6 +711,7 @@ __global__ void k_reservoir_fix(const uint8_t *__restrict__ bytes, const M3sFile
     const int own = (int)(meta & M3S_META_PAYLOAD_MASK);
     const int64_t src = fr_pos[g] + ((meta >> M3S_META_HDR_SHIFT) & 63);
     for (int i = lane; i < own; i += 32) S[dst + i] = bytes[src + i];
+    if (lane < 8) S[dst + own + lane] = 0;   // (the word the readers fetch and mask at the end of the slot's contents)
 }
 
 // end of a scan: per-file results and the totals -> mapped host memory

@@ -83,6 +83,7 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
     if (tid < 4) sm.quarter[tid] = T->quarter[tid];
     if (tid < 22) sm.pretab[tid] = T->pretab[tid];
     if (tid == 0) sm.sr_loaded = -1;
+    if (tid < 16) (&sm.info[0][0])[tid] = 0u;
     for (int i = tid; i < 2 * 51 * HF_ROW; i += HF_THREADS) (&sm.v[0][0][0])[i] = 0.f;
     // windowing (Frame.py:89-101): pcm[32 t + i] = sum_m V_{t-2m}[i] D[64 m + i] + V_{t-2m-1}[32 + i] D[64 m + 32 + i].  A V row holds the 32
     // distinct values W[l] = D[16 + l] (l < 16), W[l] = D[l - 16] (l >= 16) of the slot's 32-point DCT D; lane i reads
@@ -121,7 +122,7 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
         }
         // requantisation factors: the four slots go to the first four warps of the fetching threads (nt >= 128), two band entries per
         // lane; the unit-record fields are warp-uniform loads
-        if (tr < 128) {
+        if (tr < 128 && !(nch == 1 && (tr & 32))) {   // (a mono frame has no slots 1 and 3: their records are placeholders, their scalefactors unwritten)
             const int slot = tr >> 5;
             const M3sUnitRec *r = units + 4 * (int64_t)g + slot;
             const uint32_t a = r->a, b = r->b, c = r->c;
