@@ -884,8 +884,10 @@ k_huff(const uint8_t *__restrict__ S, const M3sUnitRec *__restrict__ units, int6
     if (u >= u_hi) return;
     const M3sUnitRec rec = units[u];
     uint32_t *out = spec + (u >> 2) * (288 * 4) + (u & 3);
-    if (!M3S_UC_VALID(rec.c)) {
+    if (!M3S_UC_VALID(rec.c)) {   // the second channel of a mono frame: zero spectrum, zero scalefactors
         for (int k = 0; k < 288; k++) out[4 * k] = 0u;
+        uint4 *so = (uint4 *)(sfout + u * M3S_SF_STRIDE);
+        so[0] = so[1] = so[2] = so[3] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const uint32_t a = rec.a, b = rec.b, c = rec.c;
@@ -1088,9 +1090,12 @@ int m3s_upload_cos36(const float *f, const double *d)
 {
     if (cudaMemcpyToSymbol(c_cos36_f, f, sizeof(float) * 18 * 18) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_cos36_d, d, sizeof(double) * 18 * 18) != cudaSuccess) return -1;
-    M3sFastConst fc;   // twiddles of the FP32 instantiation's fast transforms
+    M3sFastConst fc;   // twiddles of the fast transforms, in both precisions
     m3s_fast_const_build(fc);
     if (cudaMemcpyToSymbol(c_fast, &fc, sizeof fc) != cudaSuccess) return -1;
+    M3sFastConstD fcd;
+    m3s_fast_const_build(fcd);
+    if (cudaMemcpyToSymbol(c_fast_d, &fcd, sizeof fcd) != cudaSuccess) return -1;
     return 0;
 }
 
@@ -1849,34 +1854,38 @@ static int run_enqueue(m3s_ctx *h, M3sScanSet &ss, void *d_pcm, int16_t *d_spect
             (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)ss.units.p, (const uint8_t *)h->b_sf.p,                     \
             (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p, h->d_tab, (tabptr), d_pcm);                      \
     } while (0)
-#define M3S_LAUNCH_HYBRID_FAST1(OUT, FL, NCH, first, count)                                                                  \
+#define M3S_LAUNCH_HYBRID_FAST1(OUT, FL, NCH, R, TAB, tabptr, first, count)                                                 \
     do {                                                                                                                      \
-        const size_t smem = sizeof(HybFastSmem<OUT>);                                                                         \
-        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid_fast<OUT, FL, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        const size_t smem = sizeof(HybFastSmem<OUT, R>);                                                                      \
+        M3S_CUDA(h, cudaFuncSetAttribute(k_hybrid_fast<OUT, FL, NCH, R, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         M3S_KBEGIN(h, M3S_K_HYBRID);                                                                                          \
-        k_hybrid_fast<OUT, FL, NCH><<<(unsigned)(count), HF_THREADS, smem, s>>>(                                              \
+        k_hybrid_fast<OUT, FL, NCH, R, TAB><<<(unsigned)(count), HF_THREADS, smem, s>>>(                                      \
             (const uint32_t *)h->b_spec.p, (const M3sUnitRec *)ss.units.p, (const uint8_t *)h->b_sf.p,                        \
-            (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p + (first), h->d_tab, d_pcm);                         \
+            (const uint32_t *)ss.fr_meta.p, (const M3sWork *)h->b_work.p + (first), h->d_tab, (tabptr), d_pcm);               \
         M3S_LAUNCH_CHECK(h);                                                                                                  \
     } while (0)
     // the work list holds the stereo runs first, then the mono ones (see above): one launch per channel count that occurs
-#define M3S_LAUNCH_HYBRID_FAST(OUT, FL)                                                                                       \
+#define M3S_LAUNCH_HYBRID_FAST(OUT, FL, R, TAB, tabptr)                                                                       \
     do {                                                                                                                      \
-        if (n_stereo > 0) M3S_LAUNCH_HYBRID_FAST1(OUT, FL, 2, 0, n_stereo);                                                   \
-        if (work.size() > n_stereo) M3S_LAUNCH_HYBRID_FAST1(OUT, FL, 1, n_stereo, work.size() - n_stereo);                    \
+        if (n_stereo > 0) M3S_LAUNCH_HYBRID_FAST1(OUT, FL, 2, R, TAB, tabptr, 0, n_stereo);                                   \
+        if (work.size() > n_stereo) M3S_LAUNCH_HYBRID_FAST1(OUT, FL, 1, R, TAB, tabptr, n_stereo, work.size() - n_stereo);    \
     } while (0)
-    static const bool direct_f32 = getenv("M3S_HYBRID_DIRECT") != nullptr;   // A/B: the direct-form FP32 kernel of round 1
-    if (exact) {
-        if (fl) M3S_LAUNCH_HYBRID(double, M3sDevTablesD, true, h->d_tab_f64);
-        else M3S_LAUNCH_HYBRID(double, M3sDevTablesD, false, h->d_tab_f64);
+    static const bool direct = getenv("M3S_HYBRID_DIRECT") != nullptr;   // A/B and cross-check: the direct-form kernels of round 1
+    if (direct) {
+        if (exact) {
+            if (fl) M3S_LAUNCH_HYBRID(double, M3sDevTablesD, true, h->d_tab_f64);
+            else M3S_LAUNCH_HYBRID(double, M3sDevTablesD, false, h->d_tab_f64);
+        } else {
+            if (fl) M3S_LAUNCH_HYBRID(float, M3sDevTables, true, h->d_tab);
+            else M3S_LAUNCH_HYBRID(float, M3sDevTables, false, h->d_tab);
+        }
         M3S_LAUNCH_CHECK(h);
-    } else if (direct_f32) {
-        if (fl) M3S_LAUNCH_HYBRID(float, M3sDevTables, true, h->d_tab);
-        else M3S_LAUNCH_HYBRID(float, M3sDevTables, false, h->d_tab);
-        M3S_LAUNCH_CHECK(h);
+    } else if (exact) {
+        if (fl) M3S_LAUNCH_HYBRID_FAST(float, true, double, M3sDevTablesD, h->d_tab_f64);
+        else M3S_LAUNCH_HYBRID_FAST(int16_t, false, double, M3sDevTablesD, h->d_tab_f64);
     } else {
-        if (fl) M3S_LAUNCH_HYBRID_FAST(float, true);
-        else M3S_LAUNCH_HYBRID_FAST(int16_t, false);
+        if (fl) M3S_LAUNCH_HYBRID_FAST(float, true, float, M3sDevTables, h->d_tab);
+        else M3S_LAUNCH_HYBRID_FAST(int16_t, false, float, M3sDevTables, h->d_tab);
     }
     return M3S_OK;
 }

@@ -25,20 +25,20 @@
 #define HF_XS 608   // floats per (granule, channel) spectrum: 32 subbands x 19
 #define HF_ROW 36   // floats per 32-wide row of tt / v
 
-template <typename OUT>
+template <typename OUT, typename R>
 struct HybFastSmem {
     uint4 spec[288];                   // integer spectra of ONE frame: [pair] = (x, y) int16 of slots 0..3 (slot = 2 gr + ch)
-    float xr[2][2][2][HF_XS];          // [buffer][gr][ch]: requantised spectrum, sample s at s + s / 18
-    float tt[2][2][18][HF_ROW];        // [gr][ch][slot][subband]: IMDCT output = matrixing input
-    float v[2][51][HF_ROW];            // [ch][row]: per slot the 32 distinct matrixing outputs; 15 rows of history + 2 x 18 new
+    R xr[2][2][2][HF_XS];          // [buffer][gr][ch]: requantised spectrum, sample s at s + s / 18
+    R tt[2][2][18][HF_ROW];        // [gr][ch][slot][subband]: IMDCT output = matrixing input
+    R v[2][51][HF_ROW];            // [ch][row]: per slot the 32 distinct matrixing outputs; 15 rows of history + 2 x 18 new
     OUT stage[2][1152];                // PCM of one frame, channel-major (interleaved when it is stored)
-    float wcoef[16][32];               // windowing: per lane its 8 + 8 signed window coefficients (see the kernel)
-    float pow43[256];
-    float scale[4][64];                // per slot: 2^(e4/4) of long sfb 0..21 | short (sfb * 3 + window) at 22..60
-    float sine[4][36];
-    float cos12[12][8];
-    float cs[8], ca[8];
-    float quarter[4];
+    R wcoef[16][32];               // windowing: per lane its 8 + 8 signed window coefficients (see the kernel)
+    R pow43[256];
+    R scale[4][64];                // per slot: 2^(e4/4) of long sfb 0..21 | short (sfb * 3 + window) at 22..60
+    R sine[4][36];
+    R cos12[12][8];
+    R cs[8], ca[8];
+    R quarter[4];
     uint32_t info[4][4];               // ring over frames (g & 3) x slot: block_type [0:2) | mixed [2]
     uint16_t reorder[576];             // short-block scatter: padded destination | 0x8000 = store zero
     uint8_t band2[2][288];             // pair -> scale index: [0] long sfb, [1] 22 + short sfb * 3 + window
@@ -51,23 +51,35 @@ __device__ __forceinline__ float hf_pow2i(int e)
     e = e < -126 ? -126 : (e > 127 ? 127 : e);
     return __int_as_float((e + 127) << 23);
 }
+// the pieces that differ between the FP32 instantiation and the float64 one (M3S_DEC_EXACT)
+__device__ __forceinline__ float hf_scale(float quarter, int e4) { return quarter * hf_pow2i(e4 >> 2); }
+__device__ __forceinline__ double hf_scale(double quarter, int e4) { return quarter * scalbn(1.0, e4 >> 2); }
+__device__ __forceinline__ float hf_pow43_big(float, int ax) { return (float)ax * cbrtf((float)ax); }
+__device__ __forceinline__ double hf_pow43_big(double, int ax) { return pow((double)ax, 4.0 / 3.0); }
+__device__ __forceinline__ float hf_signed(float m, int x) { return __int_as_float(__float_as_int(m) | (x & 0x80000000)); }   // m >= 0: OR in the sign of x
+__device__ __forceinline__ double hf_signed(double m, int x) { return x < 0 ? -m : m; }
+__device__ __forceinline__ int hf_to_int(float o) { return __float2int_rz(o); }
+__device__ __forceinline__ int hf_to_int(double o) { return __double2int_rz(o); }
 
 // x[i] of the 36-point IMDCT from the 18 DCT-IV values (the index folds once the caller's loop is unrolled)
-__device__ __forceinline__ float hf_imdct_at(const float (&c)[18], int i)
+template <typename R>
+__device__ __forceinline__ R hf_imdct_at(const R (&c)[18], int i)
 {
     return i < 9 ? c[i + 9] : (i <= 26 ? -c[26 - i] : -c[i - 27]);
 }
 
 // The channel count is a template parameter (the host launches the stereo and the mono runs of a wave separately): no register
 // for it, no per-sample tests.
-template <typename OUT, bool FLOAT_OUT, int nch>
-__global__ void __launch_bounds__(HF_THREADS, 3)
+// R = float: the default path (<= 1 LSB).  R = double (M3S_DEC_EXACT): the same kernel in float64 -- the int16 samples then equal the
+// reference's (which is float64 end to end) on every golden stream; TF holds the hybrid tables in precision R.
+template <typename OUT, bool FLOAT_OUT, int nch, typename R, typename TAB>
+__global__ void __launch_bounds__(HF_THREADS, sizeof(R) == 4 ? 3 : 1)
 k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ units, const uint8_t *__restrict__ sfin,
               const uint32_t *__restrict__ fr_meta, const M3sWork *__restrict__ work, const M3sDevTables *__restrict__ T,
-              void *__restrict__ pcm_out)
+              const TAB *__restrict__ TF, void *__restrict__ pcm_out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HybFastSmem<OUT> &sm = *reinterpret_cast<HybFastSmem<OUT> *>(smem_raw);
+    HybFastSmem<OUT, R> &sm = *reinterpret_cast<HybFastSmem<OUT, R> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const M3sWork wk = work[blockIdx.x];
     // (frame indices are wave-relative and fit 32 bits: they stay `int` to keep the loop-carried state small)
@@ -76,28 +88,29 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
     const uint4 *spec4 = (const uint4 *)spec;
 
     // ---- one-time table staging
-    for (int i = tid; i < 12 * 8; i += HF_THREADS) (&sm.cos12[0][0])[i] = (&T->imdct_cos12[0][0])[i];
-    for (int i = tid; i < 4 * 36; i += HF_THREADS) (&sm.sine[0][0])[i] = (&T->sine_block[0][0])[i];
-    for (int i = tid; i < 256; i += HF_THREADS) sm.pow43[i] = T->pow43[i];
-    if (tid < 8) { sm.cs[tid] = T->alias_cs[tid]; sm.ca[tid] = T->alias_ca[tid]; }
-    if (tid < 4) sm.quarter[tid] = T->quarter[tid];
+    for (int i = tid; i < 12 * 8; i += HF_THREADS) (&sm.cos12[0][0])[i] = (&TF->imdct_cos12[0][0])[i];
+    for (int i = tid; i < 4 * 36; i += HF_THREADS) (&sm.sine[0][0])[i] = (&TF->sine_block[0][0])[i];
+    for (int i = tid; i < 256; i += HF_THREADS) sm.pow43[i] = TF->pow43[i];
+    if (tid < 8) { sm.cs[tid] = TF->alias_cs[tid]; sm.ca[tid] = TF->alias_ca[tid]; }
+    if (tid < 4) sm.quarter[tid] = TF->quarter[tid];
     if (tid < 22) sm.pretab[tid] = T->pretab[tid];
     if (tid == 0) sm.sr_loaded = -1;
     if (tid < 16) (&sm.info[0][0])[tid] = 0u;
-    for (int i = tid; i < 2 * 51 * HF_ROW; i += HF_THREADS) (&sm.v[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * 51 * HF_ROW; i += HF_THREADS) (&sm.v[0][0][0])[i] = (R)0;
     // windowing (Frame.py:89-101): pcm[32 t + i] = sum_m V_{t-2m}[i] D[64 m + i] + V_{t-2m-1}[32 + i] D[64 m + 32 + i].  A V row holds the 32
     // distinct values W[l] = D[16 + l] (l < 16), W[l] = D[l - 16] (l >= 16) of the slot's 32-point DCT D; lane i reads
     // V[i] = +W[i] | 0 | -W[32 - i] and V[32 + i] = -W[0] | -W[32 - i] | -W[i]; the signs are folded into its 16 window coefficients.
     for (int e = tid; e < 16 * 32; e += HF_THREADS) {
         const int m = e >> 5, i = e & 31;
-        const float sA = i < 16 ? 1.f : (i == 16 ? 0.f : -1.f);
-        // (the int16 path folds MP3Parser.write_to_wav's factor 32767 into the coefficients: one multiply per sample less)
-        const float k16 = FLOAT_OUT ? 1.f : 32767.f;
-        sm.wcoef[m][i] = k16 * (m < 8 ? sA * T->synth_d[64 * m + i] : -T->synth_d[64 * (m - 8) + 32 + i]);
+        const R sA = i < 16 ? (R)1 : (i == 16 ? (R)0 : (R)-1);
+        // (the FP32 int16 path folds MP3Parser.write_to_wav's factor 32767 into the coefficients: one multiply per sample less; the
+        //  float64 path multiplies the finished sample, as the reference does)
+        const R k16 = (FLOAT_OUT || sizeof(R) == 8) ? (R)1 : (R)32767;
+        sm.wcoef[m][i] = k16 * (m < 8 ? sA * TF->synth_d[64 * m + i] : -TF->synth_d[64 * (m - 8) + 32 + i]);
     }
-    float ovl[18];   // IMDCT warps: windowed second half of the previous granule of (channel = warp, subband = lane)
+    R ovl[18];   // IMDCT warps: windowed second half of the previous granule of (channel = warp, subband = lane)
 #pragma unroll
-    for (int i = 0; i < 18; i++) ovl[i] = 0.f;
+    for (int i = 0; i < 18; i++) ovl[i] = (R)0;
 
     // ---- per-frame staging: spectra, requantisation factors and block types of frame g, by threads [t0, t0 + nt)
     auto fetch_frame = [&](int g, int t0, int nt) {
@@ -137,7 +150,7 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                     const int q = idx - 22, sfb = q / 3, wnd = q - 3 * sfb;
                     e4 = gg - 210 - 8 * (int)M3S_UC_SBG(c, wnd) - mult4 * (int)sf[M3S_SF_SHORT + 13 * wnd + sfb];
                 }
-                sm.scale[slot][idx] = sm.quarter[e4 & 3] * hf_pow2i(e4 >> 2);
+                sm.scale[slot][idx] = hf_scale(sm.quarter[e4 & 3], e4);
             }
             if ((tr & 31) == 0) sm.info[g & 3][slot] = M3S_UA_BT(a) | (M3S_UB_MIXED(b) << 2);
         }
@@ -147,24 +160,24 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
 
     // ---- requantize + MS + reorder of frame g into xr[buf] (Frame.py:157-218, :561-572, :574-602) by the 192 threads [t0, t0 + 192):
     //      96 threads per granule, three pairs each; everything that depends on the granule only is hoisted out of the pair loop
-    auto requant_pair = [&](uint32_t wv, float sc, float &vx, float &vy) {
+    auto requant_pair = [&](uint32_t wv, R sc, R &vx, R &vy) {
         const int x = (int)(int16_t)(wv & 0xFFFFu), y = (int)wv >> 16;
         const int ax = x < 0 ? -x : x, ay = y < 0 ? -y : y;
-        float mx, my;
+        R mx, my;
         if ((ax | ay) < 256) { mx = sm.pow43[ax]; my = sm.pow43[ay]; }
         else {
-            mx = ax < 256 ? sm.pow43[ax] : (float)ax * cbrtf((float)ax);
-            my = ay < 256 ? sm.pow43[ay] : (float)ay * cbrtf((float)ay);
+            mx = ax < 256 ? sm.pow43[ax] : hf_pow43_big((R)0, ax);
+            my = ay < 256 ? sm.pow43[ay] : hf_pow43_big((R)0, ay);
         }
-        vx = __int_as_float(__float_as_int(mx * sc) | (x & 0x80000000));   // sign(x) |x|^(4/3) 2^(e4/4): the product is >= 0, OR in the sign
-        vy = __int_as_float(__float_as_int(my * sc) | (y & 0x80000000));
+        vx = hf_signed(mx * sc, x);   // sign(x) |x|^(4/3) 2^(e4/4)
+        vy = hf_signed(my * sc, y);
     };
-    auto requant_store = [&](float *X, bool reord, int p, float v0, float v1) {
+    auto requant_store = [&](R *X, bool reord, int p, R v0, R v1) {
         if (reord) {
             const uint32_t d01 = ((const uint32_t *)sm.reorder)[p];
             const uint32_t d0 = d01 & 0xFFFFu, d1 = d01 >> 16;
-            X[d0 & 0x3FFu] = (d0 & 0x8000u) ? 0.f : v0;
-            X[d1 & 0x3FFu] = (d1 & 0x8000u) ? 0.f : v1;
+            X[d0 & 0x3FFu] = (d0 & 0x8000u) ? (R)0 : v0;
+            X[d1 & 0x3FFu] = (d1 & 0x8000u) ? (R)0 : v1;
         } else {
             const int pos = 2 * p + p / 9;   // samples 2 p and 2 p + 1 lie in the same subband; 19 floats per subband
             X[pos] = v0;
@@ -180,19 +193,19 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
         const bool sh0 = (inf0 & 3u) == 2u, sh1 = (inf1 & 3u) == 2u;
         const bool re0 = sh0 || (inf0 & 4u), re1 = sh1 || (inf1 & 4u);
         const uint8_t *band0 = sm.band2[sh0], *band1 = sm.band2[sh1];
-        const float *sc0 = sm.scale[2 * gr], *sc1 = sm.scale[2 * gr + 1];
-        float *X0 = sm.xr[buf][gr][0], *X1 = sm.xr[buf][gr][1];
+        const R *sc0 = sm.scale[2 * gr], *sc1 = sm.scale[2 * gr + 1];
+        R *X0 = sm.xr[buf][gr][0], *X1 = sm.xr[buf][gr][1];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             const int p = t + 96 * j;
             const uint2 w2 = ((const uint2 *)&sm.spec[p])[gr];
-            float a0, a1, b0 = 0.f, b1 = 0.f;
+            R a0, a1, b0 = (R)0, b1 = (R)0;
             requant_pair(w2.x, sc0[band0[p]], a0, a1);
             if (nch == 2) requant_pair(w2.y, sc1[band1[p]], b0, b1);
             if (ms) {   // (M + S) / SQRT2, (M - S) / SQRT2 (Frame.py:568-572)
-                const float m0 = a0, m1 = a1;
-                a0 = (m0 + b0) * 0.70710678118654752f; b0 = (m0 - b0) * 0.70710678118654752f;
-                a1 = (m1 + b1) * 0.70710678118654752f; b1 = (m1 - b1) * 0.70710678118654752f;
+                const R m0 = a0, m1 = a1, rs2 = (R)0.70710678118654752;
+                a0 = (m0 + b0) * rs2; b0 = (m0 - b0) * rs2;
+                a1 = (m1 + b1) * rs2; b1 = (m1 - b1) * rs2;
             }
             requant_store(X0, re0, p, a0, a1);
             if (nch == 2) requant_store(X1, re1, p, b0, b1);
@@ -249,9 +262,10 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
         // ================================================================ phase A
         if (g > g_begin && tid >= 64) {   // slide the V history: rows 36..50 -> 0..14 (nobody else touches V in this phase; the IMDCT
                                           // warps, the phase's critical path, are left out of it)
-            for (int idx = tid - 64; idx < nch * (15 * HF_ROW / 4); idx += HF_THREADS - 64) {
-                const int ch = idx >= 15 * HF_ROW / 4, r_ = idx - ch * (15 * HF_ROW / 4);
-                ((float4 *)&sm.v[ch][0][0])[r_] = ((const float4 *)&sm.v[ch][36][0])[r_];
+            constexpr int CH16 = 15 * HF_ROW * (int)sizeof(R) / 16;   // 16-byte chunks per channel
+            for (int idx = tid - 64; idx < nch * CH16; idx += HF_THREADS - 64) {
+                const int ch = idx >= CH16, r_ = idx - ch * CH16;
+                ((uint4 *)&sm.v[ch][0][0])[r_] = ((const uint4 *)&sm.v[ch][36][0])[r_];
             }
         }
         if (warp < 2) {
@@ -261,9 +275,9 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                 for (int gr = 0; gr < 2; gr++) {
                     const uint32_t inf = sm.info[g & 3][2 * gr + ch];
                     const int bt = (int)(inf & 3u);
-                    const float *X = sm.xr[buf][gr][ch];
-                    float *ttc = &sm.tt[gr][ch][0][sb];
-                    float x[18];
+                    const R *X = sm.xr[buf][gr][ch];
+                    R *ttc = &sm.tt[gr][ch][0][sb];
+                    R x[18];
 #pragma unroll
                     for (int k = 0; k < 18; k++) x[k] = X[19 * sb + k];
                     if (bt != 2) {
@@ -277,12 +291,12 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                                 for (int i = 0; i < 8; i++) x[17 - i] = x[17 - i] * sm.cs[i] - X[19 * (sb + 1) + i] * sm.ca[i];
                             }
                         }
-                        float c[18];
-                        dct4_18(x, c);
-                        const float *w = sm.sine[bt];
+                        R c[18];
+                        dct4_18<R>(x, c);
+                        const R *w = sm.sine[bt];
 #pragma unroll
                         for (int i = 0; i < 18; i++) {
-                            float o = fmaf(hf_imdct_at(c, i), w[i], ovl[i]);
+                            R o = m3s_fma(hf_imdct_at(c, i), w[i], ovl[i]);
                             if ((i & 1) && (sb & 1)) o = -o;       // frequency inversion (Frame.py:624-631)
                             ttc[HF_ROW * i] = o;
                             ovl[i] = hf_imdct_at(c, 18 + i) * w[18 + i];
@@ -291,43 +305,43 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                         // three 12-point IMDCTs, windowed and placed at 6 / 12 / 18 with overlap (Frame.py:135-148)
 #pragma unroll
                         for (int i = 0; i < 18; i++) {
-                            float acc = 0.f;
+                            R acc = (R)0;
                             if (i >= 6) {
                                 const int w_hi = (i - 6) / 6, i_hi = i - 6 - 6 * w_hi;
                                 if (w_hi < 3) {
-                                    float a2 = 0.f;
+                                    R a2 = (R)0;
 #pragma unroll
-                                    for (int k = 0; k < 6; k++) a2 = fmaf(x[6 * w_hi + k], sm.cos12[i_hi][k], a2);
+                                    for (int k = 0; k < 6; k++) a2 = m3s_fma(x[6 * w_hi + k], sm.cos12[i_hi][k], a2);
                                     acc += a2 * sm.sine[2][i_hi];
                                 }
                                 const int w_lo = w_hi - 1;
                                 if (w_lo >= 0) {
-                                    float a2 = 0.f;
+                                    R a2 = (R)0;
 #pragma unroll
-                                    for (int k = 0; k < 6; k++) a2 = fmaf(x[6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
+                                    for (int k = 0; k < 6; k++) a2 = m3s_fma(x[6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
                                     acc += a2 * sm.sine[2][i_hi + 6];
                                 }
                             }
-                            float o = acc + ovl[i];
+                            R o = acc + ovl[i];
                             if ((i & 1) && (sb & 1)) o = -o;
                             ttc[HF_ROW * i] = o;
                         }
                         // second half -> the next granule's overlap (every ovl[i] was consumed above)
 #pragma unroll
                         for (int i = 18; i < 36; i++) {
-                            float acc = 0.f;
+                            R acc = (R)0;
                             if (i < 30) {
                                 const int w_hi = (i - 6) / 6, i_hi = i - 6 - 6 * w_hi;
                                 if (w_hi < 3) {
-                                    float a2 = 0.f;
+                                    R a2 = (R)0;
 #pragma unroll
-                                    for (int k = 0; k < 6; k++) a2 = fmaf(x[6 * w_hi + k], sm.cos12[i_hi][k], a2);
+                                    for (int k = 0; k < 6; k++) a2 = m3s_fma(x[6 * w_hi + k], sm.cos12[i_hi][k], a2);
                                     acc += a2 * sm.sine[2][i_hi];
                                 }
                                 const int w_lo = w_hi - 1;
-                                float a2 = 0.f;
+                                R a2 = (R)0;
 #pragma unroll
-                                for (int k = 0; k < 6; k++) a2 = fmaf(x[6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
+                                for (int k = 0; k < 6; k++) a2 = m3s_fma(x[6 * w_lo + k], sm.cos12[i_hi + 6][k], a2);
                                 acc += a2 * sm.sine[2][i_hi + 6];
                             }
                             ovl[i - 18] = acc;
@@ -342,19 +356,35 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
         // ================================================================ phase B
         if (tid < nch * 36) {   // matrixing: thread = (granule, channel, slot), a 32-point DCT-II in registers (Frame.py:81-87)
             const int t = tid % 18, gc = tid / 18, ch = gc % nch, gr = gc / nch;
-            float S[32];
-            const float4 *row = (const float4 *)sm.tt[gr][ch][t];
+            R S[32];
+            const R *row = sm.tt[gr][ch][t];
+            R *vo = sm.v[ch][15 + 18 * gr + t];
+            if constexpr (sizeof(R) == 4) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float4 q = row[j];
-                S[4 * j] = q.x; S[4 * j + 1] = q.y; S[4 * j + 2] = q.z; S[4 * j + 3] = q.w;
+                for (int j = 0; j < 8; j++) {
+                    const float4 q = ((const float4 *)row)[j];
+                    S[4 * j] = q.x; S[4 * j + 1] = q.y; S[4 * j + 2] = q.z; S[4 * j + 3] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const double2 q = ((const double2 *)row)[j];
+                    S[2 * j] = q.x; S[2 * j + 1] = q.y;
+                }
             }
-            dct2_lee<32>(S);
-            float4 *vo = (float4 *)sm.v[ch][15 + 18 * gr + t];
+            dct2_lee<32, R>(S);
+            if constexpr (sizeof(R) == 4) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                vo[j] = make_float4(S[16 + 4 * j], S[17 + 4 * j], S[18 + 4 * j], S[19 + 4 * j]);
-                vo[4 + j] = make_float4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]);
+                for (int j = 0; j < 4; j++) {
+                    ((float4 *)vo)[j] = make_float4(S[16 + 4 * j], S[17 + 4 * j], S[18 + 4 * j], S[19 + 4 * j]);
+                    ((float4 *)vo)[4 + j] = make_float4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    ((double2 *)vo)[j] = make_double2(S[16 + 2 * j], S[17 + 2 * j]);
+                    ((double2 *)vo)[8 + j] = make_double2(S[2 * j], S[2 * j + 1]);
+                }
             }
         }
         if (warp >= 3) {   // frame f - 1's PCM goes out of its staging tile, frame f + 2 comes in
@@ -369,24 +399,26 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
             if (ch < nch) {
                 const int idxA = lane < 16 ? lane : (lane == 16 ? 0 : 32 - lane);
                 const int idxB = lane == 0 ? 0 : (lane < 16 ? 32 - lane : lane);
-                const float *va = &sm.v[ch][1 + 18 * gr + par][idxA], *vb = &sm.v[ch][18 * gr + par][idxB];
-                float a[16], b[16], dA[8], dB[8];
+                const R *va = &sm.v[ch][1 + 18 * gr + par][idxA], *vb = &sm.v[ch][18 * gr + par][idxB];
+                R a[16], b[16], dA[8], dB[8];
 #pragma unroll
                 for (int m = 0; m < 8; m++) { dA[m] = sm.wcoef[m][lane]; dB[m] = sm.wcoef[8 + m][lane]; }
 #pragma unroll
                 for (int d = 0; d < 16; d++) { a[d] = va[2 * HF_ROW * d]; b[d] = vb[2 * HF_ROW * d]; }
 #pragma unroll
                 for (int q = 0; q < 9; q++) {
-                    float acc0 = 0.f, acc1 = 0.f;
+                    R acc0 = (R)0, acc1 = (R)0;
 #pragma unroll
                     for (int m = 0; m < 8; m++) {
-                        acc0 = fmaf(a[q - m + 7], dA[m], acc0);
-                        acc1 = fmaf(b[q - m + 7], dB[m], acc1);
+                        acc0 = m3s_fma(a[q - m + 7], dA[m], acc0);
+                        acc1 = m3s_fma(b[q - m + 7], dB[m], acc1);
                     }
-                    const float o = acc0 + acc1;
+                    const R o = acc0 + acc1;
                     OUT *so = &sm.stage[ch][gr * 576 + 32 * par + lane];
+                    // (pcm * 32767).astype(int16): truncate, keep the low 16 bits (A.D8); FP32 carries the factor in its window coefficients
                     if (FLOAT_OUT) so[64 * q] = (OUT)o;
-                    else so[64 * q] = (OUT)(int16_t)__float2int_rz(o);   // (pcm * 32767).astype(int16): truncate, keep the low 16 bits (A.D8)
+                    else if constexpr (sizeof(R) == 8) so[64 * q] = (OUT)(int16_t)hf_to_int(o * (R)32767);
+                    else so[64 * q] = (OUT)(int16_t)hf_to_int(o);
                 }
             }
             staged = f - warm;
