@@ -273,6 +273,224 @@ k_enc_analysis(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ c
 }
 
 // ================================================================================================
+// E1, folded form (the one that ships; M3S_ENC_ANALYSIS_DIRECT=1 selects the kernel above as a cross-check).
+//
+// The matrixing's 32 x 64 matrix holds cosines of a 128-point grid: a column carries at most 16 distinct magnitudes (920 distinct
+// (|v|, j) pairs for 2,025 non-zero entries), and  mul(-v, y) = -mul(v, y) - [(v y) mod 2^32 != 0].  So ONE truncated product per
+// distinct magnitude serves every band that uses +v or -v, exactly, as long as the correction bit is known -- it is 1 whenever the
+// low 26 bits of y are not all zero (tz(v) <= 6 for every entry).  tools/gen_enc_fold.py turns the tables into straight-line code
+// (m3s_enc_fold_gen.cuh: products once, then signed adds into accumulators whose start values carry the corrections); where a y
+// breaks the assumption (silence, mostly) the missing [(v y) mod 2^32 == 0] terms are added afterwards.  The MDCT's 18 x 36 table
+// folds the same way (488 distinct of 648).  Truncated products per granule-channel: 66,816 -> 9,216 + 16,560 + 15,616 = 41,392.
+//
+// Sharing products needs one thread to own ALL outputs of its inputs with the coefficient pattern known at compile time, so the
+// roles turn round: in the filterbank lane = time slot (the filterbank is stateless per slot: the CTA walks its run of granules as
+// a STREAM of slots, one per thread and block, and cuts the 18-slot granules from a ring of subband samples as they complete), in
+// the MDCT lane = band and warp = granule.  Straight-line code is big (~90 KB, far beyond the 32 KB instruction cache of an SM), so
+// the instruction fetches must be shared: every warp of the CTA runs the SAME code at the same time, and the CTAs are large.
+// Measured (kernel ms per 1.378 M frames; direct form 60.1): one column subset per warp, i.e. four code streams per 4-warp CTA: 94.2
+// (10 of 11 stall cycles "no instruction"); all columns per thread, 4 warps x 4 CTAs per SM: 51.5 (still 3.4 of 10.4); 8 warps x
+// 2 CTAs: **46.4** (0.14); 16 warps x 1 CTA: 52.6 (nothing left to cover the barriers).  Barriers inside the straight-line code
+// to keep the warps aligned did not help (47.6 - 51.2).
+// ================================================================================================
+#define M3S_FOLD_FN __device__ __forceinline__
+#define M3S_FOLD_MULHI(a, b) __mulhi((a), (b))
+#include "m3s_enc_fold_gen.cuh"
+
+__constant__ int32_t c_enc_fl[32][64];    // MP3Encoder filter matrix (:544-555) and analysis window (tables.py:34-78) for the
+__constant__ int32_t c_enc_win[512];      // correction pass of a slot whose fast path reported `bad`
+
+template <int WARPS>   // warps per CTA = 32-slot groups per block
+struct Ana3Smem {
+    static constexpr int SLOTS = 32 * WARPS;   // slots per block: one per thread
+    static constexpr int XP = 15 + SLOTS;      // columns of the sample tile: 15 slots of history + the block's slots; odd: conflict-free fills
+    static constexpr int RING = SLOTS + 36;    // subband-sample ring: a granule reaches back 36 slots from its end, a block adds SLOTS more
+    static constexpr int RUN = SLOTS * 9 / 18 - 1;   // granules per CTA: with the warm-up granule 9 blocks exactly
+    int32_t xT[32][XP];                // sample 32 u + r of this channel at [r][u - u0], as int16 << 16
+    int32_t sb[RING + 1][33];          // [ring row][band] subband samples; row RING stays zero (the state in front of a clip)
+    int32_t mf[WARPS][576];            // per warp: [band * 18 + k] MDCT lines of the granule it works on
+    uint32_t bins[WARPS][24];          // per warp: 0..20 band energies, 21 total, 22 xrmax
+    uint32_t en_thresh[32];
+    uint8_t sfb[576];
+    int32_t ca[8], cs[8];
+};
+
+template <int ANA3_XP>
+struct Ana3LoadX {   // sample k of input j of the windowing: x[32 t + 31 - j - 64 k] of this lane's slot t (p = &xT[0][column of t])
+    const int32_t *p;
+    __device__ __forceinline__ int32_t operator()(int j, int k) const
+    {
+        return j < 32 ? p[(31 - j) * ANA3_XP - 2 * k] : p[(63 - j) * ANA3_XP - 2 * k - 1];
+    }
+};
+template <int ANA3_RING>
+struct Ana3LoadSb {  // input j of the MDCT: slot j of the previous granule (j < 18) or slot j - 18 of the current one, band = lane
+    const int32_t *sb; int prev, cur;   // ring rows of the two granules' first slots; prev = ANA3_RING: the zero row for every j
+    __device__ __forceinline__ int32_t operator()(int j) const
+    {
+        int r;
+        if (j < 18) { r = prev + j; if (prev == ANA3_RING) r = ANA3_RING; else if (r >= ANA3_RING) r -= ANA3_RING; }
+        else { r = cur + j - 18; if (r >= ANA3_RING) r -= ANA3_RING; }
+        return sb[r * 33];
+    }
+};
+
+// GUARD: how shared products are protected from ptxas's multiply-add folding (m3s_enc_fold_gen.cuh); WARPS: warps per CTA
+template <int GUARD, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 16 / WARPS)
+k_enc_analysis_fold(const int16_t *__restrict__ pcm, const M3sEncClip *__restrict__ clips, const M3sEncWork *__restrict__ work,
+                    const M3sDevTables *__restrict__ T, const EncTables *__restrict__ ET, int sr_idx, int64_t chunk_frame0,
+                    int32_t *__restrict__ mdct, M3sEncStats *__restrict__ stats, const uint32_t zero)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef Ana3Smem<WARPS> Smem;
+    constexpr int ANA3_WARPS = WARPS, ANA3_THREADS = 32 * WARPS, ANA3_SLOTS = Smem::SLOTS, ANA3_XP = Smem::XP, ANA3_RING = Smem::RING;
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const M3sEncWork wk = work[blockIdx.x];
+    const M3sEncClip cl = clips[wk.clip];
+    const int ch = wk.ch;
+    for (int i = tid; i < 576; i += ANA3_THREADS) S.sfb[i] = T->long_sfb_of[sr_idx][i];
+    if (tid < 8) { S.ca[tid] = T->enc_ca[tid]; S.cs[tid] = T->enc_cs[tid]; }
+    if (tid < 32) S.en_thresh[tid] = ET->en_thresh[tid];
+    if (tid < 24 * ANA3_WARPS) (&S.bins[0][0])[tid] = 0u;
+    if (tid < 33) S.sb[ANA3_RING][tid] = 0;
+
+    const uint32_t *pcm32 = (const uint32_t *)(pcm + cl.pcm_base);  // one stereo sample per word (pcm_base is even)
+    const int sh = ch ? 0 : 16;                                     // channel 0 = low half of the word
+    const int g_end = wk.g_first + wk.count;
+    const int t_begin = wk.g_first > 0 ? 18 * (wk.g_first - 1) : 0; // first slot of the stream: one warm-up granule in front of the run
+    const int t_stop = 18 * g_end;                                  // slots of the run end here
+    const int64_t s_end = (int64_t)g_end * 576;                     // ... and so do the samples it may read (clip / chunk staging)
+    const int n_blocks = (t_stop - t_begin + ANA3_SLOTS - 1) / ANA3_SLOTS;
+    int g_next = wk.g_first;
+    for (int k = 0; k < n_blocks; k++) {
+        const int t0 = t_begin + ANA3_SLOTS * k;
+        // ---- sample tile: slots t0 - 15 .. t0 + ANA3_SLOTS - 1, transposed (row = sample within its slot, column = slot)
+        {
+            const int64_t n0 = ((int64_t)t0 - 15) * 32;
+#pragma unroll 4
+            for (int i = tid; i < 32 * ANA3_XP; i += ANA3_THREADS) {
+                const int64_t n = n0 + i;
+                const uint32_t w = (n >= 0 && n < s_end) ? __ldg(pcm32 + n) : 0u;
+                S.xT[i & 31][i >> 5] = (int32_t)((w << sh) & 0xFFFF0000u);
+            }
+        }
+        __syncthreads();   // also: every warp has left the MDCT phase of the previous block, the ring rows below are free
+        // ---- windowing + matrixing of slot t0 + tid: y_j = sum_k mul(x[32 t + 31 - j - 64 k], enwindow[j + 64 k])   (:337-356),
+        //      s_b = sum_j mul(fl[b][j], y_j); odd bands of odd slots negated   (:358-368, :678-679)
+        if (t0 + 32 * warp < t_stop) {   // warp-uniform
+            uint32_t acc[32], bad, any;
+            const Ana3LoadX<ANA3_XP> ld{&S.xT[0][15 + tid]};
+            m3s_matrix_fold<GUARD>(ld, zero, acc, bad, any);
+            if (bad) {   // some y has 26 zero low bits: its negative uses were charged a correction they may not owe
+                if (any == 0u) {
+#pragma unroll
+                    for (int b = 0; b < 32; b++) acc[b] = 0u;
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < 64; j++) {
+                        const int32_t *xp = j < 32 ? ld.p + (31 - j) * ANA3_XP : ld.p + (63 - j) * ANA3_XP - 1;
+                        uint32_t ys = 0u;
+#pragma unroll
+                        for (int kk = 0; kk < 8; kk++) ys += (uint32_t)__mulhi(xp[-2 * kk], c_enc_win[j + 64 * kk]);
+                        if ((ys & M3S_MATRIX_FOLD_YMASK) != 0u) continue;
+#pragma unroll
+                        for (int b = 0; b < 32; b++) {
+                            const int32_t v = c_enc_fl[b][j];
+                            acc[b] += (uint32_t)(v < 0 && (uint32_t)v * ys == 0u);
+                        }
+                    }
+                }
+            }
+            int32_t *row = &S.sb[(ANA3_SLOTS * k + tid) % ANA3_RING][0];
+            const uint32_t odd = 0u - (uint32_t)(lane & 1);   // t_begin and the block size are even: slot parity = lane parity
+#pragma unroll
+            for (int b = 0; b < 32; b++) row[b] = (int32_t)((b & 1) ? (acc[b] ^ odd) - odd : acc[b]);
+        }
+        __syncthreads();
+        // ---- every granule whose 18 slots are now in the ring: one warp per granule, lane = band
+        int g_hi = (t0 + ANA3_SLOTS) / 18;
+        if (g_hi > g_end) g_hi = g_end;
+        for (int G = g_next + warp; G < g_hi; G += ANA3_WARPS) {
+            int32_t *mf = S.mf[warp];
+            uint32_t *bins = S.bins[warp];
+            // ---- MDCT   (:683-701)
+            {
+                uint32_t acc[18], bad, any;
+                const int cur = (18 * G - t_begin) % ANA3_RING;
+                const int prev = G == 0 ? ANA3_RING : (18 * (G - 1) - t_begin) % ANA3_RING;
+                const Ana3LoadSb<ANA3_RING> ld{&S.sb[0][lane], prev, cur};
+                m3s_mdct_fold<GUARD>(ld, zero, acc, bad, any);
+                if (bad) {
+                    if (any == 0u) {
+#pragma unroll
+                        for (int q = 0; q < 18; q++) acc[q] = 0u;
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < 36; j++) {
+                            int r;
+                            if (j < 18) { r = prev + j; if (prev == ANA3_RING) r = ANA3_RING; else if (r >= ANA3_RING) r -= ANA3_RING; }
+                            else { r = cur + j - 18; if (r >= ANA3_RING) r -= ANA3_RING; }
+                            const uint32_t v = (uint32_t)S.sb[r][lane];
+                            if ((v & M3S_MDCT_FOLD_YMASK) != 0u) continue;
+#pragma unroll
+                            for (int q = 0; q < 18; q++) {
+                                const int32_t c = c_enc_cos[q][j];
+                                acc[q] += (uint32_t)(c < 0 && (uint32_t)c * v == 0u);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 18; q++) mf[lane * 18 + q] = (int32_t)acc[q];
+            }
+            __syncwarp();
+            // ---- alias butterflies between neighbouring bands, cmuls with >> 31   (:704-744, util.py:145-155)
+            for (int r = lane; r < 248; r += 32) {
+                const int band = 1 + (r >> 3), kk = r & 7;
+                const int64_t are = mf[band * 18 + kk], aim = mf[(band - 1) * 18 + 17 - kk];
+                const int64_t bre = S.cs[kk], bim = S.ca[kk];
+                mf[band * 18 + kk] = (int32_t)((are * bre - aim * bim) >> 31);
+                mf[(band - 1) * 18 + 17 - kk] = (int32_t)((are * bim + aim * bre) >> 31);
+            }
+            __syncwarp();
+            // ---- store + statistics: xrmax, en_tot, en[sfb]   (:772-776, :836-857)
+            const int frame = G >> 1, gr = G & 1;
+            const int64_t gslot = (((int64_t)(cl.frame_base + frame) - chunk_frame0) * 2 + ch) * 2 + gr;
+            uint32_t tot = 0u, mx = 0u;
+            for (int i = lane; i < 576; i += 32) {
+                const int32_t v = mf[i];
+                mdct[gslot * 576 + i] = v;
+                const uint32_t e = (uint32_t)(mulsr32(v, v) >> 10);
+                const int sfb = S.sfb[i];
+                if (sfb < 21 && e) atomicAdd(&bins[sfb], e);
+                tot += e;
+                mx = max(mx, v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v);
+            }
+            tot = __reduce_add_sync(0xFFFFFFFFu, tot);
+            mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+            __syncwarp();
+            if (lane < 22) {
+                const uint32_t temp = lane == 21 ? tot : bins[lane];
+                int en = 0;
+                if (temp) {
+                    en = -21;
+                    for (int j = 0; j < 31; j++) en += S.en_thresh[j] <= temp;
+                }
+                M3sEncStats *st = stats + gslot;
+                if (lane == 21) { st->en_tot = (int8_t)en; st->xrmax = (int32_t)mx; }
+                else st->en[lane] = (int8_t)en;
+            }
+            __syncwarp();
+            if (lane < 21) bins[lane] = 0u;
+            __syncwarp();
+        }
+        g_next = g_hi > g_next ? g_hi : g_next;
+    }
+}
+
+// ================================================================================================
 // E2: the probe machinery shared by every form of the rate loop, and its sequential form k_enc_rate_chain (one CTA per clip)
 // ================================================================================================
 #define RATE_WARPS 2       // warps per clip of the sequential form: warp w owns granule index gr = w of every frame (see k_enc_rate_chain)
@@ -1863,6 +2081,8 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
         if ((rc = m3s_buf_reserve(h, h->e_tabs, sizeof(EncTables)))) return rc;
         M3S_CUDA(h, cudaMemcpy(h->e_tabs.p, &E, sizeof E, cudaMemcpyHostToDevice));
         M3S_CUDA(h, cudaMemcpyToSymbol(c_enc_cos, ((const M3sDevTables *)hostT.data())->enc_cosl, sizeof(int32_t) * 18 * 36));
+        M3S_CUDA(h, cudaMemcpyToSymbol(c_enc_fl, ((const M3sDevTables *)hostT.data())->enc_fl, sizeof(int32_t) * 32 * 64));
+        M3S_CUDA(h, cudaMemcpyToSymbol(c_enc_win, ((const M3sDevTables *)hostT.data())->enwindow, sizeof(int32_t) * 512));
     }
     // ---- inputs.  Host buffers are streamed: the PCM of chunk k+1 crosses PCIe on `copy_in` while chunk k is in the
     //      kernels, and the MP3 bytes of chunk k-1 go back on `copy_out` (see the chunk loop below)
@@ -1928,6 +2148,20 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RateSmem)));
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    typedef void (*ana_fn_t)(const int16_t *, const M3sEncClip *, const M3sEncWork *, const M3sDevTables *, const EncTables *, int, int64_t,
+                             int32_t *, M3sEncStats *, uint32_t);
+    static const struct { ana_fn_t fn; int warps; size_t smem; int run; } kAnaFold[] = {   // M3S_ENC_FOLD_CFG picks another shape for experiments
+#define ANA_CFG(G, W) {k_enc_analysis_fold<G, W>, W, sizeof(Ana3Smem<W>), Ana3Smem<W>::RUN}
+        ANA_CFG(0, 8), ANA_CFG(0, 4), ANA_CFG(1, 8), ANA_CFG(0, 16)};
+#undef ANA_CFG
+    int ana_cfg = getenv("M3S_ENC_FOLD_CFG") ? atoi(getenv("M3S_ENC_FOLD_CFG")) : 0;
+    if (ana_cfg < 0 || ana_cfg >= (int)(sizeof kAnaFold / sizeof kAnaFold[0])) ana_cfg = 0;
+    const ana_fn_t ana_fold = kAnaFold[ana_cfg].fn;
+    M3S_CUDA(h, cudaFuncSetAttribute(ana_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnaFold[ana_cfg].smem));
+    M3S_CUDA(h, cudaFuncSetAttribute(ana_fold, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // M3S_ENC_ANALYSIS_DIRECT=1 selects the direct-form analysis kernel (every product on its own) as a cross-check of the folded one
+    const bool ana_direct = getenv("M3S_ENC_ANALYSIS_DIRECT") != nullptr;
+    const int64_t ana_run = ana_direct ? ENC_RUN : kAnaFold[ana_cfg].run;
     M3S_CUDA(h, cudaFuncSetAttribute(k_enc_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
     auto frames_in_chunk = [&](int i, int64_t c0) { return std::max<int64_t>(0, std::min<int64_t>(cf, clips[i].n_frames - c0)); };
     // host staging: per chunk every clip owns a region of cf * 1152 + 1056 stereo samples (1056 = the analysis history the
@@ -1952,9 +2186,9 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
             cc.frame_base = base - c0;
             // staged PCM: sample t of the clip sits at  region * i + t - (c0 * 1152 - 1056)  of this chunk's staging set
             if (host) cc.pcm_base = 2 * ((int64_t)i * region - (c0 * 1152 - 1056));
-            for (int64_t g = 2 * c0; g < 2 * (c0 + nfc); g += ENC_RUN) {
+            for (int64_t g = 2 * c0; g < 2 * (c0 + nfc); g += ana_run) {
                 M3sEncWork w;
-                w.clip = i; w.g_first = (int32_t)g; w.count = (int32_t)std::min<int64_t>(ENC_RUN, 2 * (c0 + nfc) - g);
+                w.clip = i; w.g_first = (int32_t)g; w.count = (int32_t)std::min<int64_t>(ana_run, 2 * (c0 + nfc) - g);
                 w.ch = 0; work.push_back(w);
                 w.ch = 1; work.push_back(w);
             }
@@ -2010,9 +2244,14 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
         if (k >= 2) M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_pack[pb], 0));
         M3sLaunchOn on_aux(h, h->aux);   // timing events of this launch go to the aux stream; restored on every return path
         M3S_KBEGIN(h, M3S_K_ENC_ANALYSIS);
-        k_enc_analysis<<<(unsigned)nw, ANA_THREADS, 0, h->aux>>>(
-            k_pcm, (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips, (const M3sEncWork *)h->e_work.p + work_off[k], h->d_tab,
-            (const EncTables *)h->e_tabs.p, sri, 0, (int32_t *)b_mdct[pb]->p, (M3sEncStats *)b_gran[pb]->p);
+        if (ana_direct)
+            k_enc_analysis<<<(unsigned)nw, ANA_THREADS, 0, h->aux>>>(
+                k_pcm, (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips, (const M3sEncWork *)h->e_work.p + work_off[k], h->d_tab,
+                (const EncTables *)h->e_tabs.p, sri, 0, (int32_t *)b_mdct[pb]->p, (M3sEncStats *)b_gran[pb]->p);
+        else
+            ana_fold<<<(unsigned)nw, 32 * kAnaFold[ana_cfg].warps, kAnaFold[ana_cfg].smem, h->aux>>>(
+                k_pcm, (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips, (const M3sEncWork *)h->e_work.p + work_off[k], h->d_tab,
+                (const EncTables *)h->e_tabs.p, sri, 0, (int32_t *)b_mdct[pb]->p, (M3sEncStats *)b_gran[pb]->p, 0u);
         M3S_LAUNCH_CHECK(h);
         M3S_CUDA(h, cudaEventRecord(h->ev_ana[pb], h->aux));
         if (host) {

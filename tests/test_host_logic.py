@@ -103,6 +103,20 @@ def test_fast_transforms_match_the_direct_formulas(tmp_path):
     assert "imdct36 via dct4_18" in out.stdout and "dct2_lee<32>" in out.stdout
 
 
+def test_enc_fold_generated_code(tmp_path):
+    """csrc/m3s_enc_fold_gen.cuh (the analysis kernel's matrixing / MDCT with equal truncated products computed once) is what
+    tools/gen_enc_fold.py makes of the committed tables, and -- compiled for the host -- equals the direct sums of individually
+    truncated products (MP3_Encoder.py:358-368, :683-701, util.py:121-127) whenever it does not ask for the direct redo."""
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_enc_fold.py"), "--check"]).returncode == 0
+    exe = str(tmp_path / "efc")
+    src = os.path.join(ROOT, "tests", "model", "enc_fold_check.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "errors 0" in out.stdout, out.stdout
+
+
 def test_host_affinity_helpers(tmp_path, monkeypatch):
     """hostaffinity: cpulist parsing, PCI bus-id normalisation, and the no-op on single-node hosts (the GPU pool's VMs)."""
     from mp3stego_b200 import hostaffinity as ha

@@ -39,7 +39,7 @@ def main():
         configs = [c for c in configs if any(c[0].startswith(a) for a in sys.argv[3:])] + adhoc
     ref = None
     for name, env in configs:
-        for k in ("M3S_PROBE_CTAS", "M3S_ENC_SERIAL", "M3S_ENC_OVERLAP", "M3S_ENC_CHAIN", "M3S_PROBE_CFG"):
+        for k in ("M3S_PROBE_CTAS", "M3S_ENC_SERIAL", "M3S_ENC_OVERLAP", "M3S_ENC_CHAIN", "M3S_PROBE_CFG", "M3S_ENC_ANALYSIS_DIRECT", "M3S_ENC_FOLD_CFG"):
             os.environ.pop(k, None)
         os.environ.update(env)
         out.zero_()
