@@ -17,6 +17,7 @@
 // double-precision fallback in quantize (:401-407) and the padding recurrence (:504-513, :630-632) done on the host.
 #include <math.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <vector>
@@ -304,10 +305,11 @@ template <int WARPS>   // warps per CTA = 32-slot groups per block
 struct Ana3Smem {
     static constexpr int SLOTS = 32 * WARPS;   // slots per block: one per thread
     static constexpr int XP = 15 + SLOTS;      // columns of the sample tile: 15 slots of history + the block's slots; odd: conflict-free fills
-    static constexpr int RING = SLOTS + 36;    // subband-sample ring: a granule reaches back 36 slots from its end, a block adds SLOTS more
+    static constexpr int RING = (SLOTS + 35 + 17) / 18 * 18;   // subband-sample ring: a granule reaches back 36 slots from its end, a block adds
+                                                               // SLOTS more; a multiple of 18, so that the rows of a granule never wrap
     static constexpr int RUN = SLOTS * 9 / 18 - 1;   // granules per CTA: with the warm-up granule 9 blocks exactly
     int32_t xT[32][XP];                // sample 32 u + r of this channel at [r][u - u0], as int16 << 16
-    int32_t sb[RING + 1][33];          // [ring row][band] subband samples; row RING stays zero (the state in front of a clip)
+    int32_t sb[RING + 18][33];         // [ring row][band] subband samples; rows RING.. stay zero (the granule in front of a clip)
     int32_t mf[WARPS][576];            // per warp: [band * 18 + k] MDCT lines of the granule it works on
     uint32_t bins[WARPS][24];          // per warp: 0..20 band energies, 21 total, 22 xrmax
     uint32_t en_thresh[32];
@@ -323,16 +325,9 @@ struct Ana3LoadX {   // sample k of input j of the windowing: x[32 t + 31 - j - 
         return j < 32 ? p[(31 - j) * ANA3_XP - 2 * k] : p[(63 - j) * ANA3_XP - 2 * k - 1];
     }
 };
-template <int ANA3_RING>
 struct Ana3LoadSb {  // input j of the MDCT: slot j of the previous granule (j < 18) or slot j - 18 of the current one, band = lane
-    const int32_t *sb; int prev, cur;   // ring rows of the two granules' first slots; prev = ANA3_RING: the zero row for every j
-    __device__ __forceinline__ int32_t operator()(int j) const
-    {
-        int r;
-        if (j < 18) { r = prev + j; if (prev == ANA3_RING) r = ANA3_RING; else if (r >= ANA3_RING) r -= ANA3_RING; }
-        else { r = cur + j - 18; if (r >= ANA3_RING) r -= ANA3_RING; }
-        return sb[r * 33];
-    }
+    const int32_t *prev, *cur;   // the two granules' first ring rows at this lane's band
+    __device__ __forceinline__ int32_t operator()(int j) const { return j < 18 ? prev[j * 33] : cur[(j - 18) * 33]; }
 };
 
 // GUARD: how shared products are protected from ptxas's multiply-add folding (m3s_enc_fold_gen.cuh); WARPS: warps per CTA
@@ -354,7 +349,7 @@ k_enc_analysis_fold(const int16_t *__restrict__ pcm, const M3sEncClip *__restric
     if (tid < 8) { S.ca[tid] = T->enc_ca[tid]; S.cs[tid] = T->enc_cs[tid]; }
     if (tid < 32) S.en_thresh[tid] = ET->en_thresh[tid];
     if (tid < 24 * ANA3_WARPS) (&S.bins[0][0])[tid] = 0u;
-    if (tid < 33) S.sb[ANA3_RING][tid] = 0;
+    for (int i = tid; i < 18 * 33; i += ANA3_THREADS) (&S.sb[ANA3_RING][0])[i] = 0;
 
     const uint32_t *pcm32 = (const uint32_t *)(pcm + cl.pcm_base);  // one stereo sample per word (pcm_base is even)
     const int sh = ch ? 0 : 16;                                     // channel 0 = low half of the word
@@ -369,14 +364,25 @@ k_enc_analysis_fold(const int16_t *__restrict__ pcm, const M3sEncClip *__restric
         // ---- sample tile: slots t0 - 15 .. t0 + ANA3_SLOTS - 1, transposed (row = sample within its slot, column = slot)
         {
             const int64_t n0 = ((int64_t)t0 - 15) * 32;
-#pragma unroll 4
-            for (int i = tid; i < 32 * ANA3_XP; i += ANA3_THREADS) {
+            constexpr int NLD = (32 * ANA3_XP + ANA3_THREADS - 1) / ANA3_THREADS;
+            uint32_t w[NLD];
+#pragma unroll
+            for (int q = 0; q < NLD; q++) {   // every load of the tile in flight at once: one DRAM latency per block, not one per batch
+                const int i = tid + ANA3_THREADS * q;
                 const int64_t n = n0 + i;
-                const uint32_t w = (n >= 0 && n < s_end) ? __ldg(pcm32 + n) : 0u;
-                S.xT[i & 31][i >> 5] = (int32_t)((w << sh) & 0xFFFF0000u);
+                w[q] = (i < 32 * ANA3_XP && n >= 0 && n < s_end) ? __ldg(pcm32 + n) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < NLD; q++) {
+                const int i = tid + ANA3_THREADS * q;
+                if (i < 32 * ANA3_XP) S.xT[i & 31][i >> 5] = (int32_t)((w[q] << sh) & 0xFFFF0000u);
             }
         }
         __syncthreads();   // also: every warp has left the MDCT phase of the previous block, the ring rows below are free
+        if (k + 1 < n_blocks) {   // the next block's new samples on their way into L2 while this block is in the arithmetic
+            const int64_t n = ((int64_t)t0 + ANA3_SLOTS) * 32 + 32 * tid;   // one 128-byte line per thread: 32 * SLOTS samples in all
+            if (n < s_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(pcm32 + n));
+        }
         // ---- windowing + matrixing of slot t0 + tid: y_j = sum_k mul(x[32 t + 31 - j - 64 k], enwindow[j + 64 k])   (:337-356),
         //      s_b = sum_j mul(fl[b][j], y_j); odd bands of odd slots negated   (:358-368, :678-679)
         if (t0 + 32 * warp < t_stop) {   // warp-uniform
@@ -418,9 +424,7 @@ k_enc_analysis_fold(const int16_t *__restrict__ pcm, const M3sEncClip *__restric
             // ---- MDCT   (:683-701)
             {
                 uint32_t acc[18], bad, any;
-                const int cur = (18 * G - t_begin) % ANA3_RING;
-                const int prev = G == 0 ? ANA3_RING : (18 * (G - 1) - t_begin) % ANA3_RING;
-                const Ana3LoadSb<ANA3_RING> ld{&S.sb[0][lane], prev, cur};
+                const Ana3LoadSb ld{&S.sb[G == 0 ? ANA3_RING : (18 * (G - 1) - t_begin) % ANA3_RING][lane], &S.sb[(18 * G - t_begin) % ANA3_RING][lane]};
                 m3s_mdct_fold<GUARD>(ld, zero, acc, bad, any);
                 if (bad) {
                     if (any == 0u) {
@@ -429,10 +433,7 @@ k_enc_analysis_fold(const int16_t *__restrict__ pcm, const M3sEncClip *__restric
                     } else {
 #pragma unroll 1
                         for (int j = 0; j < 36; j++) {
-                            int r;
-                            if (j < 18) { r = prev + j; if (prev == ANA3_RING) r = ANA3_RING; else if (r >= ANA3_RING) r -= ANA3_RING; }
-                            else { r = cur + j - 18; if (r >= ANA3_RING) r -= ANA3_RING; }
-                            const uint32_t v = (uint32_t)S.sb[r][lane];
+                            const uint32_t v = (uint32_t)(j < 18 ? ld.prev[j * 33] : ld.cur[(j - 18) * 33]);
                             if ((v & M3S_MDCT_FOLD_YMASK) != 0u) continue;
 #pragma unroll
                             for (int q = 0; q < 18; q++) {
@@ -1934,6 +1935,16 @@ k_enc_pack(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ fra
 // ================================================================================================
 // host orchestration
 // ================================================================================================
+// clip index of every chunk-local frame slot (what the per-granule / per-frame kernels of E2 / E3 map a slot back with), written on
+// the device: the host only sends one (first slot, count) pair per clip and chunk instead of one entry per frame
+__global__ void __launch_bounds__(128)
+k_enc_frame_clip(const int64_t *__restrict__ first, const int32_t *__restrict__ count, int n_clips, int32_t *__restrict__ frame_clip)
+{
+    const int64_t f0 = first[blockIdx.x];
+    const int n = count[blockIdx.x], clip = (int)(blockIdx.x % (unsigned)n_clips);
+    for (int q = threadIdx.x; q < n; q += 128) frame_clip[f0 + q] = clip;
+}
+
 static const int kBitrates[16] = {-1, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320, -1};
 
 static int sr_index_of(int sr) { return sr == 44100 ? 0 : sr == 48000 ? 1 : sr == 32000 ? 2 : -1; }
@@ -2027,12 +2038,22 @@ extern "C" int m3s_encode(m3s_handle_t h, const int16_t *pcm, int mem, const int
     return rc;
 }
 
+static const bool g_enc_trace = getenv("M3S_TRACE") != nullptr;   // host-clock stage timing of the encode call (diagnostic)
+static double enc_now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+#define M3S_ENC_MARK(tag) do { if (g_enc_trace) { const double t__ = enc_now_ms(); fprintf(stderr, "[m3s enc] %-22s +%.2f ms\n", tag, t__ - tr_t); tr_t = t__; } } while (0)
+
 static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_t *pcm_off, const int64_t *n_samples,
                        int32_t n_clips, int32_t sample_rate, int32_t bitrate_kbps, const uint8_t *payload_bits,
                        const int64_t *payload_off, uint8_t *mp3_out, const int64_t *mp3_off, const int64_t *mp3_cap,
                        int64_t *out_len, int64_t *hide_str_offset_out)
 {
     if (!h) return M3S_ERR_ARG;
+    double tr_t = g_enc_trace ? enc_now_ms() : 0.0;
     h->enc_taps_ok = false;
     if (!pcm || !n_samples || n_clips <= 0 || !mp3_out || !mp3_off) return m3s_fail(h, M3S_ERR_ARG, "encode: null argument");
     if ((uintptr_t)pcm & 3) return m3s_fail(h, M3S_ERR_ARG, "encode: pcm must be 4-byte aligned (one stereo sample per word)");
@@ -2072,6 +2093,7 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
         if (hide_str_offset_out) hide_str_offset_out[i] = 0;
     }
     if (total_frames == 0) return M3S_OK;
+    M3S_ENC_MARK("clip table");
     // ---- encoder constant tables (once per handle)
     if (!h->e_tabs.p) {
         std::vector<uint8_t> hostT(sizeof(M3sDevTables));
@@ -2169,10 +2191,43 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
     const int64_t region = cf * 1152 + 1056;
     const size_t stage_bytes = host ? (size_t)n_clips * (size_t)region * 4 : 0;
     if (host && (rc = m3s_buf_reserve(h, h->e_pcm, 2 * stage_bytes + 16))) return rc;
+    M3S_ENC_MARK("buffers");
+    std::vector<M3sRow> rows;
+    bool free_recorded[2] = {false, false};
+    struct ChunkEv { cudaEvent_t c0, c1, a0, a1, r1, p1, o1; };   // M3S_TRACE: copy in, analysis, rate loop, pack, copy out of every chunk
+    std::vector<ChunkEv> tev;
+    if (g_enc_trace) tev.assign((size_t)n_chunks, ChunkEv{});
+    auto tmark = [&](cudaEvent_t &e, cudaStream_t st) { if (g_enc_trace) { cudaEventCreate(&e); cudaEventRecord(e, st); } };
+    auto stage_chunk = [&](int64_t k) -> cudaError_t {   // H2D of the PCM that chunk k reads, into staging set k & 1
+        const int64_t c0 = k * cf;
+        const int pb = (int)(k & 1);
+        rows.clear();
+        for (int i = 0; i < n_clips; i++) {
+            const int64_t nfc = frames_in_chunk(i, c0);
+            if (nfc == 0) continue;
+            const int64_t first = c0 * 1152 - 1056, s0 = std::max<int64_t>(first, 0), s1 = (c0 + nfc) * 1152;
+            M3sRow r;
+            r.dst = (char *)h->e_pcm.p + (size_t)pb * stage_bytes + ((size_t)i * region + (size_t)(s0 - first)) * 4;
+            r.src = (const char *)pcm + clips[i].pcm_base * 2 + s0 * 4;
+            r.bytes = (size_t)(s1 - s0) * 4;
+            rows.push_back(r);
+        }
+        cudaError_t e = cudaSuccess;
+        if (free_recorded[pb]) e = cudaStreamWaitEvent(h->copy_in, h->ev_free[pb], 0);
+        if (g_enc_trace) tmark(tev[k].c0, h->copy_in);
+        if (e == cudaSuccess) e = m3s_copy_rows(rows, cudaMemcpyHostToDevice, h->copy_in);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[pb], h->copy_in);
+        if (g_enc_trace) tmark(tev[k].c1, h->copy_in);
+        return e;
+    };
+    // the first chunk's PCM starts crossing PCIe now, under the host work below (descriptors of every chunk); the descriptors' own
+    // upload queues behind it on the copy engine, so the second chunk is staged after them
+    if (host) M3S_CUDA(h, stage_chunk(0));
     // ---- descriptors of ALL chunks go up once, so that the chunk loop below issues no small copy (a pageable copy blocks the host
     //      until its stream gets there, which would serialise the streams of the pipeline)
     std::vector<M3sEncWork> work;          // E1 work items, chunk k = [work_off[k], work_off[k+1])
-    std::vector<int32_t> frame_clip;       // clip index of every chunk-local frame slot, chunk k = [slot_off[k], slot_off[k+1])
+    std::vector<int64_t> fc_first((size_t)n_clips * n_chunks);   // frame slots of clip i in chunk k: [fc_first, fc_first + fc_count) of the
+    std::vector<int32_t> fc_count((size_t)n_clips * n_chunks);   // frame_clip array, whose chunk k is [slot_off[k], slot_off[k+1])
     std::vector<M3sEncClip> cclips((size_t)n_clips * n_chunks);   // chunk-local clip records
     std::vector<int64_t> work_off(n_chunks + 1, 0), slot_off(n_chunks + 1, 0);
     for (int64_t k = 0; k < n_chunks; k++) {
@@ -2192,42 +2247,29 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
                 w.ch = 0; work.push_back(w);
                 w.ch = 1; work.push_back(w);
             }
-            for (int64_t q = 0; q < nfc; q++) frame_clip.push_back(i);
+            fc_first[(size_t)k * n_clips + i] = slot_off[k] + base;
+            fc_count[(size_t)k * n_clips + i] = (int32_t)nfc;
             base += nfc;
         }
         work_off[k + 1] = (int64_t)work.size();
-        slot_off[k + 1] = (int64_t)frame_clip.size();
+        slot_off[k + 1] = slot_off[k] + base;
     }
+    M3S_ENC_MARK("descriptors built");
     if ((rc = m3s_buf_reserve(h, h->e_work, sizeof(M3sEncWork) * work.size()))) return rc;
-    if ((rc = m3s_buf_reserve(h, h->e_misc, sizeof(int32_t) * frame_clip.size()))) return rc;
+    const size_t fc_bytes = ((size_t)slot_off[n_chunks] * sizeof(int32_t) + 15) / 16 * 16;   // frame_clip, then the (first, count) pairs
+    if ((rc = m3s_buf_reserve(h, h->e_misc, fc_bytes + fc_first.size() * 12))) return rc;
     if ((rc = m3s_buf_reserve(h, h->e_clips, sizeof(M3sEncClip) * cclips.size()))) return rc;
     M3S_CUDA(h, cudaMemcpyAsync(h->e_work.p, work.data(), sizeof(M3sEncWork) * work.size(), cudaMemcpyHostToDevice, h->stream));
-    M3S_CUDA(h, cudaMemcpyAsync(h->e_misc.p, frame_clip.data(), sizeof(int32_t) * frame_clip.size(), cudaMemcpyHostToDevice, h->stream));
+    M3S_CUDA(h, cudaMemcpyAsync((char *)h->e_misc.p + fc_bytes, fc_first.data(), fc_first.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    M3S_CUDA(h, cudaMemcpyAsync((char *)h->e_misc.p + fc_bytes + fc_first.size() * 8, fc_count.data(), fc_count.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    M3S_KBEGIN(h, M3S_K_ENC_AUX);
+    k_enc_frame_clip<<<(unsigned)fc_first.size(), 128, 0, h->stream>>>((const int64_t *)((char *)h->e_misc.p + fc_bytes),
+        (const int32_t *)((char *)h->e_misc.p + fc_bytes + fc_first.size() * 8), n_clips, (int32_t *)h->e_misc.p);
+    M3S_LAUNCH_CHECK(h);
     M3S_CUDA(h, cudaMemcpyAsync(h->e_clips.p, cclips.data(), sizeof(M3sEncClip) * cclips.size(), cudaMemcpyHostToDevice, h->stream));
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));   // everything uploaded so far (payload, padding table, state, descriptors) is visible to every stream
+    M3S_ENC_MARK("descriptors uploaded");
 
-    std::vector<M3sRow> rows;
-    bool free_recorded[2] = {false, false};
-    auto stage_chunk = [&](int64_t k) -> cudaError_t {   // H2D of the PCM that chunk k reads, into staging set k & 1
-        const int64_t c0 = k * cf;
-        const int pb = (int)(k & 1);
-        rows.clear();
-        for (int i = 0; i < n_clips; i++) {
-            const int64_t nfc = frames_in_chunk(i, c0);
-            if (nfc == 0) continue;
-            const int64_t first = c0 * 1152 - 1056, s0 = std::max<int64_t>(first, 0), s1 = (c0 + nfc) * 1152;
-            M3sRow r;
-            r.dst = (char *)h->e_pcm.p + (size_t)pb * stage_bytes + ((size_t)i * region + (size_t)(s0 - first)) * 4;
-            r.src = (const char *)pcm + clips[i].pcm_base * 2 + s0 * 4;
-            r.bytes = (size_t)(s1 - s0) * 4;
-            rows.push_back(r);
-        }
-        cudaError_t e = cudaSuccess;
-        if (free_recorded[pb]) e = cudaStreamWaitEvent(h->copy_in, h->ev_free[pb], 0);
-        if (e == cudaSuccess) e = m3s_copy_rows(rows, cudaMemcpyHostToDevice, h->copy_in);
-        if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[pb], h->copy_in);
-        return e;
-    };
     // E1 of chunk k on the aux stream; ev_ana[k & 1] = spectra + statistics of the chunk are ready
     auto launch_analysis = [&](int64_t k) -> int {
         const int pb = (int)(k & 1);
@@ -2243,6 +2285,7 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
         // then fills what is left instead of crowding the critical chain out
         if (k >= 2) M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_pack[pb], 0));
         M3sLaunchOn on_aux(h, h->aux);   // timing events of this launch go to the aux stream; restored on every return path
+        if (g_enc_trace) tmark(tev[k].a0, h->aux);
         M3S_KBEGIN(h, M3S_K_ENC_ANALYSIS);
         if (ana_direct)
             k_enc_analysis<<<(unsigned)nw, ANA_THREADS, 0, h->aux>>>(
@@ -2253,6 +2296,7 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
                 k_pcm, (const M3sEncClip *)h->e_clips.p + (size_t)k * n_clips, (const M3sEncWork *)h->e_work.p + work_off[k], h->d_tab,
                 (const EncTables *)h->e_tabs.p, sri, 0, (int32_t *)b_mdct[pb]->p, (M3sEncStats *)b_gran[pb]->p, 0u);
         M3S_LAUNCH_CHECK(h);
+        if (g_enc_trace) tmark(tev[k].a1, h->aux);
         M3S_CUDA(h, cudaEventRecord(h->ev_ana[pb], h->aux));
         if (host) {
             M3S_CUDA(h, cudaEventRecord(h->ev_free[pb], h->aux));   // the staging set may be refilled once the analysis has read it
@@ -2265,10 +2309,7 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
     //        aux       analysis of chunk k+1                  fills the issue slots the latency-bound rate loop leaves idle
     //        stream    rate loop + packing of chunk k         the critical path: back to back, chunk after chunk
     //        copy_out  MP3 bytes of chunk k                   (host buffers only)
-    if (host) {
-        M3S_CUDA(h, stage_chunk(0));
-        if (n_chunks > 1) M3S_CUDA(h, stage_chunk(1));
-    }
+    if (host && n_chunks > 1) M3S_CUDA(h, stage_chunk(1));
     if ((rc = launch_analysis(0))) return rc;
     for (int64_t k = 0; k < n_chunks; k++) {
         const int64_t c0 = k * cf;
@@ -2298,6 +2339,7 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
                 sri, whole, n_gran, (const int32_t *)b_mdct[pb]->p, (const M3sEncStats *)b_gran[pb]->p, (uint4 *)b_var[pb]->p,
                 (uint32_t *)b_sum[pb]->p, (uint8_t *)b_scfsi[pb]->p);
         M3S_LAUNCH_CHECK(h);
+        if (g_enc_trace) tmark(tev[k].r1, h->stream);
         M3S_CUDA(h, cudaEventRecord(h->ev_rate[pb], h->stream));
         // (overlapped order) queued behind the rate loop's CTAs on purpose: the next chunk's analysis takes what they leave free
         if (!serial && k + 1 < n_chunks && (rc = launch_analysis(k + 1))) return rc;
@@ -2324,6 +2366,7 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
             d_clips, (const int32_t *)h->e_misc.p + slot_off[k], h->d_tab, (const uint32_t *)h->e_pad.p, sri, bri, whole, 0,
             chunk_total, (const uint32_t *)b_ix[pb]->p, (const int32_t *)b_info[pb]->p, (const uint8_t *)b_scfsi[pb]->p, d_out);
         M3S_LAUNCH_CHECK(h);
+        if (g_enc_trace) tmark(tev[k].p1, h->stream);
         M3S_CUDA(h, cudaEventRecord(h->ev_pack[pb], h->stream));
         if (serial && k + 1 < n_chunks) {
             M3S_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_pack[pb], 0));
@@ -2344,12 +2387,25 @@ static int encode_impl(m3s_handle_t h, const int16_t *pcm, int mem, const int64_
                 rows.push_back(r);
             }
             M3S_CUDA(h, m3s_copy_rows(rows, cudaMemcpyDeviceToHost, h->copy_out));
+            if (g_enc_trace) tmark(tev[k].o1, h->copy_out);
         }
     }
+    M3S_ENC_MARK("chunks queued");
     M3S_CUDA(h, cudaStreamSynchronize(h->stream));
     M3S_CUDA(h, cudaStreamSynchronize(h->aux));
     M3S_CUDA(h, cudaStreamSynchronize(h->copy_out));
     if (host) M3S_CUDA(h, cudaStreamSynchronize(h->copy_in));
+    M3S_ENC_MARK("streams drained");
+    if (g_enc_trace && host) {   // timeline of the call, ms since the first copy was queued
+        auto at = [&](cudaEvent_t e) { float ms = -1.f; if (e) cudaEventElapsedTime(&ms, tev[0].c0, e); return ms; };
+        for (int64_t k = 0; k < n_chunks; k++) {
+            if (k < 6 || k >= n_chunks - 3)
+                fprintf(stderr, "[m3s enc] chunk %3lld  copy_in %7.2f..%7.2f  analysis %7.2f..%7.2f  rate ..%7.2f  pack ..%7.2f  copy_out ..%7.2f\n", (long long)k,
+                        at(tev[k].c0), at(tev[k].c1), at(tev[k].a0), at(tev[k].a1), at(tev[k].r1), at(tev[k].p1), at(tev[k].o1));
+        }
+        for (int64_t k = 0; k < n_chunks; k++)
+            for (cudaEvent_t e : {tev[k].c0, tev[k].c1, tev[k].a0, tev[k].a1, tev[k].r1, tev[k].p1, tev[k].o1}) if (e) cudaEventDestroy(e);
+    }
     // ---- results
     std::vector<M3sEncState> states(n_clips);
     M3S_CUDA(h, cudaMemcpyAsync(states.data(), h->e_state.p, sizeof(M3sEncState) * n_clips, cudaMemcpyDeviceToHost, h->stream));
