@@ -831,15 +831,16 @@ struct BitWindow {
     int have;            // valid bits in win
     int nextw;           // index of the word held in n1
     uint64_t win;
-    uint32_t n1, n2;     // words nextw and nextw + 1
-    __device__ __forceinline__ uint32_t load(int wi) const
+    uint32_t n1, n2;     // word nextw (ready to use) and word nextw + 1 AS LOADED: its byte swap and tail mask wait until it moves into
+                         // n1, one refill later -- done right behind the load they would stall on it, which is what the prefetch is there to avoid
+    __device__ __forceinline__ uint32_t load_raw(int wi) const { return wi * 32 < lim ? __ldg(w + wi) : 0u; }
+    __device__ __forceinline__ uint32_t fix(int wi, uint32_t raw) const   // big-endian word wi with the bits at or beyond lim cleared
     {
-        if (wi < (lim >> 5)) return __byte_perm(__ldg(w + wi), 0, 0x0123);
-        const int b = wi * 32;
-        if (b >= lim) return 0u;
-        const uint32_t v = __byte_perm(__ldg(w + wi), 0, 0x0123);
-        return v & ~(0xFFFFFFFFu >> (lim - b));
+        const uint32_t v = __byte_perm(raw, 0, 0x0123);
+        const int left = lim - wi * 32;                      // > 0 whenever raw was loaded; raw == 0 otherwise
+        return left < 32 ? v & ~(0xFFFFFFFFu >> (left > 0 ? left : 0)) : v;
     }
+    __device__ __forceinline__ uint32_t load(int wi) const { return fix(wi, load_raw(wi)); }
     __device__ __forceinline__ void init(const BitReader &r)   // continue where the scalefactor reader stopped
     {
         w = r.w; lim = r.lim; pos = r.pos;
@@ -848,7 +849,7 @@ struct BitWindow {
         have = 64 - sh;
         nextw = wi + 2;
         n1 = load(nextw);
-        n2 = load(nextw + 1);
+        n2 = load_raw(nextw + 1);
     }
     __device__ __forceinline__ uint32_t peek() const { return (uint32_t)(win >> 32); }
     __device__ __forceinline__ void consume(int n)   // n <= 32
@@ -860,8 +861,8 @@ struct BitWindow {
             win |= (uint64_t)n1 << (32 - have);
             have += 32;
             nextw++;
-            n1 = n2;
-            n2 = load(nextw + 1);
+            n1 = fix(nextw, n2);
+            n2 = load_raw(nextw + 1);
         }
     }
 };
