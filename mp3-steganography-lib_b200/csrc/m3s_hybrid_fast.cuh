@@ -61,6 +61,27 @@ __device__ __forceinline__ double hf_signed(double m, int x) { return x < 0 ? -m
 __device__ __forceinline__ int hf_to_int(float o) { return __float2int_rz(o); }
 __device__ __forceinline__ int hf_to_int(double o) { return __double2int_rz(o); }
 
+// Packed FP32 (Blackwell FFMA2, PTX fma.rn.f32x2): two independent round-to-nearest FMAs per instruction -- the same results as two
+// fmaf, half the issue slots.  The windowing's two accumulator chains per output sample (even / odd history rows) run as one.
+__device__ __forceinline__ uint64_t hf_pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t hf_fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float hf_sum2(uint64_t v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+
 // x[i] of the 36-point IMDCT from the 18 DCT-IV values (the index folds once the caller's loop is unrolled)
 template <typename R>
 __device__ __forceinline__ R hf_imdct_at(const R (&c)[18], int i)
@@ -405,15 +426,30 @@ k_hybrid_fast(const uint32_t *__restrict__ spec, const M3sUnitRec *__restrict__ 
                 for (int m = 0; m < 8; m++) { dA[m] = sm.wcoef[m][lane]; dB[m] = sm.wcoef[8 + m][lane]; }
 #pragma unroll
                 for (int d = 0; d < 16; d++) { a[d] = va[2 * HF_ROW * d]; b[d] = vb[2 * HF_ROW * d]; }
+                uint64_t ab2[16], d2[8];   // FP32: (a, b) and (dA, dB) as register pairs for FFMA2
+                if constexpr (sizeof(R) == 4) {
+#pragma unroll
+                    for (int m = 0; m < 8; m++) d2[m] = hf_pack2((float)dA[m], (float)dB[m]);
+#pragma unroll
+                    for (int d = 0; d < 16; d++) ab2[d] = hf_pack2((float)a[d], (float)b[d]);
+                }
 #pragma unroll
                 for (int q = 0; q < 9; q++) {
-                    R acc0 = (R)0, acc1 = (R)0;
+                    R o;
+                    if constexpr (sizeof(R) == 4) {
+                        uint64_t acc = 0ull;   // (+0.0f, +0.0f)
 #pragma unroll
-                    for (int m = 0; m < 8; m++) {
-                        acc0 = m3s_fma(a[q - m + 7], dA[m], acc0);
-                        acc1 = m3s_fma(b[q - m + 7], dB[m], acc1);
+                        for (int m = 0; m < 8; m++) acc = hf_fma2(ab2[q - m + 7], d2[m], acc);
+                        o = (R)hf_sum2(acc);
+                    } else {
+                        R acc0 = (R)0, acc1 = (R)0;
+#pragma unroll
+                        for (int m = 0; m < 8; m++) {
+                            acc0 = m3s_fma(a[q - m + 7], dA[m], acc0);
+                            acc1 = m3s_fma(b[q - m + 7], dB[m], acc1);
+                        }
+                        o = acc0 + acc1;
                     }
-                    const R o = acc0 + acc1;
                     OUT *so = &sm.stage[ch][gr * 576 + 32 * par + lane];
                     // (pcm * 32767).astype(int16): truncate, keep the low 16 bits (A.D8); FP32 carries the factor in its window coefficients
                     if (FLOAT_OUT) so[64 * q] = (OUT)o;
