@@ -179,6 +179,32 @@ def test_sequential_rate_loop_equals_parallel(built, oracle, monkeypatch):
             assert g["mp3"] == ref["mp3"] and g["hide_str_offset"] == ref["hide_str_offset"]
 
 
+@pytest.mark.parametrize("form", ["default", "direct", "cfg1", "cfg2", "cfg3"])
+def test_analysis_kernel_forms(built, oracle, monkeypatch, form):
+    """The analysis kernel ships in its folded form (equal truncated products computed once, k_enc_analysis_fold, 8 warps per CTA).
+    The direct form (M3S_ENC_ANALYSIS_DIRECT=1: every product on its own) and the other shapes of the folded one (M3S_ENC_FOLD_CFG:
+    4 / 16 warps per CTA, the xor guard) must give the oracle's MDCT lines, bytes and offsets too -- on clips long enough to span several
+    slot blocks and runs, with silence, a few-LSB stretch and clicks so that the folded form's correction pass runs
+    (MP3_Encoder.py:322-370, :652-758)."""
+    from mp3stego_b200 import _lib
+    if form == "direct":
+        monkeypatch.setenv("M3S_ENC_ANALYSIS_DIRECT", "1")
+    elif form != "default":
+        monkeypatch.setenv("M3S_ENC_FOLD_CFG", form[3:])
+    quiet = synth_wav(31, 40).copy()
+    quiet[1152 * 5:1152 * 9] = 0
+    quiet[1152 * 9:1152 * 12] = (quiet[1152 * 9:1152 * 12] >> 13).astype(np.int16)   # a few LSBs: windowed values with many zero low bits
+    clips = [synth_wav(30, 150), quiet, _clicks(11, 33 * 1152, 5), np.zeros((7 * 1152, 2), np.int16)]
+    bits = ["0110" * 900, "1" * 300, "10" * 200, ""]
+    h = _lib.Handle(0)
+    got = _encode(h, clips, 128, payloads=bits)
+    h.close()
+    for c, p, g in zip(clips, bits, got):
+        ref = oracle.encode(c, 44100, 128, p)
+        _check_taps(g, ref)
+        assert g["mp3"] == ref["mp3"] and g["hide_str_offset"] == ref["hide_str_offset"]
+
+
 def test_chunked_regular_batch_host_and_device(built, oracle):
     """Equal-length clips take the strided (2-D) PCIe staging path of the host pipeline; host and device buffers and the
     oracle must agree byte for byte across chunk boundaries."""
