@@ -649,16 +649,19 @@ __global__ void k_strip(const uint8_t *__restrict__ bytes, int64_t total_bytes, 
     const uint32_t *sw = (const uint32_t *)(sa - sh);
     // the aligned two-word read may touch up to 7 bytes past the last payload byte: keep it inside the batch buffer
     int64_t safe_words = (total_bytes - (src + head) - 8) >> 2;
-    for (int wi = lane; wi < nwords; wi += 32) {
-        uint32_t v;
-        if (wi < safe_words) {
-            uint32_t lo = __ldg(sw + wi), hi = __ldg(sw + wi + 1);
-            v = __funnelshift_r(lo, hi, 8 * sh);
-        } else {
-            const uint8_t *q = sp + 4 * wi;
-            v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-        }
-        dp[wi] = v;
+    const int nfast = (int)(safe_words < 0 ? 0 : (safe_words < nwords ? safe_words : nwords));   // words the two-word reads may serve
+    int wi = lane;
+    for (; wi + 96 < nfast; wi += 128) {   // four words per lane with all eight loads in flight: the kernel waits on DRAM latency, not on bandwidth
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { lo[q] = __ldg(sw + wi + 32 * q); hi[q] = __ldg(sw + wi + 32 * q + 1); }
+#pragma unroll
+        for (int q = 0; q < 4; q++) dp[wi + 32 * q] = __funnelshift_r(lo[q], hi[q], 8 * sh);
+    }
+    for (; wi < nfast; wi += 32) dp[wi] = __funnelshift_r(__ldg(sw + wi), __ldg(sw + wi + 1), 8 * sh);
+    for (int wt = nfast + lane; wt < nwords; wt += 32) {   // the last words of the batch buffer, byte by byte
+        const uint8_t *q = sp + 4 * wt;
+        dp[wt] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
     }
     int tail = n - head - 4 * nwords;
     if (lane < tail) S[dst + head + 4 * nwords + lane] = bytes[src + head + 4 * nwords + lane];
