@@ -1704,7 +1704,7 @@ k_enc_resolve(const M3sEncClip *__restrict__ clips, int n_clips, M3sEncState *__
 // non-silent granule of the slot, re-derived from that granule's spectra, or read from `last_in` when it lies in an earlier chunk.
 #define EMIT_WARPS 8
 #define EMIT_G 8
-__global__ void __launch_bounds__(32 * EMIT_WARPS)
+__global__ void __launch_bounds__(32 * EMIT_WARPS, 3)
 k_enc_emit(const M3sEncClip *__restrict__ clips, const int32_t *__restrict__ frame_clip, const M3sDevTables *__restrict__ T,
            const EncTables *__restrict__ ET, int sr_idx, int32_t chunk_first, int32_t chunk_frames, int64_t n_gran,
            const int32_t *__restrict__ mdct, const M3sEncStats *__restrict__ stats, const uint32_t *__restrict__ srcs,
