@@ -92,7 +92,7 @@ def random_payload_bits(n_files, bits_per_file, seed):
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -103,7 +103,9 @@ class ClockSampler:
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in the wall-clock window [t0, t1] (all samples when the window is not given, or when
+        nvidia-smi -- slow to start, more so with eight ranks spawning it at once -- delivered none inside it)."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -115,6 +117,19 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
+        if t0 is not None and t1 is not None:
+            import datetime
+            inside = []
+            for r in rows:
+                try:
+                    ts = datetime.datetime.strptime(r[7].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except (ValueError, IndexError):
+                    continue
+                if t0 - 0.05 <= ts <= t1 + 0.05:
+                    inside.append(r)
+            out["window"] = ("first device-resident timed step .. last e2e timed step" if inside
+                             else "whole leg incl. warm-up (no sample fell inside the timed regions)")
+            rows = inside or rows
         sm, power, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -497,19 +512,24 @@ def run_product_arm(args):
     ENC_K = ("k_enc_analysis", "k_enc_rate", "k_enc_resolve", "k_enc_emit", "k_enc_pack")
 
     def measure(dev_fn, host_fn, knames, bpf):
+        clocks = ClockSampler(local)   # started in front of the warm-up: nvidia-smi needs a few hundred ms before its first sample
         for _ in range(args.warmup):
             dev_fn()
         h.timing_enable(True)
         l0 = h.launches
-        clocks = ClockSampler(local)
+        t_w0 = time.time()
         n_dev, t_dev, wall = timed(dev_fn, args.steps)
-        clk = clocks.stop()
+        t_w1 = time.time()
         launches = h.launches - l0
         kt = h.timing()
         h.timing_enable(False)
         assert n_dev == total_frames * args.steps, (n_dev, total_frames)
         host_fn()
+        t_w2 = time.time()
         n_e2e, t_e2e, _ = timed(host_fn, args.steps)
+        t_w3 = time.time()
+        clk = clocks.stop(t_w0, t_w3)
+        clk["timed_windows_s"] = [round(t_w1 - t_w0, 3), round(t_w3 - t_w2, 3)]
         value = world * n_dev / t_dev
         roofl = roofline_of(kt, knames, n_dev, bpf, peak, peak_src, args.steps, value / world * bpf / 1e9 / peak)
         return dict(value=value, ms_per_step=1e3 * t_dev / args.steps, e2e_value=world * n_e2e / t_e2e,
