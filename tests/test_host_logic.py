@@ -117,6 +117,41 @@ def test_enc_fold_generated_code(tmp_path):
     assert out.returncode == 0 and "errors 0" in out.stdout, out.stdout
 
 
+def test_bench_clock_sampler_window(tmp_path):
+    """bench.ClockSampler.stop(t0, t1): only the nvidia-smi samples whose timestamps fall inside the timed window count; when none does
+    (a timed region shorter than the tool's start-up) every sample of the leg is used instead of reporting nothing; unparsable rows are
+    skipped; a throttle reason seen inside the window is reported."""
+    import datetime
+    import sys
+    import time
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+
+    class Done:
+        def terminate(self): pass
+        def wait(self, timeout=None): pass
+
+    def sampler(rows):
+        cs = bench.ClockSampler.__new__(bench.ClockSampler)
+        cs.f = open(tmp_path / "smi.csv", "w+")
+        cs.f.write("".join(rows))
+        cs.f.flush()
+        cs.p = Done()
+        return cs
+
+    now = time.time()
+    stamp = lambda dt: datetime.datetime.fromtimestamp(now + dt).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]   # noqa: E731
+    rows = ["%d, 1965, %.2f, Not Active, Not Active, Not Active, %s, %s\n" % (1500 if k < 3 else 1965, 150.0 + 60 * k, "Active" if k == 5 else "Not Active", stamp(0.1 * k))
+            for k in range(10)] + ["[N/A], garbage\n"]
+    out = sampler(rows).stop(now + 0.33, now + 0.72)    # +- 50 ms of slack: the samples at 0.3 .. 0.7 s
+    assert out["samples"] == 5 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    out = sampler(rows).stop(now + 5.0, now + 6.0)          # nothing inside: the whole leg, and the record says so
+    assert out["samples"] == 10 and "no sample" in out["window"] and out["sm_mhz"] == 1965.0
+    out = sampler([]).stop(now, now + 1.0)
+    assert out["sm_mhz"] is None and out["reasons"] == []
+
+
 def test_host_affinity_helpers(tmp_path, monkeypatch):
     """hostaffinity: cpulist parsing, PCI bus-id normalisation, and the no-op on single-node hosts (the GPU pool's VMs)."""
     from mp3stego_b200 import hostaffinity as ha
