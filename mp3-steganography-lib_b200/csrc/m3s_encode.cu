@@ -1,7 +1,9 @@
 // m3s_encode.cu -- encode half of the hot path (reference: mp3stego/encoder/MP3_Encoder.py, a port of Shine).
 //
-//   E1 k_enc_analysis  polyphase analysis + MDCT + alias butterflies, exact 32-bit fixed point; also the per-granule
+//   E1 k_enc_analysis_fold  polyphase analysis + MDCT + alias butterflies, exact 32-bit fixed point; also the per-granule
 //                      spectral statistics the rate loop and scfsi need (xrmax, en_tot, en[21]).           (:322-370, :652-758, :817-861)
+//                      The shipped form computes equal truncated products once (generated straight-line code, m3s_enc_fold_gen.cuh);
+//                      k_enc_analysis is the direct form, every product on its own, kept as a cross-check: M3S_ENC_ANALYSIS_DIRECT=1.
 //   E2 the per-granule quantisation / rate loop with table selection and the stego table swap (:760-1264), in three kernels:
 //      k_enc_probe    one warp per granule-channel and NO chain between granules: the reference's step search is walked for every
 //                     payload variant the granule can meet (the <= 3 payload bits at its hide_str_offset: 15 cases), the
@@ -78,8 +80,9 @@ __device__ __forceinline__ int32_t mulsr32(int32_t a, int32_t b)  // util.mulsr 
 }
 
 // ================================================================================================
-// E1: analysis filterbank + MDCT.  Every product is the reference's mul(a, b) = (a * b) >> 32 truncated on its own
-// (util.py:121-127), so no algebraic folding is exact and the work is 66,816 IMAD.HI per granule-channel; IMAD.HI issues
+// E1, direct form (cross-check; the folded form below ships): analysis filterbank + MDCT.  Every product is the reference's
+// mul(a, b) = (a * b) >> 32 truncated on its own (util.py:121-127), so no algebraic folding of the SUMS is exact and the work
+// is 66,816 IMAD.HI per granule-channel; IMAD.HI issues
 // at a quarter of the FP32 rate (tools/ubench_pipes.cu: 29 lanes/clk/SM), which is this kernel's roof.  The design keeps
 // everything else off that pipe's critical path by register tiling: both channels advance together (half the barriers),
 //   windowing   thread (ch, slot parity, i): 16 samples in registers feed 9 slots x 8 taps               (0.22 LDS / mul)
